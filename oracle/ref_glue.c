@@ -1,0 +1,358 @@
+/*
+ * ref_glue.c -- TEST INFRASTRUCTURE ONLY (see oracle_api.h).
+ *
+ * Glue that exposes the UNMODIFIED reference sources (compiled where they lie
+ * under /root/reference by oracle/Makefile, scalar build = SSE_INTRIN off,
+ * gcc -std=gnu11 -O2 -ffp-contract=off) through the oracle API.  Nothing here
+ * re-implements the search, the tree builder or the cameras: every such call
+ * lands in the reference's own object code.  What IS restated here, because
+ * the reference file cannot be compiled in this image (Blocks/GCD/SDL2/vn3d):
+ *   - the vox_render block loop, via render_loop.h (renderer.c:200-327);
+ * and what is new:
+ *   - breadth-first flattening of the reference's pointer tree, so the GPU
+ *     traversal can be tested on exactly the tree the reference built.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <omp.h>
+
+/* reference headers (need -DVOXVISION_BUILDING -DVOXTREES_SOURCE -DVOXRND_SOURCE) */
+#include "voxtrees/tree.h"
+#include "voxtrees/search.h"
+#include "voxtrees/geom.h"
+#include "voxrnd/camera.h"
+#include "voxrnd/modules.h"
+
+#include "oracle_api.h"
+#include "render_loop.h"
+
+#ifdef SSE_INTRIN
+#error "ref_glue.c is written for the scalar reference build (vox_dot = float[3])"
+#endif
+
+/* the two camera files are compiled with -Dmodule_init=<kind>_module_init */
+struct vox_module* simple_module_init (void);
+struct vox_module* doom_module_init (void);
+
+/* Layout mirrors of the private camera structs (simple-camera.c:10-17,
+ * doom-camera.c:8-15), used only to read the POD state out. */
+struct simple_camera_mirror
+{
+    struct vox_camera_interface *iface;
+    float xsub, ysub;
+    vox_dot position;
+    vox_quat rotation;
+    float mul, fov;
+};
+struct doom_camera_mirror
+{
+    struct vox_camera_interface *iface;
+    float xsub, ysub;
+    vox_dot position;
+    float phi, sinphi, cosphi, k;
+    float mul, fov;
+};
+
+struct id_pair { const struct vox_node *node; int32_t id; };
+
+struct orc_tree
+{
+    struct vox_node *root;
+    vox_dot *set;     /* the (reordered) input copy */
+    size_t n;
+    /* breadth-first order, built lazily */
+    const struct vox_node **bfs;
+    uint64_t *dots_off;
+    struct id_pair *ids;  /* sorted by pointer */
+    orc_tree_info info;
+    int indexed;
+};
+
+struct orc_camera
+{
+    int kind;
+    struct vox_camera *cam;
+};
+
+const char* orc_impl_name (void) { return "reference-scalar"; }
+
+void orc_set_voxel (float x, float y, float z) { vox_set_voxel_size (x, y, z); }
+void orc_get_voxel (float out[3]) { memcpy (out, vox_voxel, 3*sizeof(float)); }
+
+orc_tree* orc_tree_build (const float *xyz, size_t n)
+{
+    orc_tree *t = calloc (1, sizeof *t);
+    t->n = n;
+    t->set = malloc ((n ? n : 1) * sizeof (vox_dot));
+    memcpy (t->set, xyz, n * sizeof (vox_dot));
+    t->root = vox_make_tree (t->set, n);
+    return t;
+}
+
+orc_tree* orc_tree_build_by_insertion (const float *xyz, size_t n)
+{
+    orc_tree *t = calloc (1, sizeof *t);
+    t->n = n;
+    t->set = malloc ((n ? n : 1) * sizeof (vox_dot));
+    memcpy (t->set, xyz, n * sizeof (vox_dot));
+    for (size_t i=0; i<n; i++)
+    {
+        vox_dot d;
+        vox_dot_copy (d, t->set[i]);
+        vox_insert_voxel (&t->root, d);
+    }
+    return t;
+}
+
+void orc_tree_free (orc_tree *t)
+{
+    if (!t) return;
+    vox_destroy_tree (t->root);
+    free (t->set); free (t->bfs); free (t->dots_off); free (t->ids);
+    free (t);
+}
+
+void orc_tree_reordered_set (orc_tree *t, float *xyz)
+{
+    memcpy (xyz, t->set, t->n * sizeof (vox_dot));
+}
+
+static int cmp_id_pair (const void *a, const void *b)
+{
+    const struct id_pair *x = a, *y = b;
+    return (x->node > y->node) - (x->node < y->node);
+}
+
+static void count_nodes (const struct vox_node *node, uint32_t depth, orc_tree_info *info)
+{
+    if (!node) { info->n_null++; return; }
+    info->n_nodes++;
+    if (depth > info->depth) info->depth = depth;
+    if (node->flags & VOX_DENSE_LEAF) info->n_dense++;
+    else if (node->flags & VOX_LEAF)
+    {
+        info->n_leaf++;
+        if (node->flags & VOX_OVERFLOW) info->n_overflow++;
+        info->n_dots += node->dots_num;
+    }
+    else
+    {
+        info->n_inner++;
+        for (int i=0; i<VOX_NS; i++) count_nodes (node->data.inner.children[i], depth+1, info);
+    }
+}
+
+static void build_index (orc_tree *t)
+{
+    if (t->indexed) return;
+    memset (&t->info, 0, sizeof t->info);
+    if (t->root) count_nodes (t->root, 1, &t->info);
+    uint64_t n = t->info.n_nodes;
+    t->bfs = malloc ((n ? n : 1) * sizeof *t->bfs);
+    t->dots_off = malloc ((n ? n : 1) * sizeof *t->dots_off);
+    t->ids = malloc ((n ? n : 1) * sizeof *t->ids);
+    uint64_t head = 0, tail = 0, dots = 0;
+    if (t->root) t->bfs[tail++] = t->root;
+    while (head < tail)
+    {
+        const struct vox_node *node = t->bfs[head];
+        t->ids[head].node = node; t->ids[head].id = (int32_t)head;
+        t->dots_off[head] = dots;
+        if (node->flags & VOX_DENSE_LEAF) {}
+        else if (node->flags & VOX_LEAF) dots += node->dots_num;
+        else for (int i=0; i<VOX_NS; i++)
+        {
+            const struct vox_node *c = node->data.inner.children[i];
+            if (c) t->bfs[tail++] = c;
+        }
+        head++;
+    }
+    qsort (t->ids, n, sizeof *t->ids, cmp_id_pair);
+    t->indexed = 1;
+}
+
+static int32_t node_to_id (void *ctx, const void *node)
+{
+    orc_tree *t = ctx;
+    struct id_pair key = { node, 0 };
+    struct id_pair *p = bsearch (&key, t->ids, t->info.n_nodes, sizeof key, cmp_id_pair);
+    return p ? p->id : -2;
+}
+
+void orc_tree_info_get (orc_tree *t, orc_tree_info *info)
+{
+    build_index (t);
+    *info = t->info;
+}
+
+void orc_tree_flatten (orc_tree *t, orc_flat *out)
+{
+    build_index (t);
+    uint64_t n = t->info.n_nodes, next_child = 1;
+    for (uint64_t id=0; id<n; id++)
+    {
+        const struct vox_node *node = t->bfs[id];
+        memcpy (out->bb_min + 3*id, node->bounding_box.min, 3*sizeof(float));
+        memcpy (out->bb_max + 3*id, node->bounding_box.max, 3*sizeof(float));
+        out->flags[id] = node->flags;
+        out->dots_num[id] = node->dots_num;
+        out->center[3*id] = out->center[3*id+1] = out->center[3*id+2] = 0;
+        out->first_child[id] = 0;
+        out->child_mask[id] = 0;
+        out->dots_off[id] = t->dots_off[id];
+        if (node->flags & VOX_DENSE_LEAF) {}
+        else if (node->flags & VOX_LEAF)
+            memcpy (out->dots + 3*t->dots_off[id], node->data.dots, node->dots_num*sizeof(vox_dot));
+        else
+        {
+            memcpy (out->center + 3*id, node->data.inner.center, 3*sizeof(float));
+            out->first_child[id] = (uint32_t)next_child;
+            uint32_t mask = 0;
+            for (int i=0; i<VOX_NS; i++)
+                if (node->data.inner.children[i]) { mask |= 1u << i; next_child++; }
+            out->child_mask[id] = mask;
+        }
+    }
+}
+
+/* "Hit voxel" derived from (leaf, hit point): first dot of the leaf whose
+ * closed box [dot, dot+vox_voxel] contains the point. */
+static int64_t derive_dot (orc_tree *t, int32_t id, const float *p)
+{
+    const struct vox_node *node = t->bfs[id];
+    if (node->flags & VOX_DENSE_LEAF) return -1;
+    for (unsigned i=0; i<node->dots_num; i++)
+    {
+        const float *d = node->data.dots[i];
+        int in = 1;
+        for (int k=0; k<3; k++)
+        {
+            float mx = d[k] + vox_voxel[k];
+            if (p[k] < d[k] || p[k] > mx) in = 0;
+        }
+        if (in) return (int64_t)(t->dots_off[id] + i);
+    }
+    return -2;
+}
+
+void orc_ray_batch (orc_tree *t, uint32_t start_node,
+                    const float *origins, const float *dirs, size_t n,
+                    int32_t *leaf_id, float *hit, int64_t *dot_idx,
+                    orc_stats *stats, int threads)
+{
+    build_index (t);
+    if (stats) memset (stats, 0, sizeof *stats);
+    const struct vox_node *start = t->root ? t->bfs[start_node] : NULL;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (size_t i=0; i<n; i++)
+    {
+        vox_dot o, d, res;
+        memcpy (o, origins + 3*i, sizeof o);
+        memcpy (d, dirs + 3*i, sizeof d);
+        const struct vox_node *leaf = vox_ray_tree_intersection (start, o, d, res);
+        int32_t id = leaf ? node_to_id (t, leaf) : -1;
+        if (leaf_id) leaf_id[i] = id;
+        if (leaf && hit) memcpy (hit + 3*i, res, sizeof res);
+        if (dot_idx) dot_idx[i] = leaf ? derive_dot (t, id, res) : -1;
+    }
+}
+
+void orc_ball_batch (orc_tree *t, const float *centers, const float *radii,
+                     size_t n, uint8_t *out, int threads)
+{
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (size_t i=0; i<n; i++)
+    {
+        vox_dot c;
+        memcpy (c, centers + 3*i, sizeof c);
+        out[i] = (uint8_t) vox_tree_ball_collidep (t->root, c, radii[i]);
+    }
+}
+
+/* ---- cameras: calls go through the reference vtable ---- */
+
+orc_camera* orc_camera_new (int kind)
+{
+    struct vox_module *m = (kind == ORC_CAMERA_DOOM) ? doom_module_init () : simple_module_init ();
+    struct vox_camera_interface *iface = (struct vox_camera_interface*) m->methods;
+    orc_camera *c = calloc (1, sizeof *c);
+    c->kind = kind;
+    c->cam = iface->construct_camera (NULL);
+    return c;
+}
+
+void orc_camera_free (orc_camera *c)
+{
+    if (!c) return;
+    c->cam->iface->destroy_camera (c->cam);
+    free (c);
+}
+
+void orc_camera_set_position (orc_camera *c, const float p[3])
+{ vox_dot d; memcpy (d, p, sizeof d); c->cam->iface->set_property_dot (c->cam, "position", d); }
+void orc_camera_set_fov (orc_camera *c, float fov)
+{ c->cam->iface->set_property_number (c->cam, "fov", fov); }
+void orc_camera_set_rotation (orc_camera *c, const float a[3])
+{ vox_dot d; memcpy (d, a, sizeof d); c->cam->iface->set_property_dot (c->cam, "rotation", d); }
+void orc_camera_look_at (orc_camera *c, const float p[3])
+{ vox_dot d; memcpy (d, p, sizeof d); c->cam->iface->look_at (c->cam, d); }
+void orc_camera_rotate (orc_camera *c, const float delta[3])
+{ vox_dot d; memcpy (d, delta, sizeof d); c->cam->iface->rotate_camera (c->cam, d); }
+void orc_camera_move (orc_camera *c, const float delta[3])
+{ vox_dot d; memcpy (d, delta, sizeof d); c->cam->iface->move_camera (c->cam, d); }
+void orc_camera_set_window_size (orc_camera *c, int w, int h)
+{ c->cam->iface->set_window_size (c->cam, w, h); }
+void orc_camera_get_position (orc_camera *c, float p[3])
+{ vox_dot d; c->cam->iface->get_position (c->cam, d); memcpy (p, d, sizeof d); }
+void orc_camera_screen2world (orc_camera *c, float dir[3], int sx, int sy)
+{ vox_dot d; c->cam->iface->screen2world (c->cam, d, sx, sy); memcpy (dir, d, sizeof d); }
+
+void orc_camera_get_state (orc_camera *c, float s[11])
+{
+    memset (s, 0, 11*sizeof(float));
+    if (c->kind == ORC_CAMERA_DOOM)
+    {
+        const struct doom_camera_mirror *m = (const void*) c->cam;
+        memcpy (s, m->position, 3*sizeof(float));
+        s[3] = m->sinphi; s[4] = m->cosphi; s[5] = m->k; s[6] = m->phi;
+        s[7] = m->mul; s[8] = m->xsub; s[9] = m->ysub; s[10] = m->fov;
+    }
+    else
+    {
+        const struct simple_camera_mirror *m = (const void*) c->cam;
+        memcpy (s, m->position, 3*sizeof(float));
+        memcpy (s+3, m->rotation, 4*sizeof(float));
+        s[7] = m->mul; s[8] = m->xsub; s[9] = m->ysub; s[10] = m->fov;
+    }
+}
+
+/* ---- render: restated block loop, reference search + camera underneath ---- */
+
+static const void* hook_ray (const void *node, const float *o, const float *d, float *res)
+{ return vox_ray_tree_intersection (node, o, d, res); }
+static void hook_s2w (void *cam, float *dir, int sx, int sy)
+{ struct vox_camera *c = cam; c->iface->screen2world (c, dir, sx, sy); }
+static void hook_pos (void *cam, float *pos)
+{ struct vox_camera *c = cam; c->iface->get_position (c, pos); }
+static float hook_sqr_metric (const float *a, const float *b) { return vox_sqr_metric (a, b); }
+static float hook_sqr_norm (const float *a) { return vox_sqr_norm (a); }
+
+int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
+                const uint8_t *texture, const orc_pixfmt *fmt,
+                uint32_t *pixels, int32_t *leaf_id, float *hit, int threads)
+{
+    build_index (t);
+    orc_render_hooks hk = {
+        .scene = t->root, .camera = c->cam,
+        .ray = hook_ray, .screen2world = hook_s2w, .get_position = hook_pos,
+        .sqr_metric = hook_sqr_metric, .sqr_norm = hook_sqr_norm,
+        .node_id = leaf_id ? node_to_id : NULL, .idctx = t,
+    };
+    memcpy (hk.voxel, vox_voxel, sizeof hk.voxel);
+    return orc_render_loop (&hk, w, h, quality, texture, fmt, pixels, leaf_id, hit, threads);
+}
