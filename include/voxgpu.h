@@ -1,0 +1,186 @@
+/**
+   @file voxgpu.h
+   @brief The thin C-ABI layer between the host C libraries and the CUDA
+   kernels (libvoxgpu.so).  Plain pointers and sizes only.
+
+   This is the drop-in boundary for the device side of the hot path:
+     - voxgpu_tree_upload       <- the pointer tree built by vox_make_tree
+                                   (reference: src/voxtrees/tree.c:249-338, node
+                                   layout tree.h:22-38), flattened
+     - voxgpu_rays_*            <- vox_ray_tree_intersection, src/voxtrees/search.c:8-153
+     - voxgpu_balls_*           <- vox_tree_ball_collidep,    src/voxtrees/search.c:155-183
+     - voxgpu_render            <- the vox_render block loop,  src/voxrnd/renderer.c:200-319
+                                   with screen2world (simple-camera.c:21-31,
+                                   doom-camera.c:36-57), get_color (renderer.c:27-52)
+                                   and the de-tiling of vox_redraw (copy-helper.c:5-40)
+                                   folded into one kernel.
+   libvoxtrees / libvoxrnd call it; bench.py and multi-GPU drivers may call it
+   directly with device buffers and their own streams.
+
+   Every function returns 0 on success and a negative value on failure unless
+   stated otherwise; voxgpu_last_error() then describes the failure.  There is
+   no CPU fallback anywhere behind this interface.
+**/
+#ifndef VOXGPU_H
+#define VOXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOXGPU_EXPORT __attribute__((visibility ("default")))
+
+typedef struct voxgpu_tree voxgpu_tree;
+typedef void* voxgpu_stream;   /* a cudaStream_t, or NULL for the default stream */
+
+/* Node flags as in the reference (tree.h:15-18). */
+#define VOXGPU_LEAF       1u
+#define VOXGPU_DENSE_LEAF 2u
+
+/** Host view of a flattened tree: breadth-first, the non-NULL children of an
+    inner node consecutive in subspace order. Points are packed float[3]. */
+typedef struct
+{
+    uint64_t n_nodes, n_dots;
+    uint32_t depth;
+    const float    *bb_min;      /* 3*n_nodes */
+    const float    *bb_max;      /* 3*n_nodes */
+    const uint32_t *flags;       /* n_nodes */
+    const uint32_t *dots_num;    /* n_nodes */
+    const float    *center;      /* 3*n_nodes */
+    const uint32_t *first_child; /* n_nodes */
+    const uint32_t *child_mask;  /* n_nodes */
+    const uint64_t *dots_off;    /* n_nodes */
+    const float    *dots;        /* 3*n_dots */
+    float voxel[3];              /* vox_voxel at build time */
+} voxgpu_flat;
+
+/** Camera for device-side ray generation (see vox_camera_desc in voxrnd/camera.h). */
+#define VOXGPU_CAMERA_SIMPLE 0
+#define VOXGPU_CAMERA_DOOM   1
+#define VOXGPU_CAMERA_TABLE  2   /* directions come from a device buffer */
+typedef struct
+{
+    int kind;
+    float position[3];
+    float mul, xsub, ysub;
+    float rotation[4];
+    float sinphi, cosphi, k;
+    const float *dir_table;      /* TABLE: device pointer, float4 per pixel, w*h entries */
+} voxgpu_camera;
+
+/** What SDL_MapRGB needs from a 32-bpp pixel format. */
+typedef struct
+{
+    uint32_t amask;
+    uint8_t rloss, gloss, bloss, pad0;
+    uint8_t rshift, gshift, bshift, pad1;
+} voxgpu_pixfmt;
+
+/** One render request: rows [y0, y1) of a w x h frame. */
+typedef struct
+{
+    int w, h;
+    int y0, y1;
+    int pitch_pixels;            /* distance between rows of `pixels`, in pixels */
+    unsigned quality;            /* VOX_QUALITY_* bits, renderer.h:81-127 */
+    voxgpu_pixfmt fmt;
+} voxgpu_frame;
+
+/** Counters of the instrumented ("stats") variant of the ray kernel. */
+typedef struct
+{
+    unsigned long long rays, hits;
+    unsigned long long calls;        /* node records fetched (non-NULL calls) */
+    unsigned long long inner, leaf, dense;
+    unsigned long long dots_tested;
+    unsigned long long expansions;   /* inner nodes whose dividing planes were evaluated */
+    unsigned long long max_stack;
+} voxgpu_stats;
+
+/* ---- device management ---- */
+VOXGPU_EXPORT const char* voxgpu_last_error (void);
+VOXGPU_EXPORT int  voxgpu_device_count (void);            /* 0 if none / no driver */
+VOXGPU_EXPORT int  voxgpu_set_device (int device);
+VOXGPU_EXPORT int  voxgpu_get_device (void);
+VOXGPU_EXPORT int  voxgpu_sm_count (void);
+VOXGPU_EXPORT int  voxgpu_synchronize (voxgpu_stream stream);
+
+/* ---- memory helpers (so host C never needs cuda_runtime.h) ---- */
+VOXGPU_EXPORT void* voxgpu_malloc (size_t bytes);                 /* device */
+VOXGPU_EXPORT void  voxgpu_free (void *dptr);
+VOXGPU_EXPORT void* voxgpu_host_alloc (size_t bytes);             /* pinned + mapped */
+VOXGPU_EXPORT void  voxgpu_host_free (void *hptr);
+VOXGPU_EXPORT int   voxgpu_host_register (void *hptr, size_t bytes);
+VOXGPU_EXPORT int   voxgpu_host_unregister (void *hptr);
+VOXGPU_EXPORT void* voxgpu_host_device_pointer (void *hptr);      /* device alias of mapped host memory */
+VOXGPU_EXPORT int   voxgpu_memcpy_h2d (void *dptr, const void *hptr, size_t bytes, voxgpu_stream s);
+VOXGPU_EXPORT int   voxgpu_memcpy_d2h (void *hptr, const void *dptr, size_t bytes, voxgpu_stream s);
+VOXGPU_EXPORT int   voxgpu_memset (void *dptr, int value, size_t bytes, voxgpu_stream s);
+VOXGPU_EXPORT voxgpu_stream voxgpu_stream_create (void);
+VOXGPU_EXPORT void  voxgpu_stream_destroy (voxgpu_stream s);
+
+/* ---- tree ---- */
+/** Convert to the device layout and upload (cudaMemcpyAsync from pinned staging) on the current device. */
+VOXGPU_EXPORT voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *flat);
+VOXGPU_EXPORT void voxgpu_tree_free (voxgpu_tree *tree);
+VOXGPU_EXPORT size_t voxgpu_tree_device_bytes (const voxgpu_tree *tree);
+VOXGPU_EXPORT int voxgpu_tree_device (const voxgpu_tree *tree);
+
+/* ---- batched ray queries (K2) ----
+ * origins/dirs: float4 per ray (xyz + unused lane = vox_dot).
+ * leaf_ids: int32 per ray (-1 = miss); points: float4 per ray (written on a hit);
+ * voxels: int32 per ray (index into the flat dots, -1 = dense leaf or miss).
+ * Any output may be NULL. */
+VOXGPU_EXPORT int voxgpu_rays_device (const voxgpu_tree *tree, uint32_t start_node,
+                                      const float *d_origins, const float *d_dirs, size_t n,
+                                      int32_t *d_leaf_ids, float *d_points, int32_t *d_voxels,
+                                      voxgpu_stream stream);
+/** Host buffers: copies in, runs, copies out, synchronises. n_hits may be NULL. */
+VOXGPU_EXPORT int voxgpu_rays_host (const voxgpu_tree *tree, uint32_t start_node,
+                                    const float *origins, const float *dirs, size_t n,
+                                    int32_t *leaf_ids, float *points, int32_t *voxels,
+                                    long *n_hits);
+/** Instrumented variant (device buffers, synchronous): same results + counters. */
+VOXGPU_EXPORT int voxgpu_rays_stats (const voxgpu_tree *tree, uint32_t start_node,
+                                     const float *d_origins, const float *d_dirs, size_t n,
+                                     int32_t *d_leaf_ids, float *d_points, int32_t *d_voxels,
+                                     voxgpu_stats *stats);
+
+/* ---- batched ball queries (K3) ---- centers: float4 per ball; out: 1 byte per ball. */
+VOXGPU_EXPORT int voxgpu_balls_device (const voxgpu_tree *tree, const float *d_centers,
+                                       const float *d_radii, size_t n, uint8_t *d_out,
+                                       voxgpu_stream stream);
+VOXGPU_EXPORT int voxgpu_balls_host (const voxgpu_tree *tree, const float *centers,
+                                     const float *radii, size_t n, uint8_t *out, long *n_hits);
+
+/* ---- primary-ray render (K1) ----
+ * d_texture: 32*32*32 bytes on the device; d_pixels: device-accessible pointer
+ * (device memory, or the device alias of mapped pinned host memory) to pixel
+ * (0, y0) -- i.e. the first row of the requested band.  Every pixel of the
+ * band is written (0 where nothing is hit).  d_leaf_ids / d_points (optional,
+ * same indexing as pixels but dense w-pitch, int32 / float4 per pixel) expose the
+ * per-pixel search result for parity tests. */
+VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *camera,
+                                 const voxgpu_frame *frame, const uint8_t *d_texture,
+                                 uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
+                                 voxgpu_stream stream);
+
+/** Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+VOXGPU_EXPORT unsigned long long voxgpu_launch_count (void);
+
+/** CUDA-event timing helpers: elapsed milliseconds between two marks on a stream. */
+typedef struct voxgpu_timer voxgpu_timer;
+VOXGPU_EXPORT voxgpu_timer* voxgpu_timer_create (void);
+VOXGPU_EXPORT void  voxgpu_timer_destroy (voxgpu_timer *t);
+VOXGPU_EXPORT int   voxgpu_timer_start (voxgpu_timer *t, voxgpu_stream s);
+VOXGPU_EXPORT int   voxgpu_timer_stop (voxgpu_timer *t, voxgpu_stream s);
+VOXGPU_EXPORT float voxgpu_timer_elapsed_ms (voxgpu_timer *t);   /* synchronises on the stop mark */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,554 @@
+/*
+ * voxgpu.cu -- CUDA kernels (sm_100a) and the thin C-ABI of include/voxgpu.h.
+ *
+ *   K1 k_render : camera ray generation (simple-camera.c:21-31 / doom-camera.c:36-57)
+ *                 + first-hit octree search (search.c:8-153) + get_color
+ *                 (renderer.c:27-52) + linear framebuffer store, one thread per
+ *                 pixel, one warp per 8x4 pixel tile.  Replaces the 4x4-block
+ *                 dispatch_apply loop of renderer.c:214-318 and copy_squares
+ *                 (copy-helper.c:5-40).
+ *   K2 k_rays   : the same search for an array of independent rays.
+ *   K3 k_balls  : vox_tree_ball_collidep (search.c:155-183) for an array of balls.
+ *
+ * Compile with -fmad=false (see traverse.cuh for why).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "voxgpu.h"
+#include "traverse.cuh"
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail (const char *fmt, ...)
+{
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (g_err, sizeof g_err, fmt, ap);
+    va_end (ap);
+    return -1;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail ("%s failed: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); } while (0)
+#define CU_NULL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fail ("%s failed: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); return NULL; } } while (0)
+
+extern "C" const char* voxgpu_last_error (void) { return g_err; }
+extern "C" unsigned long long voxgpu_launch_count (void) { return g_launches.load (); }
+
+/* ------------------------------------------------------------------ device */
+
+extern "C" int voxgpu_device_count (void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount (&n);
+    if (e != cudaSuccess) { fail ("cudaGetDeviceCount: %s", cudaGetErrorString (e)); return 0; }
+    return n;
+}
+extern "C" int voxgpu_set_device (int device) { CU (cudaSetDevice (device)); return 0; }
+extern "C" int voxgpu_get_device (void) { int d = -1; if (cudaGetDevice (&d) != cudaSuccess) return -1; return d; }
+extern "C" int voxgpu_sm_count (void)
+{
+    int d = 0, n = 0;
+    CU (cudaGetDevice (&d));
+    CU (cudaDeviceGetAttribute (&n, cudaDevAttrMultiProcessorCount, d));
+    return n;
+}
+extern "C" int voxgpu_synchronize (voxgpu_stream s)
+{
+    if (s) CU (cudaStreamSynchronize ((cudaStream_t) s));
+    else CU (cudaDeviceSynchronize ());
+    return 0;
+}
+
+extern "C" void* voxgpu_malloc (size_t bytes)
+{
+    void *p = NULL;
+    CU_NULL (cudaMalloc (&p, bytes ? bytes : 16));
+    return p;
+}
+extern "C" void voxgpu_free (void *p) { if (p) cudaFree (p); }
+extern "C" void* voxgpu_host_alloc (size_t bytes)
+{
+    void *p = NULL;
+    CU_NULL (cudaHostAlloc (&p, bytes ? bytes : 16, cudaHostAllocMapped | cudaHostAllocPortable));
+    return p;
+}
+extern "C" void voxgpu_host_free (void *p) { if (p) cudaFreeHost (p); }
+extern "C" int voxgpu_host_register (void *p, size_t bytes)
+{
+    CU (cudaHostRegister (p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int voxgpu_host_unregister (void *p) { CU (cudaHostUnregister (p)); return 0; }
+extern "C" void* voxgpu_host_device_pointer (void *p)
+{
+    void *d = NULL;
+    CU_NULL (cudaHostGetDevicePointer (&d, p, 0));
+    return d;
+}
+extern "C" int voxgpu_memcpy_h2d (void *d, const void *h, size_t n, voxgpu_stream s)
+{ CU (cudaMemcpyAsync (d, h, n, cudaMemcpyHostToDevice, (cudaStream_t) s)); return 0; }
+extern "C" int voxgpu_memcpy_d2h (void *h, const void *d, size_t n, voxgpu_stream s)
+{ CU (cudaMemcpyAsync (h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t) s)); return 0; }
+extern "C" int voxgpu_memset (void *d, int v, size_t n, voxgpu_stream s)
+{ CU (cudaMemsetAsync (d, v, n, (cudaStream_t) s)); return 0; }
+extern "C" voxgpu_stream voxgpu_stream_create (void)
+{
+    cudaStream_t s = NULL;
+    CU_NULL (cudaStreamCreateWithFlags (&s, cudaStreamNonBlocking));
+    return (voxgpu_stream) s;
+}
+extern "C" void voxgpu_stream_destroy (voxgpu_stream s) { if (s) cudaStreamDestroy ((cudaStream_t) s); }
+
+/* ------------------------------------------------------------------- timer */
+
+struct voxgpu_timer { cudaEvent_t a, b; };
+extern "C" voxgpu_timer* voxgpu_timer_create (void)
+{
+    voxgpu_timer *t = (voxgpu_timer*) calloc (1, sizeof *t);
+    if (cudaEventCreate (&t->a) != cudaSuccess || cudaEventCreate (&t->b) != cudaSuccess)
+    { fail ("cudaEventCreate failed"); free (t); return NULL; }
+    return t;
+}
+extern "C" void voxgpu_timer_destroy (voxgpu_timer *t)
+{ if (!t) return; cudaEventDestroy (t->a); cudaEventDestroy (t->b); free (t); }
+extern "C" int voxgpu_timer_start (voxgpu_timer *t, voxgpu_stream s) { CU (cudaEventRecord (t->a, (cudaStream_t) s)); return 0; }
+extern "C" int voxgpu_timer_stop (voxgpu_timer *t, voxgpu_stream s) { CU (cudaEventRecord (t->b, (cudaStream_t) s)); return 0; }
+extern "C" float voxgpu_timer_elapsed_ms (voxgpu_timer *t)
+{
+    float ms = -1.0f;
+    if (cudaEventSynchronize (t->b) != cudaSuccess) { fail ("cudaEventSynchronize failed"); return -1.0f; }
+    if (cudaEventElapsedTime (&ms, t->a, t->b) != cudaSuccess) { fail ("cudaEventElapsedTime failed"); return -1.0f; }
+    return ms;
+}
+
+/* -------------------------------------------------------------------- tree */
+
+struct voxgpu_tree
+{
+    int device;
+    uint64_t n_nodes, n_dots;
+    uint32_t depth;
+    float4 *nodes;   /* 3 per node */
+    float4 *dots;
+    float voxel[3];
+};
+
+extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
+{
+    if (!f || f->n_nodes == 0) { fail ("voxgpu_tree_upload: empty tree"); return NULL; }
+    if (f->n_nodes >= 0x7fffffffull || f->n_dots >= 0x7fffffffull)
+    { fail ("voxgpu_tree_upload: tree too large for 31-bit ids (%llu nodes, %llu dots)",
+            (unsigned long long) f->n_nodes, (unsigned long long) f->n_dots); return NULL; }
+    if (f->depth > VOXGPU_MAX_DEPTH)
+    { fail ("voxgpu_tree_upload: tree depth %u exceeds the device stack (%d levels)", f->depth, VOXGPU_MAX_DEPTH); return NULL; }
+
+    voxgpu_tree *t = (voxgpu_tree*) calloc (1, sizeof *t);
+    t->n_nodes = f->n_nodes; t->n_dots = f->n_dots; t->depth = f->depth;
+    memcpy (t->voxel, f->voxel, sizeof t->voxel);
+    if (cudaGetDevice (&t->device) != cudaSuccess) { fail ("no CUDA device: %s", cudaGetErrorString (cudaGetLastError ())); free (t); return NULL; }
+
+    const size_t node_bytes = (size_t) f->n_nodes * 3 * sizeof (float4);
+    const size_t dot_bytes = (size_t) (f->n_dots ? f->n_dots : 1) * sizeof (float4);
+    float4 *stage = NULL;
+    cudaStream_t s = NULL;
+    cudaError_t e;
+    if ((e = cudaMalloc (&t->nodes, node_bytes)) != cudaSuccess ||
+        (e = cudaMalloc (&t->dots, dot_bytes)) != cudaSuccess ||
+        (e = cudaHostAlloc (&stage, node_bytes > dot_bytes ? node_bytes : dot_bytes, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags (&s, cudaStreamNonBlocking)) != cudaSuccess)
+    {
+        fail ("voxgpu_tree_upload: %s", cudaGetErrorString (e));
+        goto bad;
+    }
+
+    /* device records, written straight into the pinned staging buffer */
+    for (uint64_t id=0; id<f->n_nodes; id++)
+    {
+        const uint32_t fl = f->flags[id];
+        uint32_t meta, link;
+        if (fl & VOXGPU_DENSE_LEAF) { meta = VOXGPU_KIND_DENSE; link = 0; }
+        else if (fl & VOXGPU_LEAF)
+        {
+            if (f->dots_num[id] >= (1u << 30)) { fail ("leaf with %u dots", f->dots_num[id]); goto bad; }
+            meta = VOXGPU_KIND_LEAF | (f->dots_num[id] << 2);
+            link = (uint32_t) f->dots_off[id];
+        }
+        else { meta = VOXGPU_KIND_INNER | ((f->child_mask[id] & 0xffu) << 8); link = f->first_child[id]; }
+        float4 q0, q1, q2;
+        q0.x = f->bb_min[3*id]; q0.y = f->bb_min[3*id+1]; q0.z = f->bb_min[3*id+2];
+        memcpy (&q0.w, &meta, 4);
+        q1.x = f->bb_max[3*id]; q1.y = f->bb_max[3*id+1]; q1.z = f->bb_max[3*id+2];
+        memcpy (&q1.w, &link, 4);
+        q2.x = f->center[3*id]; q2.y = f->center[3*id+1]; q2.z = f->center[3*id+2]; q2.w = 0;
+        stage[3*id] = q0; stage[3*id+1] = q1; stage[3*id+2] = q2;
+    }
+    if ((e = cudaMemcpyAsync (t->nodes, stage, node_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaStreamSynchronize (s)) != cudaSuccess)
+    { fail ("voxgpu_tree_upload: node copy: %s", cudaGetErrorString (e)); goto bad; }
+    for (uint64_t i=0; i<f->n_dots; i++)
+    {
+        float4 q; q.x = f->dots[3*i]; q.y = f->dots[3*i+1]; q.z = f->dots[3*i+2]; q.w = 0;
+        stage[i] = q;
+    }
+    if (f->n_dots &&
+        ((e = cudaMemcpyAsync (t->dots, stage, f->n_dots * sizeof (float4), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+         (e = cudaStreamSynchronize (s)) != cudaSuccess))
+    { fail ("voxgpu_tree_upload: dots copy: %s", cudaGetErrorString (e)); goto bad; }
+    cudaFreeHost (stage);
+    cudaStreamDestroy (s);
+    return t;
+bad:
+    if (stage) cudaFreeHost (stage);
+    if (s) cudaStreamDestroy (s);
+    cudaFree (t->nodes); cudaFree (t->dots);
+    free (t);
+    return NULL;
+}
+
+extern "C" void voxgpu_tree_free (voxgpu_tree *t)
+{
+    if (!t) return;
+    int cur = -1;
+    cudaGetDevice (&cur);
+    if (cur != t->device) cudaSetDevice (t->device);
+    cudaFree (t->nodes); cudaFree (t->dots);
+    if (cur != t->device && cur >= 0) cudaSetDevice (cur);
+    free (t);
+}
+extern "C" size_t voxgpu_tree_device_bytes (const voxgpu_tree *t)
+{ return t ? (size_t) t->n_nodes * 48 + (size_t) t->n_dots * 16 : 0; }
+extern "C" int voxgpu_tree_device (const voxgpu_tree *t) { return t ? t->device : -1; }
+
+static TreeRef tree_ref (const voxgpu_tree *t)
+{
+    TreeRef r;
+    r.nodes = t->nodes; r.dots = t->dots;
+    r.vx = t->voxel[0]; r.vy = t->voxel[1]; r.vz = t->voxel[2];
+    return r;
+}
+
+static int check_tree (const voxgpu_tree *t, uint32_t start_node, const char *who)
+{
+    if (!t) return fail ("%s: NULL device tree", who);
+    if (start_node >= t->n_nodes) return fail ("%s: start node %u out of range", who, start_node);
+    int cur = -1;
+    CU (cudaGetDevice (&cur));
+    if (cur != t->device) return fail ("%s: tree lives on device %d, current device is %d", who, t->device, cur);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- K2: rays */
+
+#define RAYS_BLOCK 128
+
+template <bool STATS>
+__global__ void __launch_bounds__(RAYS_BLOCK)
+k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const float4 * __restrict__ dirs,
+        size_t n, int * __restrict__ leaf_ids, float4 * __restrict__ points, int * __restrict__ voxels,
+        unsigned long long *stats)
+{
+    const size_t i = (size_t) blockIdx.x * RAYS_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    float4 stack[VOXGPU_RAY_STACK];
+    const float4 o = __ldg (origins + i), d = __ldg (dirs + i);
+    RayResult r;
+    RayCounters c = {0, 0, 0, 0, 0, 0, 0};
+    ray_tree<STATS> (tr, start, v3 (o), v3 (d), stack, r, &c);
+    if (leaf_ids) leaf_ids[i] = r.leaf;
+    if (voxels) voxels[i] = r.voxel;
+    if (points && r.leaf >= 0) points[i] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+    if (STATS)
+    {
+        atomicAdd (stats + 0, 1ull);
+        atomicAdd (stats + 1, r.leaf >= 0 ? 1ull : 0ull);
+        atomicAdd (stats + 2, (unsigned long long) c.calls);
+        atomicAdd (stats + 3, (unsigned long long) c.inner);
+        atomicAdd (stats + 4, (unsigned long long) c.leaf);
+        atomicAdd (stats + 5, (unsigned long long) c.dense);
+        atomicAdd (stats + 6, (unsigned long long) c.dots);
+        atomicAdd (stats + 7, (unsigned long long) c.expansions);
+        atomicMax (stats + 8, (unsigned long long) c.max_stack);
+    }
+}
+
+extern "C" int voxgpu_rays_device (const voxgpu_tree *t, uint32_t start, const float *d_o, const float *d_d,
+                                   size_t n, int32_t *d_leaf, float *d_pts, int32_t *d_vox, voxgpu_stream s)
+{
+    if (check_tree (t, start, "voxgpu_rays_device")) return -1;
+    if (n == 0) return 0;
+    const size_t blocks = (n + RAYS_BLOCK - 1) / RAYS_BLOCK;
+    if (blocks > 0x7fffffffull) return fail ("voxgpu_rays_device: too many rays");
+    k_rays<false><<<(unsigned) blocks, RAYS_BLOCK, 0, (cudaStream_t) s>>> (
+        tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, NULL);
+    g_launches++;
+    CU (cudaGetLastError ());
+    return 0;
+}
+
+extern "C" int voxgpu_rays_stats (const voxgpu_tree *t, uint32_t start, const float *d_o, const float *d_d,
+                                  size_t n, int32_t *d_leaf, float *d_pts, int32_t *d_vox, voxgpu_stats *out)
+{
+    if (check_tree (t, start, "voxgpu_rays_stats")) return -1;
+    unsigned long long *d_st = NULL, h[9];
+    CU (cudaMalloc (&d_st, sizeof h));
+    CU (cudaMemset (d_st, 0, sizeof h));
+    if (n)
+    {
+        const size_t blocks = (n + RAYS_BLOCK - 1) / RAYS_BLOCK;
+        k_rays<true><<<(unsigned) blocks, RAYS_BLOCK>>> (
+            tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, d_st);
+        g_launches++;
+    }
+    cudaError_t e = cudaMemcpy (h, d_st, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree (d_st);
+    if (e != cudaSuccess) return fail ("voxgpu_rays_stats: %s", cudaGetErrorString (e));
+    out->rays = h[0]; out->hits = h[1]; out->calls = h[2]; out->inner = h[3]; out->leaf = h[4];
+    out->dense = h[5]; out->dots_tested = h[6]; out->expansions = h[7]; out->max_stack = h[8];
+    return 0;
+}
+
+extern "C" int voxgpu_rays_host (const voxgpu_tree *t, uint32_t start, const float *o, const float *d, size_t n,
+                                 int32_t *leaf, float *pts, int32_t *vox, long *n_hits)
+{
+    if (check_tree (t, start, "voxgpu_rays_host")) return -1;
+    if (n_hits) *n_hits = 0;
+    if (n == 0) return 0;
+    float4 *d_o = NULL, *d_d = NULL, *d_p = NULL;
+    int *d_l = NULL, *d_v = NULL;
+    int rc = -1;
+    cudaError_t e = cudaSuccess;
+    int32_t *tmp_leaf = NULL;
+    if ((e = cudaMalloc (&d_o, n * sizeof (float4))) != cudaSuccess) goto done;
+    if ((e = cudaMalloc (&d_d, n * sizeof (float4))) != cudaSuccess) goto done;
+    if ((e = cudaMalloc (&d_l, n * sizeof (int))) != cudaSuccess) goto done;
+    if (pts && (e = cudaMalloc (&d_p, n * sizeof (float4))) != cudaSuccess) goto done;
+    if (vox && (e = cudaMalloc (&d_v, n * sizeof (int))) != cudaSuccess) goto done;
+    if ((e = cudaMemcpy (d_o, o, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
+    if ((e = cudaMemcpy (d_d, d, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
+    /* points are only written on a hit: start from the caller's contents */
+    if (pts && (e = cudaMemcpy (d_p, pts, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
+    if (voxgpu_rays_device (t, start, (float*) d_o, (float*) d_d, n, d_l, (float*) d_p, d_v, NULL)) goto cleanup;
+    if (!leaf && n_hits) leaf = tmp_leaf = (int32_t*) malloc (n * sizeof (int32_t));
+    if (leaf && (e = cudaMemcpy (leaf, d_l, n * sizeof (int), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
+    if (pts && (e = cudaMemcpy (pts, d_p, n * sizeof (float4), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
+    if (vox && (e = cudaMemcpy (vox, d_v, n * sizeof (int), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
+    if ((e = cudaDeviceSynchronize ()) != cudaSuccess) goto done;
+    if (n_hits && leaf) { long h = 0; for (size_t i=0; i<n; i++) h += leaf[i] >= 0; *n_hits = h; }
+    rc = 0;
+done:
+    if (e != cudaSuccess) fail ("voxgpu_rays_host: %s", cudaGetErrorString (e));
+cleanup:
+    free (tmp_leaf);
+    cudaFree (d_o); cudaFree (d_d); cudaFree (d_p); cudaFree (d_l); cudaFree (d_v);
+    return rc;
+}
+
+/* --------------------------------------------------------------- K3: balls */
+
+#define BALLS_BLOCK 128
+
+__global__ void __launch_bounds__(BALLS_BLOCK)
+k_balls (TreeRef tr, const float4 * __restrict__ centers, const float * __restrict__ radii, size_t n,
+         unsigned char * __restrict__ out)
+{
+    const size_t i = (size_t) blockIdx.x * BALLS_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    unsigned stack[VOXGPU_BALL_STACK];
+    const float4 c = __ldg (centers + i);
+    out[i] = ball_tree (tr, 0, v3 (c), __ldg (radii + i), stack) ? 1 : 0;
+}
+
+extern "C" int voxgpu_balls_device (const voxgpu_tree *t, const float *d_c, const float *d_r, size_t n,
+                                    uint8_t *d_out, voxgpu_stream s)
+{
+    if (check_tree (t, 0, "voxgpu_balls_device")) return -1;
+    if (n == 0) return 0;
+    const size_t blocks = (n + BALLS_BLOCK - 1) / BALLS_BLOCK;
+    if (blocks > 0x7fffffffull) return fail ("voxgpu_balls_device: too many balls");
+    k_balls<<<(unsigned) blocks, BALLS_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), (const float4*) d_c, d_r, n, d_out);
+    g_launches++;
+    CU (cudaGetLastError ());
+    return 0;
+}
+
+extern "C" int voxgpu_balls_host (const voxgpu_tree *t, const float *c, const float *r, size_t n,
+                                  uint8_t *out, long *n_hits)
+{
+    if (check_tree (t, 0, "voxgpu_balls_host")) return -1;
+    if (n_hits) *n_hits = 0;
+    if (n == 0) return 0;
+    float4 *d_c = NULL; float *d_r = NULL; unsigned char *d_o = NULL;
+    int rc = -1;
+    cudaError_t e;
+    if ((e = cudaMalloc (&d_c, n * sizeof (float4))) != cudaSuccess) goto done;
+    if ((e = cudaMalloc (&d_r, n * sizeof (float))) != cudaSuccess) goto done;
+    if ((e = cudaMalloc (&d_o, n)) != cudaSuccess) goto done;
+    if ((e = cudaMemcpy (d_c, c, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
+    if ((e = cudaMemcpy (d_r, r, n * sizeof (float), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
+    if (voxgpu_balls_device (t, (float*) d_c, d_r, n, d_o, NULL)) { e = cudaSuccess; goto cleanup; }
+    if ((e = cudaMemcpy (out, d_o, n, cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
+    if ((e = cudaDeviceSynchronize ()) != cudaSuccess) goto done;
+    if (n_hits) { long h = 0; for (size_t i=0; i<n; i++) h += out[i] != 0; *n_hits = h; }
+    rc = 0;
+done:
+    if (e != cudaSuccess) fail ("voxgpu_balls_host: %s", cudaGetErrorString (e));
+cleanup:
+    cudaFree (d_c); cudaFree (d_r); cudaFree (d_o);
+    return rc;
+}
+
+/* -------------------------------------------------------------- K1: render */
+
+#define RENDER_BLOCK 128
+
+struct DevCamera
+{
+    int kind;
+    float px, py, pz;
+    float mul, xsub, ysub;
+    float qw, qi, qj, qk;
+    float sinphi, cosphi, k;
+    const float4 *table;
+};
+
+struct DevFrame
+{
+    int w, y0, rows, pitch;
+    unsigned amask;
+    unsigned char rloss, gloss, bloss, rshift, gshift, bshift;
+};
+
+/* vect-ops.c:8-16 vox_cross_product */
+__device__ __forceinline__ V3 cross3 (const V3 a, const V3 b)
+{
+    V3 r;
+    r.x = __fsub_rn (__fmul_rn (a.y, b.z), __fmul_rn (a.z, b.y));
+    r.y = __fadd_rn (__fmul_rn (-a.x, b.z), __fmul_rn (a.z, b.x));
+    r.z = __fsub_rn (__fmul_rn (a.x, b.y), __fmul_rn (a.y, b.x));
+    return r;
+}
+
+/* simple-camera.c:21-31 + vect-ops.c:28-36, doom-camera.c:24-57 */
+__device__ __forceinline__ V3 screen2world (const DevCamera &cam, int sx, int sy, int w)
+{
+    V3 dir;
+    if (cam.kind == VOXGPU_CAMERA_TABLE)
+    {
+        const float4 t = __ldg (cam.table + (size_t) sy * w + sx);
+        dir.x = t.x; dir.y = t.y; dir.z = t.z;
+        return dir;
+    }
+    V3 ray;
+    ray.x = __fsub_rn (__fmul_rn (cam.mul, (float) sx), cam.xsub);
+    ray.y = 1.0f;
+    ray.z = __fsub_rn (cam.ysub, __fmul_rn (cam.mul, (float) sy));
+    if (cam.kind == VOXGPU_CAMERA_DOOM)
+    {
+        ray.z = __fadd_rn (ray.z, cam.k);
+        dir.x = __fsub_rn (__fmul_rn (ray.x, cam.cosphi), __fmul_rn (ray.y, cam.sinphi));
+        dir.y = __fadd_rn (__fmul_rn (ray.y, cam.cosphi), __fmul_rn (ray.x, cam.sinphi));
+        dir.z = ray.z;
+        return dir;
+    }
+    V3 q; q.x = cam.qi; q.y = cam.qj; q.z = cam.qk;
+    V3 t = cross3 (q, ray);
+    t.x = __fmul_rn (t.x, 2.0f); t.y = __fmul_rn (t.y, 2.0f); t.z = __fmul_rn (t.z, 2.0f);
+    const V3 t2 = cross3 (q, t);
+    dir.x = __fadd_rn (__fadd_rn (ray.x, __fmul_rn (cam.qw, t.x)), t2.x);
+    dir.y = __fadd_rn (__fadd_rn (ray.y, __fmul_rn (cam.qw, t.y)), t2.y);
+    dir.z = __fadd_rn (__fadd_rn (ray.z, __fmul_rn (cam.qw, t.z)), t2.z);
+    return dir;
+}
+
+/* renderer.c:27-41 get_color (no light manager) + SDL_MapRGB */
+__device__ __forceinline__ unsigned shade (const TreeRef &tr, const DevFrame &fr, const unsigned char *tex, const V3 p)
+{
+    const int x = abs (__float2int_rz (__fdiv_rn (p.x, tr.vx))) & 31;
+    const int y = abs (__float2int_rz (__fdiv_rn (p.y, tr.vy))) & 31;
+    const int z = abs (__float2int_rz (__fdiv_rn (p.z, tr.vz))) & 31;
+    const unsigned c = __ldg (tex + (x*1024 + y*32 + z));
+    return ((c >> fr.rloss) << fr.rshift) | ((c >> fr.gloss) << fr.gshift) | ((c >> fr.bloss) << fr.bshift) | fr.amask;
+}
+
+/*
+ * One warp renders an 8x4 pixel tile (coherent rays, 32-byte row segments on
+ * the store); a block of 4 warps covers a 16x8 tile pair.  Every pixel of the
+ * band is written, 0 on a miss: that is vox_redraw's memset of the squares
+ * (renderer.c:324) folded into the store.
+ */
+template <bool OUT_HITS>
+__global__ void __launch_bounds__(RENDER_BLOCK)
+k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
+          unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points)
+{
+    const int tiles_x = fr.w >> 3;
+    const int ntiles = tiles_x * (fr.rows >> 2);
+    const int tile = blockIdx.x * (RENDER_BLOCK/32) + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const int lane = threadIdx.x & 31;
+    const int sx = (tile % tiles_x) * 8 + (lane & 7);
+    const int ry = (tile / tiles_x) * 4 + (lane >> 3);   /* row inside the band */
+    const int sy = fr.y0 + ry;
+
+    float4 stack[VOXGPU_RAY_STACK];
+    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
+    const V3 dir = screen2world (cam, sx, sy, fr.w);
+    RayResult r;
+    ray_tree<false> (tr, 0, origin, dir, stack, r, NULL);
+
+    unsigned color = 0;
+    if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+    pixels[(size_t) ry * fr.pitch + sx] = color;
+    if (OUT_HITS)
+    {
+        const size_t pos = (size_t) ry * fr.w + sx;
+        if (leaf_ids) leaf_ids[pos] = r.leaf;
+        if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+    }
+}
+
+extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                              const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                              voxgpu_stream s)
+{
+    if (check_tree (t, 0, "voxgpu_render")) return -1;
+    if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
+    if ((f->w & 0xf) || (f->h & 0x3) || f->w <= 0 || f->h <= 0)
+        return fail ("voxgpu_render: bad geometry %dx%d (renderer.c:97-100)", f->w, f->h);
+    if (f->y0 < 0 || f->y1 > f->h || f->y0 >= f->y1 || (f->y0 & 3) || (f->y1 & 3))
+        return fail ("voxgpu_render: bad row band [%d,%d)", f->y0, f->y1);
+    if (c->kind == VOXGPU_CAMERA_TABLE && !c->dir_table) return fail ("voxgpu_render: TABLE camera without table");
+
+    DevCamera dc;
+    dc.kind = c->kind;
+    dc.px = c->position[0]; dc.py = c->position[1]; dc.pz = c->position[2];
+    dc.mul = c->mul; dc.xsub = c->xsub; dc.ysub = c->ysub;
+    dc.qw = c->rotation[0]; dc.qi = c->rotation[1]; dc.qj = c->rotation[2]; dc.qk = c->rotation[3];
+    dc.sinphi = c->sinphi; dc.cosphi = c->cosphi; dc.k = c->k;
+    dc.table = (const float4*) c->dir_table;
+    DevFrame df;
+    df.w = f->w; df.y0 = f->y0; df.rows = f->y1 - f->y0; df.pitch = f->pitch_pixels;
+    df.amask = f->fmt.amask;
+    df.rloss = f->fmt.rloss; df.gloss = f->fmt.gloss; df.bloss = f->fmt.bloss;
+    df.rshift = f->fmt.rshift; df.gshift = f->fmt.gshift; df.bshift = f->fmt.bshift;
+
+    const int ntiles = (df.w >> 3) * (df.rows >> 2);
+    const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
+    if (d_leaf || d_pts)
+        k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
+    else
+        k_render<false><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL);
+    g_launches++;
+    CU (cudaGetLastError ());
+    return 0;
+}
