@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of primary-ray rendering, skull 1920x1080 along the
+scripted 360-frame orbit (BASELINE.json configs[1], SURVEY.md 8d "C2").
+
+    python bench.py --gpus N --steps K --warmup W            this repository's CUDA path
+    python bench.py --impl reference --gpus N ...            the reference's CPU path (rank 0 only)
+
+A step = one pass over the 360-frame camera path (360 kernel launches, one
+frame = 2 073 600 primary rays).  Prints ONE JSON line (rank 0).
+
+  value      device-timed throughput: frames land in HBM, CUDA events on the
+             launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e        the same frames through the reference-facing API (vox_render +
+             vox_redraw) into a HOST surface: per frame the camera goes host->device
+             and the 8.3 MB frame device->host (straight from the kernel's stores
+             into the pinned, mapped surface).
+  roofline   for the dominant kernel k_render: algorithmic bytes per launch
+             (node/dot records the reference's recursion touches, counted by the
+             instrumented oracle on sampled frames, + 4 B per pixel) / mean launch time,
+             against the measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's own C code (oracle/_ref, else the C restatement)
+             rendering sampled frames on all host cores of this box.
+
+N > 1: one process per GPU (torchrun), tree replicated, every rank renders its
+own 360 frames (rank r's orbit is shifted by r/N of a frame step, so all N*360
+frames differ) and the finished frames are gathered to GPU 0 with NCCL in
+batches on a side stream while the next batch renders.  Weak scaling.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+FRAMES = 360
+FOV = 1.2
+RAYS_PER_FRAME = W * H
+# device layout record sizes (voxvision_b200/csrc/gpu/traverse.cuh): what one visit must read
+BYTES_INNER, BYTES_LEAF, BYTES_DENSE, BYTES_DOT, BYTES_PIXEL = 48, 32, 32, 16, 4
+METRIC = "Mrays/s primary-ray render (skull 1080p)"
+GATHER_BATCH = 8          # frames per NCCL gather
+RING = 2 * GATHER_BATCH   # device framebuffers per rank
+
+
+def rank_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons, sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def frame_pose(ds, frame, rank, world):
+    return ds.orbit_pose(frame + rank / world, FRAMES)
+
+
+# ---------------------------------------------------------------- reference arm
+
+def pick_cpu_oracle(orc):
+    for which, kind in (("ref_sse", "reference"), ("ref_fast", "reference"), ("ref", "reference"), ("port", "port")):
+        if orc.available(which):
+            try:
+                return orc.Oracle(which), kind
+            except OSError:
+                continue
+    orc.build("port")
+    return orc.Oracle("port"), "port"
+
+
+def cpu_render_rate(ds, O, sample_frames, repeats, threads, quality=0):
+    """Mrays/s of the CPU path on `sample_frames`, best of `repeats` passes."""
+    tree = O.tree(ds.volume_voxels("skull"))
+    cams = [ds.setup_camera(O.camera(0), *ds.orbit_pose(f, FRAMES), FOV, W, H) for f in sample_frames]
+    tree.render(cams[0], W, H, quality, threads=threads, want_hits=False)      # warm-up, builds the index
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for c in cams:
+            tree.render(c, W, H, quality, threads=threads, want_hits=False)
+        best = min(best, time.perf_counter() - t0)
+    return len(cams) * RAYS_PER_FRAME / best / 1e6, best
+
+
+def run_reference(args):
+    rank, _, world = rank_env()
+    if rank != 0:
+        return
+    from oracle import orc
+    from tools import datasets as ds
+    O, kind = pick_cpu_oracle(orc)
+    threads = os.cpu_count() or 1
+    sample = list(range(0, FRAMES, 10))                 # 36 frames of the orbit per step
+    tree = O.tree(ds.volume_voxels("skull"))
+    cams = [ds.setup_camera(O.camera(0), *ds.orbit_pose(f, FRAMES), FOV, W, H) for f in sample]
+    step = lambda: [tree.render(c, W, H, 0, threads=threads, want_hits=False) for c in cams]
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * len(sample) * RAYS_PER_FRAME / dt / 1e6
+    sample_txt = f"{len(sample)} of the {FRAMES} orbit frames per step (every 10th), quality BEST"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "bundled skull volume (sample>40), scripted orbit",
+        "config": {"workload": "C2 skull 1920x1080 x 360-frame orbit (sampled)", "oracle": O.name,
+                   "threads": threads, "frames_per_step": len(sample)},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
+                         "sample": sample_txt},
+        "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# --------------------------------------------------------------------- own arm
+
+def algorithmic_bytes_per_frame(ds, orc_mod, sample_frames, threads):
+    """Bytes the reference's recursion must touch per frame, from the instrumented oracle."""
+    P = orc_mod.Oracle("port")
+    tree = P.tree(ds.volume_voxels("skull"))
+    total = 0.0
+    for f in sample_frames:
+        cam = ds.setup_camera(P.camera(0), *ds.orbit_pose(f, FRAMES), FOV, W, H)
+        org, dirs = cam.rays(W, H)
+        *_, st = tree.rays(org, dirs, threads=threads, want_stats=True)
+        total += (st["inner"] * BYTES_INNER + st["leaf"] * BYTES_LEAF + st["dense"] * BYTES_DENSE +
+                  st["dots_tested"] * BYTES_DOT + RAYS_PER_FRAME * BYTES_PIXEL)
+    return total / len(sample_frames)
+
+
+def run_own(args):
+    rank, local_rank, world = rank_env()
+    import voxvision_b200 as vv
+    from voxvision_b200 import api
+    from tools import datasets as ds
+
+    if not vv.gpu_available():
+        raise SystemExit("bench.py: no CUDA device (" + vv.last_error() + "); there is no CPU fallback to time")
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    vv.set_device(local_rank)
+    g = api.libs.gpu
+
+    tree = vv.Tree.build(ds.volume_voxels("skull"))
+    dev_tree = tree.device_handle()
+    ctx = vv.Context(W, H)
+    ctx.set_scene(tree)
+    ctx.set_quality(vv.QUALITY_BEST)
+    fmt, tex = ctx.pixfmt(), ctx.texture()
+
+    # per-frame cameras: host-side camera maths, through the camera module's vtable
+    cam = vv.Camera("simple-camera")
+    gcams, poses = [], []
+    for f in range(FRAMES):
+        pos, look = frame_pose(ds, f, rank, world)
+        ds.setup_camera(cam, pos, look, FOV, W, H)
+        gcams.append(cam.gpu_camera())
+        poses.append((pos, look))
+    frame_desc = api.GpuFrame(W, H, 0, H, W, vv.QUALITY_BEST, fmt)
+
+    # ---- device-resident leg ------------------------------------------------
+    frame_bytes = W * H * 4
+    if world > 1:
+        render_stream = torch.cuda.Stream()
+        comm_stream = torch.cuda.Stream()
+        s_ptr = C.c_void_p(render_stream.cuda_stream)
+        ring = torch.empty((2, GATHER_BATCH, H, W), dtype=torch.int32, device="cuda")
+        ring_ptr = lambda i: ring[(i // GATHER_BATCH) % 2, i % GATHER_BATCH].data_ptr()
+        gathered = ([torch.empty_like(ring[0]) for _ in range(world)] if rank == 0 else None)
+        d_tex_t = torch.from_numpy(tex.copy()).cuda()
+        d_tex = d_tex_t.data_ptr()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    else:
+        s_ptr = C.c_void_p(g.voxgpu_stream_create())
+        bufs = [vv.DeviceBuffer(frame_bytes) for _ in range(RING)]
+        ring_ptr = lambda i: bufs[i % RING].ptr
+        d_tex_b = vv.DeviceBuffer.from_array(tex)
+        d_tex = d_tex_b.ptr
+        flush_b = vv.DeviceBuffer(256 << 20)
+
+    def flush_l2():
+        if world > 1:
+            with torch.cuda.stream(render_stream):
+                flush.zero_()
+        else:
+            g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)
+
+    def device_step():
+        """360 launches back to back; N>1: every GATHER_BATCH frames go to GPU 0 on the side stream."""
+        flush_l2()
+        batch_done = []
+        for f in range(FRAMES):
+            if world > 1 and f % GATHER_BATCH == 0 and f >= 2 * GATHER_BATCH:
+                render_stream.wait_event(batch_done[f // GATHER_BATCH - 2])   # ring slot free again
+            rc = g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None, s_ptr)
+            if rc:
+                raise vv.VoxError(g.voxgpu_last_error().decode())
+            if world > 1 and f % GATHER_BATCH == GATHER_BATCH - 1:
+                ev = torch.cuda.Event()
+                ev.record(render_stream)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    dist.gather(ring[(f // GATHER_BATCH) % 2], gathered, dst=0)
+                    done = torch.cuda.Event()
+                    done.record(comm_stream)
+                batch_done.append(done)
+        if world > 1:
+            render_stream.wait_stream(comm_stream)
+
+    def sync_all():
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+        else:
+            g.voxgpu_synchronize(None)
+
+    timer = vv.Timer()
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = vv.launch_count()
+    timer.start(s_ptr)
+    for _ in range(args.steps):
+        device_step()
+    timer.stop(s_ptr)
+    sync_all()
+    ms_total = timer.elapsed_ms()
+    launches = vv.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only duration (no gather, no flush): CUDA events around each launch, same stream
+    kt = vv.Timer()
+    kernel_ms = []
+    for f in range(0, FRAMES, 4):
+        kt.start(s_ptr)
+        g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None, s_ptr)
+        kt.stop(s_ptr)
+        kernel_ms.append(kt.elapsed_ms())
+    sync_all()
+
+    # ---- end-to-end leg: the reference-facing API with a host surface --------
+    def e2e_step():
+        for f in range(FRAMES):
+            pos, look = poses[f]
+            cam.set_position(pos)
+            cam.look_at(look)
+            ctx.set_camera(cam)
+            ctx.render()
+            ctx.redraw()            # frame f is now in surface->pixels (host memory)
+        return int(ctx.pixels()[H // 2, W // 2])
+
+    ctx.set_camera(cam)
+    e2e_step()
+    sync_all()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if vv.last_error():
+        raise vv.VoxError(vv.last_error())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_rays = world * args.steps * FRAMES * RAYS_PER_FRAME
+    value = total_rays / (ms_total * 1e-3) / 1e6
+    e2e_value = world * e2e_steps * FRAMES * RAYS_PER_FRAME / e2e_s / 1e6
+
+    # ---- roofline + CPU baseline (rank 0; oracle = checker/baseline only) ----
+    from oracle import orc
+    threads = os.cpu_count() or 1
+    peak, peak_src = measured_peak()
+    bytes_per_launch = algorithmic_bytes_per_frame(ds, orc, list(range(0, FRAMES, 45)), threads)
+    mean_kernel_ms = float(np.mean(kernel_ms))
+    achieved = bytes_per_launch / (mean_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_render_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_render", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": round(bytes_per_launch), "bytes_per_ray": round(bytes_per_launch / RAYS_PER_FRAME, 2),
+                "kernel_ms_mean": round(mean_kernel_ms, 5), "kernel_ms_min": round(float(np.min(kernel_ms)), 5),
+                "note": "the 18 MB tree is L2-resident, so DRAM traffic is far below the algorithmic bytes; "
+                        "the kernel is latency/issue bound (see profiles/)"}
+    cpu_baseline = None
+    if world == 1:
+        O, kind = pick_cpu_oracle(orc)
+        sample = list(range(0, FRAMES, 10))
+        rate, secs = cpu_render_rate(ds, O, sample, 5, threads)
+        cpu_baseline = {"value": round(rate, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
+                        "oracle": O.name,
+                        "sample": f"{len(sample)} of the {FRAMES} orbit frames (every 10th), quality BEST, "
+                                  f"OpenMP over 4x4 blocks on all {threads} host threads, best of 5 passes ({secs:.2f} s each)"}
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "bundled skull volume (sample>40, 1 073 426 voxels) from the committed occupancy fixture; "
+                "scripted 360-frame orbit camera",
+        "config": {"workload": "C2: skull 1920x1080, 360-frame orbit, quality BEST, simple-camera",
+                   "frames_per_step_per_gpu": FRAMES, "rays_per_frame": RAYS_PER_FRAME,
+                   "parallelism": f"frames x{world} (tree replicated" + (", NCCL gather to GPU 0 in the timed region)" if world > 1 else ")"),
+                   "l2": "256 MB L2 flush at the start of every step; within a step the 18 MB tree stays "
+                         "L2-resident across frames by design (every frame has a different camera and its own framebuffer)"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s",
+                "h2d_bytes_per_step": FRAMES * (C.sizeof(api.GpuCamera) + C.sizeof(api.GpuFrame)),
+                "d2h_bytes_per_step": FRAMES * frame_bytes, "steps": e2e_steps,
+                "path": "vox_render + vox_redraw per frame, kernel stores straight into the pinned mapped surface"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,9 @@ ORC_EXPORT void orc_camera_move (orc_camera *c, const float delta[3]);
 ORC_EXPORT void orc_camera_set_window_size (orc_camera *c, int w, int h);
 ORC_EXPORT void orc_camera_get_position (orc_camera *c, float p[3]);
 ORC_EXPORT void orc_camera_screen2world (orc_camera *c, float dir[3], int sx, int sy);
+/* All primary rays of a w x h frame, row-major: origins[3*(y*w+x)] = get_position,
+ * dirs[...] = screen2world (x, y) -- the rays vox_render casts (renderer.c:236,292). */
+ORC_EXPORT void orc_camera_rays (orc_camera *c, int w, int h, float *origins, float *dirs);
 /* POD state: simple -> {pos[3], quat[4] (w,i,j,k), mul, xsub, ysub, fov};
  *            doom   -> {pos[3], sinphi, cosphi, k, phi, mul, xsub, ysub, fov}. */
 ORC_EXPORT void orc_camera_get_state (orc_camera *c, float state[11]);

@@ -106,6 +106,7 @@ class Oracle:
         L.orc_camera_set_window_size.argtypes = [vp, i, i]
         L.orc_camera_screen2world.argtypes = [vp, vp, i, i]
         L.orc_camera_get_state.argtypes = [vp, vp]
+        L.orc_camera_rays.argtypes = [vp, i, i, vp, vp]
         L.orc_render.restype = i
         L.orc_render.argtypes = [vp, vp, i, i, u, vp, C.POINTER(PixFmt), vp, vp, vp, i]
 
@@ -235,6 +236,12 @@ class OracleCamera:
         a = np.zeros(3, np.float32)
         self.orc.lib.orc_camera_screen2world(self.h, a.ctypes.data, sx, sy)
         return a
+
+    def rays(self, w, h):
+        """All primary rays of a w x h frame (origins, dirs), row-major."""
+        o, d = np.empty((h * w, 3), np.float32), np.empty((h * w, 3), np.float32)
+        self.orc.lib.orc_camera_rays(self.h, w, h, o.ctypes.data, d.ctypes.data)
+        return o, d
 
     def state(self):
         a = np.zeros(11, np.float32)

@@ -29,9 +29,11 @@
 #include "oracle_api.h"
 #include "render_loop.h"
 
-#ifdef SSE_INTRIN
-#error "ref_glue.c is written for the scalar reference build (vox_dot = float[3])"
-#endif
+/* The oracle API speaks packed float[3]; the reference's vox_dot is float[3]
+ * (scalar build) or 16-byte aligned float[4] (SSE build).  DOT_IN/DOT_OUT move
+ * the three coordinates across. */
+#define DOT_IN(dst, src)  do { memset ((dst), 0, sizeof (vox_dot)); memcpy ((dst), (src), 3*sizeof (float)); } while (0)
+#define DOT_OUT(dst, src) memcpy ((dst), (src), 3*sizeof (float))
 
 /* the two camera files are compiled with -Dmodule_init=<kind>_module_init */
 struct vox_module* simple_module_init (void);
@@ -77,17 +79,21 @@ struct orc_camera
     struct vox_camera *cam;
 };
 
+#ifdef SSE_INTRIN
+const char* orc_impl_name (void) { return "reference-sse"; }
+#else
 const char* orc_impl_name (void) { return "reference-scalar"; }
+#endif
 
 void orc_set_voxel (float x, float y, float z) { vox_set_voxel_size (x, y, z); }
-void orc_get_voxel (float out[3]) { memcpy (out, vox_voxel, 3*sizeof(float)); }
+void orc_get_voxel (float out[3]) { DOT_OUT (out, vox_voxel); }
 
 orc_tree* orc_tree_build (const float *xyz, size_t n)
 {
     orc_tree *t = calloc (1, sizeof *t);
     t->n = n;
-    t->set = malloc ((n ? n : 1) * sizeof (vox_dot));
-    memcpy (t->set, xyz, n * sizeof (vox_dot));
+    t->set = aligned_alloc (16, (((n ? n : 1) * sizeof (vox_dot)) + 15) & ~(size_t) 15);
+    for (size_t i=0; i<n; i++) DOT_IN (t->set[i], xyz + 3*i);
     t->root = vox_make_tree (t->set, n);
     return t;
 }
@@ -96,8 +102,8 @@ orc_tree* orc_tree_build_by_insertion (const float *xyz, size_t n)
 {
     orc_tree *t = calloc (1, sizeof *t);
     t->n = n;
-    t->set = malloc ((n ? n : 1) * sizeof (vox_dot));
-    memcpy (t->set, xyz, n * sizeof (vox_dot));
+    t->set = aligned_alloc (16, (((n ? n : 1) * sizeof (vox_dot)) + 15) & ~(size_t) 15);
+    for (size_t i=0; i<n; i++) DOT_IN (t->set[i], xyz + 3*i);
     for (size_t i=0; i<n; i++)
     {
         vox_dot d;
@@ -117,7 +123,7 @@ void orc_tree_free (orc_tree *t)
 
 void orc_tree_reordered_set (orc_tree *t, float *xyz)
 {
-    memcpy (xyz, t->set, t->n * sizeof (vox_dot));
+    for (size_t i=0; i<t->n; i++) DOT_OUT (xyz + 3*i, t->set[i]);
 }
 
 static int cmp_id_pair (const void *a, const void *b)
@@ -195,8 +201,8 @@ void orc_tree_flatten (orc_tree *t, orc_flat *out)
     for (uint64_t id=0; id<n; id++)
     {
         const struct vox_node *node = t->bfs[id];
-        memcpy (out->bb_min + 3*id, node->bounding_box.min, 3*sizeof(float));
-        memcpy (out->bb_max + 3*id, node->bounding_box.max, 3*sizeof(float));
+        DOT_OUT (out->bb_min + 3*id, node->bounding_box.min);
+        DOT_OUT (out->bb_max + 3*id, node->bounding_box.max);
         out->flags[id] = node->flags;
         out->dots_num[id] = node->dots_num;
         out->center[3*id] = out->center[3*id+1] = out->center[3*id+2] = 0;
@@ -205,10 +211,11 @@ void orc_tree_flatten (orc_tree *t, orc_flat *out)
         out->dots_off[id] = t->dots_off[id];
         if (node->flags & VOX_DENSE_LEAF) {}
         else if (node->flags & VOX_LEAF)
-            memcpy (out->dots + 3*t->dots_off[id], node->data.dots, node->dots_num*sizeof(vox_dot));
+            for (unsigned k=0; k<node->dots_num; k++)
+                DOT_OUT (out->dots + 3*(t->dots_off[id] + k), node->data.dots[k]);
         else
         {
-            memcpy (out->center + 3*id, node->data.inner.center, 3*sizeof(float));
+            DOT_OUT (out->center + 3*id, node->data.inner.center);
             out->first_child[id] = (uint32_t)next_child;
             uint32_t mask = 0;
             for (int i=0; i<VOX_NS; i++)
@@ -251,12 +258,12 @@ void orc_ray_batch (orc_tree *t, uint32_t start_node,
     for (size_t i=0; i<n; i++)
     {
         vox_dot o, d, res;
-        memcpy (o, origins + 3*i, sizeof o);
-        memcpy (d, dirs + 3*i, sizeof d);
+        DOT_IN (o, origins + 3*i);
+        DOT_IN (d, dirs + 3*i);
         const struct vox_node *leaf = vox_ray_tree_intersection (start, o, d, res);
         int32_t id = leaf ? node_to_id (t, leaf) : -1;
         if (leaf_id) leaf_id[i] = id;
-        if (leaf && hit) memcpy (hit + 3*i, res, sizeof res);
+        if (leaf && hit) DOT_OUT (hit + 3*i, res);
         if (dot_idx) dot_idx[i] = leaf ? derive_dot (t, id, res) : -1;
     }
 }
@@ -269,7 +276,7 @@ void orc_ball_batch (orc_tree *t, const float *centers, const float *radii,
     for (size_t i=0; i<n; i++)
     {
         vox_dot c;
-        memcpy (c, centers + 3*i, sizeof c);
+        DOT_IN (c, centers + 3*i);
         out[i] = (uint8_t) vox_tree_ball_collidep (t->root, c, radii[i]);
     }
 }
@@ -294,23 +301,37 @@ void orc_camera_free (orc_camera *c)
 }
 
 void orc_camera_set_position (orc_camera *c, const float p[3])
-{ vox_dot d; memcpy (d, p, sizeof d); c->cam->iface->set_property_dot (c->cam, "position", d); }
+{ vox_dot d; DOT_IN (d, p); c->cam->iface->set_property_dot (c->cam, "position", d); }
 void orc_camera_set_fov (orc_camera *c, float fov)
 { c->cam->iface->set_property_number (c->cam, "fov", fov); }
 void orc_camera_set_rotation (orc_camera *c, const float a[3])
-{ vox_dot d; memcpy (d, a, sizeof d); c->cam->iface->set_property_dot (c->cam, "rotation", d); }
+{ vox_dot d; DOT_IN (d, a); c->cam->iface->set_property_dot (c->cam, "rotation", d); }
 void orc_camera_look_at (orc_camera *c, const float p[3])
-{ vox_dot d; memcpy (d, p, sizeof d); c->cam->iface->look_at (c->cam, d); }
+{ vox_dot d; DOT_IN (d, p); c->cam->iface->look_at (c->cam, d); }
 void orc_camera_rotate (orc_camera *c, const float delta[3])
-{ vox_dot d; memcpy (d, delta, sizeof d); c->cam->iface->rotate_camera (c->cam, d); }
+{ vox_dot d; DOT_IN (d, delta); c->cam->iface->rotate_camera (c->cam, d); }
 void orc_camera_move (orc_camera *c, const float delta[3])
-{ vox_dot d; memcpy (d, delta, sizeof d); c->cam->iface->move_camera (c->cam, d); }
+{ vox_dot d; DOT_IN (d, delta); c->cam->iface->move_camera (c->cam, d); }
 void orc_camera_set_window_size (orc_camera *c, int w, int h)
 { c->cam->iface->set_window_size (c->cam, w, h); }
 void orc_camera_get_position (orc_camera *c, float p[3])
-{ vox_dot d; c->cam->iface->get_position (c->cam, d); memcpy (p, d, sizeof d); }
+{ vox_dot d; c->cam->iface->get_position (c->cam, d); DOT_OUT (p, d); }
 void orc_camera_screen2world (orc_camera *c, float dir[3], int sx, int sy)
-{ vox_dot d; c->cam->iface->screen2world (c->cam, d, sx, sy); memcpy (dir, d, sizeof d); }
+{ vox_dot d; c->cam->iface->screen2world (c->cam, d, sx, sy); DOT_OUT (dir, d); }
+
+void orc_camera_rays (orc_camera *c, int w, int h, float *origins, float *dirs)
+{
+    float pos[3];
+    orc_camera_get_position (c, pos);
+#pragma omp parallel for schedule(static)
+    for (int y=0; y<h; y++)
+        for (int x=0; x<w; x++)
+        {
+            size_t i = (size_t) y*w + x;
+            memcpy (origins + 3*i, pos, sizeof pos);
+            orc_camera_screen2world (c, dirs + 3*i, x, y);
+        }
+}
 
 void orc_camera_get_state (orc_camera *c, float s[11])
 {
@@ -318,14 +339,14 @@ void orc_camera_get_state (orc_camera *c, float s[11])
     if (c->kind == ORC_CAMERA_DOOM)
     {
         const struct doom_camera_mirror *m = (const void*) c->cam;
-        memcpy (s, m->position, 3*sizeof(float));
+        DOT_OUT (s, m->position);
         s[3] = m->sinphi; s[4] = m->cosphi; s[5] = m->k; s[6] = m->phi;
         s[7] = m->mul; s[8] = m->xsub; s[9] = m->ysub; s[10] = m->fov;
     }
     else
     {
         const struct simple_camera_mirror *m = (const void*) c->cam;
-        memcpy (s, m->position, 3*sizeof(float));
+        DOT_OUT (s, m->position);
         memcpy (s+3, m->rotation, 4*sizeof(float));
         s[7] = m->mul; s[8] = m->xsub; s[9] = m->ysub; s[10] = m->fov;
     }
@@ -334,13 +355,20 @@ void orc_camera_get_state (orc_camera *c, float s[11])
 /* ---- render: restated block loop, reference search + camera underneath ---- */
 
 static const void* hook_ray (const void *node, const float *o, const float *d, float *res)
-{ return vox_ray_tree_intersection (node, o, d, res); }
+{
+    vox_dot o_, d_, r_;
+    DOT_IN (o_, o); DOT_IN (d_, d);
+    const struct vox_node *leaf = vox_ray_tree_intersection (node, o_, d_, r_);
+    if (leaf) DOT_OUT (res, r_);
+    return leaf;
+}
 static void hook_s2w (void *cam, float *dir, int sx, int sy)
-{ struct vox_camera *c = cam; c->iface->screen2world (c, dir, sx, sy); }
+{ struct vox_camera *c = cam; vox_dot d; c->iface->screen2world (c, d, sx, sy); DOT_OUT (dir, d); }
 static void hook_pos (void *cam, float *pos)
-{ struct vox_camera *c = cam; c->iface->get_position (c, pos); }
-static float hook_sqr_metric (const float *a, const float *b) { return vox_sqr_metric (a, b); }
-static float hook_sqr_norm (const float *a) { return vox_sqr_norm (a); }
+{ struct vox_camera *c = cam; vox_dot d; c->iface->get_position (c, d); DOT_OUT (pos, d); }
+static float hook_sqr_metric (const float *a, const float *b)
+{ vox_dot a_, b_; DOT_IN (a_, a); DOT_IN (b_, b); return vox_sqr_metric (a_, b_); }
+static float hook_sqr_norm (const float *a) { vox_dot a_; DOT_IN (a_, a); return vox_sqr_norm (a_); }
 
 int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
                 const uint8_t *texture, const orc_pixfmt *fmt,
@@ -353,6 +381,6 @@ int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
         .sqr_metric = hook_sqr_metric, .sqr_norm = hook_sqr_norm,
         .node_id = leaf_id ? node_to_id : NULL, .idctx = t,
     };
-    memcpy (hk.voxel, vox_voxel, sizeof hk.voxel);
+    DOT_OUT (hk.voxel, vox_voxel);
     return orc_render_loop (&hk, w, h, quality, texture, fmt, pixels, leaf_id, hit, threads);
 }

@@ -728,6 +728,20 @@ void orc_camera_screen2world (orc_camera *c, float dir[3], int sx, int sy)
     rotate_vec (c->quat, ray, dir);
 }
 
+void orc_camera_rays (orc_camera *c, int w, int h, float *origins, float *dirs)
+{
+    float pos[3];
+    orc_camera_get_position (c, pos);
+#pragma omp parallel for schedule(static)
+    for (int y=0; y<h; y++)
+        for (int x=0; x<w; x++)
+        {
+            size_t i = (size_t) y*w + x;
+            memcpy (origins + 3*i, pos, sizeof pos);
+            orc_camera_screen2world (c, dirs + 3*i, x, y);
+        }
+}
+
 void orc_camera_get_state (orc_camera *c, float s[11])
 {
     memset (s, 0, 11*sizeof(float));

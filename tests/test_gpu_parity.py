@@ -1,0 +1,388 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the
+oracle (the reference's own object code when oracle/_ref is present, else the
+CPU restatement) and against the committed golden fixtures.  Bit-exact
+everywhere: leaf ids, hit points (fp32 bit patterns), voxel indices, collision
+booleans, pixels."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from util import CROSS, ball_voxels, bits, flat_equal, sha
+
+pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1
+
+
+def render_device(vv, tree, cam, w, h, tex, fmt, y0=0, y1=None, want_hits=True, gcam=None):
+    """voxgpu_render into device buffers (the entry multi-GPU drivers use)."""
+    api = vv.api
+    y1 = h if y1 is None else y1
+    rows = y1 - y0
+    d_tex = vv.DeviceBuffer.from_array(tex)
+    d_pix = vv.DeviceBuffer(w * rows * 4)
+    d_leaf = vv.DeviceBuffer(w * rows * 4)
+    d_pts = vv.DeviceBuffer(w * rows * 16)
+    api.libs.gpu.voxgpu_memset(d_pix.ptr, 0xff, w * rows * 4, None)
+    gc = gcam or cam.gpu_camera()
+    fr = api.GpuFrame(w, h, y0, y1, w, 0, fmt)
+    rc = api.libs.gpu.voxgpu_render(tree.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr,
+                                    d_leaf.ptr if want_hits else None, d_pts.ptr if want_hits else None, None)
+    assert rc == 0, api.libs.gpu.voxgpu_last_error()
+    pix = d_pix.download(np.uint32, (rows, w))
+    leaf = d_leaf.download(np.int32, (rows, w)) if want_hits else None
+    pts = d_pts.download(np.float32, (rows, w, 4))[:, :, :3] if want_hits else None
+    return pix, leaf, pts
+
+
+def assert_rays_equal(got, want, check_voxel=True):
+    leaf, pts, vox = got
+    oleaf, opts, odot = want
+    assert np.array_equal(leaf, oleaf), f"{int((leaf != oleaf).sum())} leaf ids differ"
+    m = oleaf >= 0
+    assert np.array_equal(bits(pts[m]), bits(opts[m])), "hit points differ"
+    if check_voxel:
+        assert np.array_equal(vox[m].astype(np.int64), odot[m]), "hit voxels differ"
+    assert (vox[~m] == -1).all()
+
+
+# ------------------------------------------------------------------ K2 rays
+
+def test_rays_skull_golden(gpu, golden, skull, ds):
+    """Against vectors produced by the reference's object code (no oracle library at run time)."""
+    meta, arr = golden
+    t = gpu.Tree.build(skull)
+    o, d = ds.random_rays(4096, side=256)
+    leaf, pts, vox = t.rays(o, d)
+    assert np.array_equal(leaf, arr["skull_rays_leaf"])
+    m = leaf >= 0
+    assert int(m.sum()) == meta["skull_rays_hits"]
+    assert np.array_equal(bits(pts[m]), bits(arr["skull_rays_hit"][m]))
+    c, r = ds.random_balls(4096, *t.bounding_box())
+    assert np.array_equal(t.balls(c, r), arr["skull_balls"])
+
+
+def test_cross_reference_test_vector(gpu, golden):
+    """tests/tests.c:600-659: on the make_tree-built cross and on the reference's insertion-built one."""
+    meta, arr = golden
+    t = gpu.Tree.build(CROSS)
+    leaf, p = t.ray([-2, -2, 0], [1, 1, -1])
+    assert leaf == meta["cross_make_leaf"] and np.array_equal(bits(p), bits(arr["cross_make_hit"]))
+    flat = {k[len("cross_ins_flat_"):]: v for k, v in arr.items() if k.startswith("cross_ins_flat_")}
+    flat["depth"] = meta["cross_ins_depth"]
+    ti = gpu.Tree.from_arrays(flat)
+    leaf, p = ti.ray([-2, -2, 0], [1, 1, -1])
+    assert leaf == meta["cross_ins_leaf"] and np.array_equal(bits(p), bits(arr["cross_ins_hit"]))
+    oo, dd = __import__("tools.datasets", fromlist=["x"]).random_rays(2048, side=10)
+    oo -= 5
+    l, h, _ = ti.rays(oo, dd)
+    assert np.array_equal(l, arr["cross_ins_rays_leaf"])
+    assert np.array_equal(bits(h[l >= 0]), bits(arr["cross_ins_rays_hit"][l >= 0]))
+
+
+def test_benchmark_known_answers(gpu, golden):
+    meta, _ = golden
+    one = gpu.Tree.build(np.array([[0, 10, 0]], np.float32))
+    j = np.arange(10, dtype=np.float32)
+    o = np.stack([j - 5, 0 * j, 0 * j], 1)
+    d = np.stack([(j - 5) / np.float32(10.0), 0 * j + 1, 0 * j], 1).astype(np.float32)
+    assert int((one.rays(o, d)[0] >= 0).sum()) == meta["hitbox_hits"]
+    one0 = gpu.Tree.build(np.array([[0, 0, 0]], np.float32))
+    jj = np.arange(-100, 100, dtype=np.float32)
+    c = np.stack([0 * jj, 0 * jj + 10, jj], 1)
+    assert int(one0.balls(c, np.full(200, 1000, np.float32)).sum()) == 200
+
+
+@pytest.mark.parametrize("scene", ["skull", "bonsai", "ball50", "sparse", "cross", "dup"])
+def test_rays_and_balls_vs_oracle(gpu, checker, ds, skull, bonsai, scene):
+    rng = np.random.default_rng(17)
+    if scene == "skull":
+        vox, side, off = skull, 256, 0
+    elif scene == "bonsai":
+        vox, side, off = bonsai, 256, 0
+    elif scene == "ball50":
+        vox, side, off = ball_voxels(50), 100, -50
+    elif scene == "sparse":
+        vox = np.unique(rng.integers(0, 128, (150000, 3)), axis=0).astype(np.float32)
+        rng.shuffle(vox)
+        side, off = 128, 0
+    elif scene == "cross":
+        vox, side, off = CROSS, 10, -5
+    else:   # duplicates -> an overflowed leaf with > 7 dots next to ordinary nodes
+        vox = np.concatenate([np.tile(np.array([[3, 4, 5]], np.float32), (20, 1)), ball_voxels(4) + 20])
+        side, off = 32, 0
+    t, o = gpu.Tree.build(vox), checker.tree(vox)
+    assert flat_equal(t.export(), o.flatten()) == []
+    n = 300000
+    org, d = ds.random_rays(n, side=side)
+    org += off
+    d[:2000, 0] = 0                      # division by zero inside hit_box (geom.c:79-85)
+    d[2000:4000, 1:] = 0                 # axis-aligned
+    org[4000:8000] = rng.random((4000, 3)).astype(np.float32) * side + off   # origins inside the volume
+    org[8000:10000] = np.floor(org[8000:10000])                               # exactly on voxel faces
+    d[10000:11000] = np.round(d[10000:11000] / side * 4)                      # small integer directions
+    assert_rays_equal(t.rays(org, d), o.rays(org, d, threads=THREADS), check_voxel=(checker.which == "port"))
+    lo, hi = t.bounding_box()
+    c, r = ds.random_balls(n, lo, hi)
+    r[:1000] = 0                                                                # zero radius never collides (strict <)
+    assert np.array_equal(t.balls(c, r), o.balls(c, r, threads=THREADS))
+
+
+def test_rays_from_inner_and_leaf_nodes(gpu, checker, ds, skull):
+    """The returned leaf must be usable as a tree (renderer.c:297); so must any node."""
+    t, o = gpu.Tree.build(skull), checker.tree(skull)
+    fl = t.export()
+    org, d = ds.random_rays(20000, side=256)
+    kinds = fl["flags"] & 3
+    picks = list(np.flatnonzero(kinds == 1)[:20]) + list(np.flatnonzero(kinds == 0)[1:20]) + \
+        list(np.flatnonzero(kinds == 2)[:10])
+    for nid in picks:
+        got = t.rays(org, d, start_node=int(nid))
+        want = o.rays(org, d, start_node=int(nid), threads=THREADS)
+        assert_rays_equal(got, want, check_voxel=False)
+
+
+def test_nonunit_voxel(gpu, checker, ds):
+    rng = np.random.default_rng(12)
+    idx = np.unique(rng.integers(-30, 30, (20000, 3)), axis=0)
+    rng.shuffle(idx)
+    size = np.array([0.5, 2.0, 0.25], np.float32)
+    vox = idx.astype(np.float32) * size
+    try:
+        gpu.set_voxel_size(*size)
+        checker.set_voxel(*size)
+        t, o = gpu.Tree.build(vox), checker.tree(vox)
+        org = (rng.random((100000, 3)).astype(np.float32) - 0.5) * np.array([60, 240, 30], np.float32)
+        d = rng.standard_normal((100000, 3)).astype(np.float32)
+        assert_rays_equal(t.rays(org, d), o.rays(org, d, threads=THREADS), check_voxel=False)
+        r = rng.random(100000).astype(np.float32) * 4
+        assert np.array_equal(t.balls(org, r), o.balls(org, r, threads=THREADS))
+        # the frame too: get_color divides by the voxel size (renderer.c:31-33)
+        w, h = 320, 160
+        cam = ds.setup_camera(gpu.Camera(), (5, -90, 3), (0, 0, 0), 1.0, w, h)
+        ocam = ds.setup_camera(checker.camera(0), (5, -90, 3), (0, 0, 0), 1.0, w, h)
+        ctx = gpu.Context(w, h)
+        pix, leaf, pts = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+        opix, oleaf, ohit = o.render(ocam, w, h, 0, ctx.texture(), threads=THREADS)
+        assert (oleaf >= 0).sum() > 1000
+        assert np.array_equal(pix, opix) and np.array_equal(leaf, oleaf)
+    finally:
+        gpu.set_voxel_size(1, 1, 1)
+        checker.set_voxel(1, 1, 1)
+
+
+def test_single_query_api_and_edge_cases(gpu, checker, ds, skull):
+    t, o = gpu.Tree.build(skull), checker.tree(skull)
+    org, d = ds.random_rays(64, side=256)
+    oleaf, ohit, _ = o.rays(org, d)
+    for i in range(64):
+        leaf, p = t.ray(org[i], d[i])
+        if oleaf[i] < 0:
+            assert leaf is None
+        else:
+            assert leaf == oleaf[i] and np.array_equal(bits(p), bits(ohit[i]))
+    # the leaf handle returned by one search is accepted by the next
+    i = int(np.flatnonzero(oleaf >= 0)[0])
+    leaf, p = t.ray(org[i], d[i])
+    leaf2, p2 = t.ray(org[i], d[i], start=t.node(leaf))
+    assert leaf2 == leaf
+    c, r = ds.random_balls(64, *t.bounding_box())
+    ob = o.balls(c, r)
+    assert [t.ball(c[k], float(r[k])) for k in range(64)] == list(ob)
+    # empty batches, empty tree
+    assert t.rays(np.zeros((0, 3)), np.zeros((0, 3)))[0].shape == (0,)
+    assert t.balls(np.zeros((0, 3)), np.zeros(0)).shape == (0,)
+    e = gpu.Tree.build(np.zeros((0, 3), np.float32))
+    assert (e.rays(org, d)[0] == -1).all() and not e.balls(c, r).any()
+    # NaN / inf inputs do not hang or crash and agree with the oracle's booleans
+    bad_o, bad_d = org.copy(), d.copy()
+    bad_d[:8] = np.nan; bad_o[8:16] = np.inf; bad_d[16:24] = 0
+    got, want = t.rays(bad_o, bad_d), o.rays(bad_o, bad_d)
+    assert np.array_equal(got[0], want[0])
+
+
+def test_traversal_counters_match_oracle(gpu, port, ds, skull):
+    """The instrumented kernel visits exactly the nodes the reference's recursion visits
+    (this is what makes the oracle's visit counts the roofline's algorithmic bytes)."""
+    t, o = gpu.Tree.build(skull), port.tree(skull)
+    org, d = ds.random_rays(200000, side=256)
+    *_, st = o.rays(org, d, threads=THREADS, want_stats=True)
+    g = gpu.api.libs.gpu
+    d_o, d_d = gpu.DeviceBuffer.from_array(gpu.api.dots4(org)), gpu.DeviceBuffer.from_array(gpu.api.dots4(d))
+    gs = gpu.api.GpuStats()
+    assert g.voxgpu_rays_stats(t.device_handle(), 0, d_o.ptr, d_d.ptr, len(org), None, None, None, C.byref(gs)) == 0
+    gs = gs.as_dict()
+    assert gs["rays"] == len(org)
+    assert gs["calls"] == st["calls"] - st["null_calls"]
+    assert (gs["inner"], gs["leaf"], gs["dense"]) == (st["inner"], st["leaf"], st["dense"])
+    assert gs["dots_tested"] == st["dots_tested"]
+    assert gs["expansions"] * 3 == st["plane_tests"]
+    assert gs["max_stack"] <= 2 * t.info().depth
+
+
+# ----------------------------------------------------------------- K1 render
+
+@pytest.mark.parametrize("frame", [0, 45, 90, 135, 180, 225, 270, 315])
+def test_c2_frames_golden(gpu, golden, skull, ds, frame):
+    """Skull 1080p at full size against the reference-generated digests (SURVEY.md 8d known answers)."""
+    meta, _ = golden
+    cache = test_c2_frames_golden.__dict__
+    t = cache.setdefault("tree", gpu.Tree.build(skull))
+    ctx = cache.setdefault("ctx", gpu.Context(1920, 1080))
+    assert sha(ctx.texture()) == meta["texture_sha"]
+    pos, look = ds.orbit_pose(frame)
+    cam = ds.setup_camera(gpu.Camera("simple-camera"), pos, look, 1.2, 1920, 1080)
+    want = meta["c2"][str(frame)]
+    pix, leaf, pts = render_device(gpu, t, cam, 1920, 1080, ctx.texture(), ctx.pixfmt())
+    m = leaf >= 0
+    assert int(m.sum()) == want["hits"] == ds.C2_KNOWN_HITS[frame]
+    assert sha(leaf) == want["leaf_sha"]
+    assert sha(np.ascontiguousarray(pts[m])) == want["hit_sha"]
+    assert sha(pix) == want["pix_sha"]
+    # the reference-facing path: vox_render + vox_redraw into the (pinned) surface
+    ctx.set_scene(t); ctx.set_camera(cam)
+    assert ctx.set_quality(gpu.QUALITY_BEST)
+    ctx.pixels()[:] = 0xdeadbeef
+    ctx.render(); ctx.redraw()
+    assert gpu.last_error() == ""
+    assert sha(ctx.pixels()) == want["pix_sha"]
+    assert ctx.kernel_ms() > 0
+
+
+@pytest.mark.parametrize("name,kind,pos", [("simple-camera", 0, (128, 128, 400)), ("doom-camera", 1, (100, -250, 180))])
+def test_c1_bonsai_both_cameras(gpu, checker, golden, bonsai, ds, name, kind, pos):
+    meta, _ = golden
+    t = gpu.Tree.build(bonsai)
+    ctx = gpu.Context(800, 600)
+    cam = ds.setup_camera(gpu.Camera(name), pos, (128, 128, 128), 1.2, 800, 600)
+    pix, leaf, pts = render_device(gpu, t, cam, 800, 600, ctx.texture(), ctx.pixfmt())
+    want = meta["c1"]["simple" if kind == 0 else "doom"]
+    m = leaf >= 0
+    assert int(m.sum()) == want["hits"] and sha(leaf) == want["leaf_sha"]
+    assert sha(np.ascontiguousarray(pts[m])) == want["hit_sha"] and sha(pix) == want["pix_sha"]
+    # a moved / rotated camera, against the live oracle
+    ocam = ds.setup_camera(checker.camera(kind), pos, (128, 128, 128), 1.2, 800, 600)
+    for c in (cam, ocam):
+        c.rotate([0.05, -0.1, 0.2]); c.move([3, -2, 1])
+    pix, leaf, pts = render_device(gpu, t, cam, 800, 600, ctx.texture(), ctx.pixfmt())
+    opix, oleaf, ohit = checker.tree(bonsai).render(ocam, 800, 600, 0, ctx.texture(), threads=THREADS)
+    assert np.array_equal(leaf, oleaf) and np.array_equal(pix, opix)
+    assert np.array_equal(bits(pts[oleaf >= 0]), bits(ohit[oleaf >= 0]))
+
+
+def test_row_bands_tile_the_frame(gpu, skull, ds):
+    """Multi-GPU partition: any 4-aligned row band equals the same rows of the full frame."""
+    t = gpu.Tree.build(skull)
+    w, h = 640, 360
+    ctx = gpu.Context(w, h)
+    pos, look = ds.orbit_pose(30)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    full = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+    for y0, y1 in ((0, 92), (92, 180), (180, 360), (356, 360)):
+        band = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt(), y0, y1)
+        assert np.array_equal(band[0], full[0][y0:y1]) and np.array_equal(band[1], full[1][y0:y1])
+    api = gpu.api
+    fr = api.GpuFrame(w, h, 2, 10, w, 0, ctx.pixfmt())
+    gc = cam.gpu_camera()
+    d = gpu.DeviceBuffer(w * h * 4)
+    assert api.libs.gpu.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d.ptr, d.ptr, None, None, None) != 0
+    assert b"row band" in api.libs.gpu.voxgpu_last_error()
+
+
+def test_foreign_camera_without_describe(gpu, checker, skull, ds):
+    """A camera written against the reference's 10-slot vtable (no `describe`) still renders:
+    its host screen2world is tabulated."""
+    t = gpu.Tree.build(skull)
+    w, h = 320, 160
+    pos, look = ds.orbit_pose(200)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    ctx = gpu.Context(w, h)
+    ctx.set_scene(t); ctx.set_camera(cam); ctx.set_quality(0)
+    ctx.render(); ctx.redraw()
+    want = ctx.pixels().copy()
+    assert (want != 0).sum() > 1000
+    null_describe = type(cam.iface.describe)()          # NULL function pointer
+    cam.obj.contents.iface.contents.describe = null_describe
+    ctx.pixels()[:] = 1
+    ctx.render(); ctx.redraw()
+    assert gpu.last_error() == ""
+    assert np.array_equal(ctx.pixels(), want)
+
+
+def test_pixel_formats_and_texture(gpu, checker, skull, ds, orc):
+    t, o = gpu.Tree.build(skull), checker.tree(skull)
+    w, h = 320, 160
+    pos, look = ds.orbit_pose(100)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    ocam = ds.setup_camera(checker.camera(0), pos, look, 1.2, w, h)
+    tex = np.random.default_rng(1).integers(0, 256, 32768).astype(np.uint8)
+    for amask, loss, shift in ((0, (0, 0, 0), (16, 8, 0)), (0xff000000, (0, 0, 0), (0, 8, 16)), (0, (3, 2, 3), (11, 5, 0))):
+        fmt = gpu.api.GpuPixFmt(amask, *loss, 0, *shift, 0)
+        ofmt = orc.PixFmt(amask, *loss, 0, *shift, 0)
+        pix, _, _ = render_device(gpu, t, cam, w, h, tex, fmt)
+        opix = o.render(ocam, w, h, 0, tex, fmt=ofmt, want_hits=False)
+        assert np.array_equal(pix, opix)
+
+
+def test_collision_detector(gpu, skull):
+    """vox_cd_collide (cd.c:38-55): a move into the skull is undone, a move in free space is kept."""
+    t = gpu.Tree.build(skull)
+    ctx = gpu.Context(64, 16)
+    cam = gpu.Camera()
+    cam.set_position([128, 128, -200])
+    ctx.set_scene(t); ctx.set_camera(cam)
+    r = gpu.libs.rnd
+    cd = r.vox_make_cd()
+    r.vox_cd_attach_camera(cd, cam.h, 3.0)
+    r.vox_cd_attach_context(cd, ctx.h)
+    cam.set_position([128, 128, -150]); r.vox_cd_collide(cd)
+    assert np.array_equal(cam.get_position(), [128, 128, -150])
+    inside = t.export()["dots"][1000]
+    assert t.ball(inside, 3.0) == 1
+    cam.set_position(inside); r.vox_cd_collide(cd)
+    assert np.array_equal(cam.get_position(), [128, 128, -150])
+    r.vox_destroy_cd(cd)
+
+
+# ------------------------------------------------- full-size configs, by properties
+
+def test_c3_full_size_properties(gpu, port, ds):
+    """C3: 16 Mi rays against the ~10 M-voxel random tree.  Too big for the CPU oracle in
+    seconds, so: known voxel count, a 64 Ki-ray oracle sample bit-exact, and size-independent
+    properties on the full batch (hit point on the hit voxel; leaf id is a leaf; determinism)."""
+    vox, _ = ds.random_voxels()
+    assert len(vox) == 10063815
+    t = gpu.Tree.build(vox)
+    ti = t.info()
+    assert (ti.n_inner, ti.n_leaf, ti.n_dense) == (479723, 2096194, 883177)
+    n = 1 << 24
+    o, d = ds.random_rays(n, side=512, start_index=512 ** 3)
+    leaf, pts, voxel = t.rays(o, d)
+    fl = t.export()
+    m = leaf >= 0
+    assert 0.2 < m.mean() <= 1.0
+    kinds = fl["flags"][leaf[m]] & 3
+    assert (kinds != 0).all()
+    lm = m & (voxel >= 0)
+    lo = fl["dots"][voxel[lm]]
+    p = pts[lm]
+    assert ((p >= lo) & (p <= lo + 1)).all()        # the hit point lies on the hit voxel
+    dm = m & (voxel < 0)
+    assert ((pts[dm] >= fl["bb_min"][leaf[dm]]) & (pts[dm] <= fl["bb_max"][leaf[dm]])).all()
+    leaf2, pts2, _ = t.rays(o[: 1 << 20], d[: 1 << 20])
+    assert np.array_equal(leaf2, leaf[: 1 << 20]) and np.array_equal(bits(pts2), bits(pts[: 1 << 20]))
+    # oracle sample (the port builds the same tree in a few seconds)
+    ot = port.tree(vox)
+    k = 1 << 16
+    assert_rays_equal((leaf[:k], pts[:k], voxel[:k]), ot.rays(o[:k], d[:k], threads=THREADS))
+
+
+def test_c4_full_size(gpu, checker, ds, skull):
+    """C4: 4 Mi balls vs the skull tree, whole batch against the oracle (booleans bit-exact)."""
+    t, o = gpu.Tree.build(skull), checker.tree(skull)
+    c, r = ds.random_balls(1 << 22, *t.bounding_box())
+    got = t.balls(c, r)
+    assert np.array_equal(got, o.balls(c, r, threads=THREADS))
+    # monotone in the radius: growing a colliding ball keeps it colliding
+    assert (t.balls(c[:100000], r[:100000] * 2) >= got[:100000]).all()

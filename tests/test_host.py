@@ -1,0 +1,256 @@
+"""Host-side logic of the product, on CPU: the C-ABI libraries load and export
+everything include/*.h declares, the flattened tree builder equals the
+reference's tree, cameras/contexts behave like the reference's, and -- with
+no GPU -- every search fails loudly instead of falling back."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import CROSS, ball_voxels, bits, check_tree_invariants, flat_equal, sha
+
+
+def declared_symbols(vv):
+    """Every VOX_EXPORT / VOXGPU_EXPORT declaration in include/."""
+    names = set()
+    for dirpath, _, files in os.walk(vv.INCLUDE_DIR):
+        for f in files:
+            if not f.endswith(".h"):
+                continue
+            text = open(os.path.join(dirpath, f)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            text = re.sub(r"^\s*#.*$", "", text, flags=re.M)      # preprocessor lines
+            for m in re.finditer(r"VOX(?:GPU)?_EXPORT\s+([^;{]*?);", text, flags=re.S):
+                decl = " ".join(m.group(1).split())
+                fn = re.search(r"(\w+)\s*\(", decl)
+                names.add(fn.group(1) if fn else re.search(r"(\w+)\s*$", decl).group(1))
+    return names
+
+
+def test_libraries_export_every_declared_symbol(vv):
+    names = declared_symbols(vv)
+    assert {"vox_make_tree", "vox_ray_tree_intersection", "vox_tree_ball_collidep", "vox_render",
+            "vox_redraw", "vox_voxel", "voxgpu_render", "voxgpu_rays_device", "voxgpu_balls_device"} <= names
+    exported = set()
+    for lib in ("libvoxgpu.so", "libvoxtrees.so", "libvoxrnd.so"):
+        out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(vv.LIB_DIR, lib)],
+                             capture_output=True, text=True, check=True).stdout
+        exported |= {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = sorted(names - exported)
+    assert not missing, f"declared in include/ but not exported: {missing}"
+    # and they resolve through dlopen as well
+    for n in ("vox_make_tree", "vox_ray_tree_intersection_batch", "vox_tree_ball_collidep_batch"):
+        assert getattr(vv.libs.trees, n)
+    for n in ("vox_render", "vox_redraw", "vox_camera_methods", "vox_cd_collide"):
+        assert getattr(vv.libs.rnd, n)
+    for lib in ("simple-camera.so", "doom-camera.so"):
+        out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(vv.LIB_DIR, lib)],
+                             capture_output=True, text=True, check=True).stdout
+        assert " module_init" in out
+
+
+def test_gpu_code_is_sm100a(vv):
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(vv.LIB_DIR, "libvoxgpu.so")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_builder_equals_oracle(vv, port, skull, bonsai):
+    rng = np.random.default_rng(5)
+    sparse = np.unique(rng.integers(0, 100, (60000, 3)), axis=0).astype(np.float32)
+    rng.shuffle(sparse)
+    cases = {"skull": skull, "bonsai": bonsai, "ball50": ball_voxels(50), "sparse": sparse, "cross": CROSS,
+             "one": CROSS[:1], "seven": CROSS[:7], "eight": CROSS[:8], "line": CROSS[5:13]}
+    for name, vox in cases.items():
+        t, o = vv.Tree.build(vox), port.tree(vox)
+        assert flat_equal(t.export(), o.flatten()) == [], name
+        assert np.array_equal(t.reordered[:, :3], o.reordered_set()), name
+        assert t.voxels() == len(vox)
+        fl = t.export()
+        lo, hi = t.bounding_box()
+        assert np.array_equal(lo, fl["bb_min"][0]) and np.array_equal(hi, fl["bb_max"][0])
+
+
+def test_builder_golden_hashes(vv, golden, skull):
+    """Product builder vs the hashes of the reference's own tree (no oracle library involved)."""
+    meta, _ = golden
+    t = vv.Tree.build(skull)
+    want = meta["trees"]["skull"]
+    for k, v in t.export().items():
+        assert (sha(v) if isinstance(v, np.ndarray) else v) == want[k], k
+    assert sha(np.ascontiguousarray(t.reordered[:, :3])) == want["reordered_sha"]
+    assert check_tree_invariants(vv.Tree.build(ball_voxels(20)).export()) > 100
+
+
+def test_builder_overflow_leaf_and_empty(vv, port):
+    # identical points cannot be separated: one overflowed leaf (tree.c:281-305)
+    dup = np.tile(np.array([[3, 4, 5]], np.float32), (20, 1))
+    t, o = vv.Tree.build(dup), port.tree(dup)
+    fl = t.export()
+    assert flat_equal(fl, o.flatten()) == []
+    assert fl["flags"][0] == 5 and fl["dots_num"][0] == 20
+    # a cluster of duplicates next to ordinary voxels
+    mix = np.concatenate([dup, ball_voxels(4) + 20]).astype(np.float32)
+    assert flat_equal(vv.Tree.build(mix).export(), port.tree(mix).flatten()) == []
+    # n == 0 is the NULL tree (tree.c:251-254)
+    e = vv.Tree.build(np.zeros((0, 3), np.float32))
+    assert e.h is None and e.voxels() == 0
+
+
+def test_builder_nonunit_voxel(vv, port):
+    rng = np.random.default_rng(12)
+    idx = np.unique(rng.integers(-30, 30, (20000, 3)), axis=0)
+    rng.shuffle(idx)
+    size = np.array([0.5, 2.0, 0.25], np.float32)
+    vox = idx.astype(np.float32) * size
+    try:
+        vv.set_voxel_size(*size)
+        port.set_voxel(*size)
+        assert np.array_equal(vv.get_voxel_size(), size)
+        assert flat_equal(vv.Tree.build(vox).export(), port.tree(vox).flatten()) == []
+    finally:
+        vv.set_voxel_size(1, 1, 1)
+        port.set_voxel(1, 1, 1)
+
+
+def test_import_export_roundtrip_and_validation(vv, port):
+    fl = port.tree(ball_voxels(10)).flatten()
+    t = vv.Tree.from_arrays(fl)
+    assert flat_equal(t.export(), fl) == []
+    bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in fl.items()}
+    bad["first_child"][0] += 1
+    with pytest.raises(vv.VoxError):
+        vv.Tree.from_arrays(bad)
+
+
+def test_dense_leaf_tree(vv):
+    box = vv.api._Box()
+    for i, (a, b) in enumerate(((1, 5), (2, 4), (0, 8))):
+        box.min[i], box.max[i] = a, b
+    h = vv.libs.trees.vox_make_dense_leaf(C.byref(box))
+    t = vv.Tree(h)
+    assert t.voxels() == 4 * 2 * 8 and t.export()["flags"][0] == 2
+
+
+@pytest.mark.parametrize("name,kind", [("simple-camera", 0), ("doom-camera", 1)])
+def test_cameras_reference_known_answers_and_oracle(vv, port, name, kind):
+    """tests/tests.c:661-777 on the product cameras, then state parity with the oracle."""
+    cam = vv.Camera(name)
+    cam.set_position([0, 0, 0])
+    cam.set_window_size(100, 100)
+    assert np.allclose(cam.screen2world(50, 50), [0, 1, 0], atol=1e-5)
+    cam.set_rotation([0, 0, math.pi / 2])
+    assert np.allclose(cam.screen2world(50, 50), [-1, 0, 0], atol=1e-5)
+    cam.rotate([0, math.pi / 2, 0])
+    assert np.allclose(cam.screen2world(50, 50), [-1, 0, 0], atol=1e-5)
+    cam.move([0, 1, 0])
+    assert np.allclose(cam.get_position(), [-1, 0, 0], atol=1e-5)
+
+    a, b = vv.Camera(name), port.camera(kind)
+    for c in (a, b):
+        c.set_position([100, -250, 180]); c.set_fov(1.2); c.look_at([128, 128, 128]); c.set_window_size(1920, 1080)
+        c.rotate([0.1, 0.2, 0.3]); c.move([1, 2, 3])
+    sa, sb = a.state(), b.state()
+    sb[10] = 0                      # fov is not part of the device description
+    if kind == 1:
+        sb[6] = 0                   # nor is phi (sin/cos are)
+    assert np.array_equal(bits(sa), bits(sb))
+    for sx, sy in ((0, 0), (100, 200), (1919, 1079), (960, 540)):
+        assert np.array_equal(bits(a.screen2world(sx, sy)), bits(b.screen2world(sx, sy)))
+    # construct_camera(copy) keeps the state (tests.c:765-777)
+    h2 = a.iface.construct_camera(a.h)
+    pos = vv.api.dots4([[0, 0, 0]])
+    C.cast(h2, C.POINTER(vv.api._CameraObj)).contents.iface.contents.get_position(h2, pos.ctypes.data)
+    assert np.array_equal(pos[0, :3], a.get_position())
+
+
+def test_quaternion_known_answer(vv):
+    """tests/tests.c:302-358 quat_mul: (4,1,2,3)*(2,0,2,0) = (4,-4,12,8); rotation keeps the norm."""
+    q1, q2, res = vv.api.dots4([[0, 0, 0]]), vv.api.dots4([[0, 0, 0]]), vv.api.dots4([[0, 0, 0]])
+    q1[0] = (4, 1, 2, 3); q2[0] = (2, 0, 2, 0)
+    vv.libs.rnd.vox_quat_mul(q1.ctypes.data, q2.ctypes.data, res.ctypes.data)
+    assert np.array_equal(res[0], [4, -4, 12, 8])
+    base, v = vv.api.dots4([[0, 0, 0]]), vv.api.dots4([[1, 5, 2]])
+    base[0] = (0.5, 0.5, 0.5, 0.5)
+    vv.libs.rnd.vox_rotate_vector(base.ctypes.data, v.ctypes.data, res.ctypes.data)
+    assert abs(float(res[0, :3] @ res[0, :3]) - 30.0) < 1e-5
+
+
+def test_context_contracts(vv):
+    with pytest.raises(vv.VoxError):
+        vv.Context(1000, 600)          # width % 16 (renderer.c:97-100)
+    with pytest.raises(vv.VoxError):
+        vv.Context(1024, 601)          # height % 4
+    ctx = vv.Context(64, 16)
+    assert ctx.set_quality(vv.QUALITY_BEST) and ctx.set_quality(vv.QUALITY_ADAPTIVE | vv.QUALITY_RAY_MERGE)
+    assert not ctx.set_quality(vv.QUALITY_FAST | vv.QUALITY_RAY_MERGE)   # merge needs ADAPTIVE
+    assert not ctx.set_quality(3) and not ctx.set_quality(12 | 2)
+    f = ctx.pixfmt()
+    s = ctx.h.contents.surface.contents
+    assert (s.w, s.h, s.pitch) == (64, 16, 256)
+    assert vv.libs.rnd.vox_map_rgb(s.format, 0x12, 0x34, 0x56) == 0x123456
+    # a NULL scene renders an all-zero frame without touching the GPU (search.c:22)
+    cam = vv.Camera()
+    ctx.set_camera(cam)
+    ctx.pixels()[:] = 7
+    ctx.render(); ctx.redraw()
+    assert not ctx.pixels().any()
+    tex = ctx.texture()
+    assert tex.shape == (32768,) and tex.min() >= 64
+    ctx.set_texture(np.arange(32768, dtype=np.uint32).astype(np.uint8))
+    assert ctx.texture()[300] == 300 % 256
+
+
+def test_metrics(vv):
+    a, b = vv.api.dots4([[1, 2, 3]]), vv.api.dots4([[4, 0, 3.5]])
+    t = vv.libs.trees
+    assert t.vox_abs_metric(a.ctypes.data, b.ctypes.data) == 5.5
+    assert t.vox_sqr_metric(a.ctypes.data, b.ctypes.data) == 13.25
+    assert t.vox_sqr_norm(a.ctypes.data) == 14.0
+
+
+def test_raw_volume_loader(vv, port, ds, tmp_path, skull):
+    path = str(tmp_path / "skull_like.dat")
+    ds.write_raw_volume("skull", path)
+    t = vv.Tree.from_raw_file(path, (256, 256, 256), 1, 40)
+    assert t.voxels() == len(skull)
+    assert flat_equal(t.export(), port.tree(skull).flatten()) == []
+    with pytest.raises(vv.VoxError, match="Wrong size"):
+        vv.Tree.from_raw_file(path, (256, 256, 255), 1, 40)
+    with pytest.raises(vv.VoxError):
+        vv.Tree.from_raw_file(str(tmp_path / "missing.dat"), (2, 2, 2), 1, 0)
+
+
+def test_no_gpu_means_loud_failure(vv):
+    """The product has no CPU search path: without a device every query raises."""
+    if vv.gpu_available():
+        pytest.skip("a CUDA device is present")
+    t = vv.Tree.build(CROSS)
+    with pytest.raises(vv.VoxError, match="no CUDA device"):
+        t.rays([[0, 0, 9]], [[0, 0, -1]])
+    with pytest.raises(vv.VoxError, match="no CUDA device"):
+        t.balls([[0, 0, 0]], [1.0])
+    with pytest.raises(vv.VoxError, match="no CUDA device"):
+        t.ray([0, 0, 9], [0, 0, -1])
+    with pytest.raises(vv.VoxError, match="no CUDA device"):
+        t.ball([0, 0, 0], 1.0)
+    ctx = vv.Context(64, 16)
+    ctx.set_scene(t); ctx.set_camera(vv.Camera())
+    ctx.render()
+    assert "no CUDA device" in vv.last_error()
+
+
+def test_product_never_touches_the_oracle(vv):
+    """No source file of the product mentions the oracle directory or its API."""
+    root = os.path.dirname(vv.LIB_DIR)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".c", ".h", ".cu", ".cuh", ".py")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "orc_" not in text and "libvoxoracle" not in text and "libvoxref" not in text, f
+                if f.endswith(".py"):
+                    assert "import orc" not in text and "from oracle" not in text, f

@@ -510,7 +510,7 @@ class Camera:
         return g
 
     def state(self):
-        """Same 11 floats as the oracle's orc_camera_get_state (fov is not exposed: 0)."""
+        """POD state as 11 floats: pos[3], quat[4] | (sinphi, cosphi, k, 0), mul, xsub, ysub, 0."""
         d = self.describe()
         s = np.zeros(11, np.float32)
         s[0:3] = d.position[:]
