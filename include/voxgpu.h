@@ -169,6 +169,11 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
                                  uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
                                  voxgpu_stream stream);
 
+/** Development knob: 0 = the first, one-CTA-per-4-tiles render kernel with the
+    plain traversal (kept for A/B measurements), 1 = the persistent kernel with the
+    reorganised traversal (default).  Results are identical. */
+VOXGPU_EXPORT void voxgpu_set_variant (int variant);
+
 /** Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 VOXGPU_EXPORT unsigned long long voxgpu_launch_count (void);
 

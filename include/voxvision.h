@@ -54,8 +54,8 @@ struct vox_box
 #define vox_box_copy(b1, b2) memcpy ((b1), (b2), sizeof (struct vox_box))
 
 /**
-   \brief Text of the last error raised on the calling thread by any voxvision
-   library call (CUDA failures included), or "" if none.
+   \brief Error text of the last query / render call made on the calling thread
+   (CUDA failures included), or "" if that call succeeded.
 
    The reference has no error channel besides NULL / 0 returns
    (SURVEY.md 8b "Error conventions"); those conventions are kept and this

@@ -225,8 +225,8 @@ libs = _Libs()
 
 
 def last_error():
-    e = libs.trees.vox_last_error().decode()
-    return e or libs.gpu.voxgpu_last_error().decode()
+    """Error text of the last voxtrees/voxrnd call on this thread ("" if it succeeded)."""
+    return libs.trees.vox_last_error().decode()
 
 
 def device_count():

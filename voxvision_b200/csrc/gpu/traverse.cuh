@@ -373,3 +373,198 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
 }
 
 #endif
+
+/* ======================================================================
+ * Production traversal.  Same search, same fp32 operations in the same
+ * order as ray_tree<> above (which stays as the instrumented / readable
+ * form and as an on-device cross-check), reorganised after the first ncu
+ * profile (profiles/r01_*):
+ *
+ *  - hit_box only divides on the axes where the origin was clamped.  On an
+ *    unclamped axis the reference computes (o-o)/d = +-0 or NaN, which can
+ *    never become the winning positive distance (geom.c:79-87), so the
+ *    division -- which also fell into the IEEE slow path because of its zero
+ *    numerator, 15% of all issued instructions -- is dropped without changing
+ *    any result, NaN/inf inputs included.
+ *  - the bound checks of hit_box / hit_plane_within_box are evaluated as
+ *    predicates instead of early-exit branches.
+ *  - one loop iteration = "take pending work until there is a call" followed
+ *    by exactly one call, so the lanes of a warp meet at the (expensive) box
+ *    test every iteration instead of drifting between call / pop / expand
+ *    iterations.
+ * ====================================================================== */
+
+__device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3 o, const V3 d, V3 &res)
+{
+    const bool lx = o.x < mn.x, hx = o.x > mx.x;
+    const bool ly = o.y < mn.y, hy = o.y > mx.y;
+    const bool lz = o.z < mn.z, hz = o.z > mx.z;
+    const bool kx = lx | hx, ky = ly | hy, kz = lz | hz;
+    res = o;
+    if (!(kx | ky | kz)) return true;                 /* origin inside: geom.c:73 */
+
+    float cx = lx ? mn.x : (hx ? mx.x : o.x);
+    float cy = ly ? mn.y : (hy ? mx.y : o.y);
+    float cz = lz ? mn.z : (hz ? mx.z : o.z);
+
+    int axis = 0;
+    float tmax = -1.0f;
+    if (kx) { const float t = __fdiv_rn (__fsub_rn (cx, o.x), d.x); if (t > tmax) { tmax = t; axis = 0; } }
+    if (ky) { const float t = __fdiv_rn (__fsub_rn (cy, o.y), d.y); if (t > tmax) { tmax = t; axis = 1; } }
+    if (kz) { const float t = __fdiv_rn (__fsub_rn (cz, o.z), d.z); if (t > tmax) { tmax = t; axis = 2; } }
+
+    const float px = __fadd_rn (o.x, __fmul_rn (tmax, d.x));
+    const float py = __fadd_rn (o.y, __fmul_rn (tmax, d.y));
+    const float pz = __fadd_rn (o.z, __fmul_rn (tmax, d.z));
+    bool ok = tmax > 0.0f;
+    if (axis != 0) { ok &= !(px < mn.x || px > mx.x); cx = px; }
+    if (axis != 1) { ok &= !(py < mn.y || py > mx.y); cy = py; }
+    if (axis != 2) { ok &= !(pz < mn.z || pz > mx.z); cz = pz; }
+    res.x = cx; res.y = cy; res.z = cz;
+    return ok;
+}
+
+/* geom.c:101-123; returns validity, point in res (garbage when invalid) */
+__device__ __forceinline__ bool ray_plane_fast (const V3 o, const V3 d, float plane, float oa, float da,
+                                                const V3 mn, const V3 mx, V3 &res)
+{
+    float k = __fsub_rn (plane, oa);
+    const bool cand = !(k == 0.0f || ((da < 0.0f) != (k < 0.0f)));
+    if (!cand) return false;
+    k = __fdiv_rn (k, da);
+    res.x = __fadd_rn (o.x, __fmul_rn (k, d.x));
+    res.y = __fadd_rn (o.y, __fmul_rn (k, d.y));
+    res.z = __fadd_rn (o.z, __fmul_rn (k, d.z));
+    return !(res.x < mn.x || res.x > mx.x) & !(res.y < mn.y || res.y > mx.y) & !(res.z < mn.z || res.z > mx.z);
+}
+
+__device__ __forceinline__ void ray_tree_fast (const TreeRef &tr, unsigned start, const V3 origin, const V3 d,
+                                               float4 *stack, RayResult &out)
+{
+    int sp = 0;
+    unsigned cur = start;
+    V3 org = origin;
+    bool have_call = true;
+
+    out.leaf = -1;
+    out.voxel = -1;
+
+    for (;;)
+    {
+        /* ---- pending work until there is a call to make ---- */
+        while (!have_call)
+        {
+            if (sp == 0) return;
+            const float4 e = stack[--sp];
+            const unsigned tag = __float_as_uint (e.w);
+            org.x = e.x; org.y = e.y; org.z = e.z;
+            if (!(tag & VOXGPU_EXPAND_BIT)) { cur = tag; have_call = true; break; }
+
+            /* search.c:99-148: the first child missed; evaluate the dividing planes */
+            const unsigned id = tag & ~VOXGPU_EXPAND_BIT;
+            const float4 q0 = __ldg (tr.nodes + 3*(size_t)id);
+            const float4 q1 = __ldg (tr.nodes + 3*(size_t)id + 1);
+            const float4 q2 = __ldg (tr.nodes + 3*(size_t)id + 2);
+            const V3 mn = v3 (q0), mx = v3 (q1), c = v3 (q2);
+            const unsigned mask = (__float_as_uint (q0.w) >> 8) & 0xffu;
+            const unsigned first = __float_as_uint (q1.w);
+
+            V3 p0, p1, p2;
+            const bool v0 = ray_plane_fast (org, d, c.x, org.x, d.x, mn, mx, p0);
+            const bool v1 = ray_plane_fast (org, d, c.y, org.y, d.y, mn, mx, p1);
+            const bool v2 = ray_plane_fast (org, d, c.z, org.z, d.z, mn, mx, p2);
+            /* compact the valid ones in axis order 0,1,2 (search.c:108-113) into slots A,B,C
+               (explicit selects: no dynamically indexed arrays, nothing spills to local memory) */
+            const int n = (int) v0 + (int) v1 + (int) v2;
+            if (n == 0) continue;
+            const float m0 = l1_metric (org, p0), m1 = l1_metric (org, p1), m2 = l1_metric (org, p2);
+            V3 pa, pb, pc = p2;
+            float ma, mb, mc = m2;
+            unsigned aa, ab, ac = 2u;
+            if (v0) { pa = p0; ma = m0; aa = 0u; } else if (v1) { pa = p1; ma = m1; aa = 1u; } else { pa = p2; ma = m2; aa = 2u; }
+            if (v0 & v1) { pb = p1; mb = m1; ab = 1u; } else { pb = p2; mb = m2; ab = 2u; }
+            /* search.c:115-134: selection sort, strict <, swap semantics */
+#define VOXGPU_SWAP(P, M, A, Q, N, B) do { V3 tp = P; P = Q; Q = tp; float tm = M; M = N; N = tm; \
+                                           unsigned ta = A; A = B; B = ta; } while (0)
+            if (n >= 2 && mb < ma) VOXGPU_SWAP (pa, ma, aa, pb, mb, ab);
+            if (n == 3)
+            {
+                if (mc < ma) VOXGPU_SWAP (pa, ma, aa, pc, mc, ac);
+                if (mc < mb) VOXGPU_SWAP (pb, mb, ab, pc, mc, ac);
+            }
+#undef VOXGPU_SWAP
+            const unsigned sub = subspace_corrected (c, org, d);
+            const unsigned s0 = sub ^ (1u << aa);
+            const unsigned s1 = (n > 1) ? s0 ^ (1u << ab) : 8u;
+            const unsigned s2 = (n > 2) ? s1 ^ (1u << ac) : 8u;
+            const bool e0 = (mask >> s0) & 1u, e1 = (mask >> s1) & 1u, e2 = (mask >> s2) & 1u;   /* mask has 8 bits: s=8 -> 0 */
+            /* nearest existing child is called now, the others wait on the stack (farthest deepest) */
+            if (e2 && (e0 | e1))
+                stack[sp++] = make_float4 (pc.x, pc.y, pc.z, __uint_as_float (child_id (first, mask, s2)));
+            if (e1 && e0)
+                stack[sp++] = make_float4 (pb.x, pb.y, pb.z, __uint_as_float (child_id (first, mask, s1)));
+            if (e0)      { cur = child_id (first, mask, s0); org = pa; have_call = true; }
+            else if (e1) { cur = child_id (first, mask, s1); org = pb; have_call = true; }
+            else if (e2) { cur = child_id (first, mask, s2); org = pc; have_call = true; }
+        }
+
+        /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
+        have_call = false;
+        const float4 q0 = __ldg (tr.nodes + 3*(size_t)cur);
+        const float4 q1 = __ldg (tr.nodes + 3*(size_t)cur + 1);
+        const unsigned meta = __float_as_uint (q0.w);
+        const unsigned link = __float_as_uint (q1.w);
+        const unsigned kind = meta & 3u;
+
+        V3 entry;
+        if (!ray_box_fast (v3 (q0), v3 (q1), org, d, entry)) continue;
+
+        if (kind == VOXGPU_KIND_INNER)
+        {
+            const float4 q2 = __ldg (tr.nodes + 3*(size_t)cur + 2);
+            const unsigned mask = (meta >> 8) & 0xffu;
+            const unsigned sub = subspace_corrected (v3 (q2), entry, d);
+            stack[sp++] = make_float4 (entry.x, entry.y, entry.z, __uint_as_float (cur | VOXGPU_EXPAND_BIT));
+            if (mask & (1u << sub))
+            {
+                cur = child_id (link, mask, sub);
+                org = entry;
+                have_call = true;
+            }
+            continue;
+        }
+        if (kind == VOXGPU_KIND_DENSE)
+        {
+            out.leaf = (int) cur; out.voxel = -1; out.point = entry;
+            return;
+        }
+        /* leaf, search.c:39-81 */
+        {
+            const unsigned n = meta >> 2;
+            float closest = __int_as_float (0x7f800000);
+            for (unsigned i=0; i<n; i++)
+            {
+                const float4 dq = __ldg (tr.dots + (size_t)link + i);
+                V3 vmin = v3 (dq), vmax, far;
+                vmax.x = __fadd_rn (vmin.x, tr.vx);
+                vmax.y = __fadd_rn (vmin.y, tr.vy);
+                vmax.z = __fadd_rn (vmin.z, tr.vz);
+                if (ray_box_fast (vmin, vmax, entry, d, far))
+                {
+                    const float dist = l1_metric (entry, far);
+                    if (dist == 0.0f)
+                    {
+                        out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
+                        return;
+                    }
+                    if (dist < closest)
+                    {
+                        closest = dist;
+                        out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
+                    }
+                }
+            }
+            if (out.leaf >= 0) return;
+        }
+    }
+}

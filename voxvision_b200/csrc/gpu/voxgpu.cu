@@ -263,7 +263,8 @@ k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const f
     const float4 o = __ldg (origins + i), d = __ldg (dirs + i);
     RayResult r;
     RayCounters c = {0, 0, 0, 0, 0, 0, 0};
-    ray_tree<STATS> (tr, start, v3 (o), v3 (d), stack, r, &c);
+    if (STATS) ray_tree<true> (tr, start, v3 (o), v3 (d), stack, r, &c);
+    else ray_tree_fast (tr, start, v3 (o), v3 (d), stack, r);
     if (leaf_ids) leaf_ids[i] = r.leaf;
     if (voxels) voxels[i] = r.voxel;
     if (points && r.leaf >= 0) points[i] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
@@ -517,6 +518,88 @@ k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restri
     }
 }
 
+/*
+ * Persistent form of K1 (the one voxgpu_render launches).  80% of the 8x4 tiles
+ * of a typical frame miss the root box and finish in a few hundred cycles; with
+ * one CTA per 4 tiles the SMs spent a third of the kernel waiting for CTA
+ * launches (profiles/r01_*).  Here the grid is sized to the resident capacity
+ * of the GPU and every warp pulls tile indices from a global counter until the
+ * frame is done.  The counter resets itself: the last warp to leave zeroes it,
+ * so no memset precedes the launch.
+ */
+template <bool OUT_HITS>
+__global__ void __launch_bounds__(RENDER_BLOCK)
+k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
+                     unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
+                     unsigned *counters)
+{
+    const int tiles_x = fr.w >> 3;
+    const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
+    const int lane = threadIdx.x & 31;
+    const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
+    float4 stack[VOXGPU_RAY_STACK];
+    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
+
+    for (;;)
+    {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd (&counters[0], 1u);
+        tile = __shfl_sync (0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+
+        const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
+        const int ry = (int) (tile / tiles_x) * 4 + (lane >> 3);
+        const int sy = fr.y0 + ry;
+        const V3 dir = screen2world (cam, sx, sy, fr.w);
+        RayResult r;
+        ray_tree_fast (tr, 0, origin, dir, stack, r);
+
+        unsigned color = 0;
+        if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+        pixels[(size_t) ry * fr.pitch + sx] = color;
+        if (OUT_HITS)
+        {
+            const size_t pos = (size_t) ry * fr.w + sx;
+            if (leaf_ids) leaf_ids[pos] = r.leaf;
+            if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+        }
+        __syncwarp ();
+    }
+    if (lane == 0)
+    {
+        const unsigned done = atomicAdd (&counters[1], 1u);
+        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
+    }
+}
+
+/* Per-device pool of self-resetting tile counters; launches rotate through the
+   slots so that renders in flight on different streams never share one. */
+#define COUNTER_SLOTS 64
+static unsigned *g_counters[64] = {0};
+static int g_render_blocks[64][2] = {{0}};
+static std::atomic<unsigned> g_counter_seq{0};
+static int g_variant = 1;
+
+extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
+
+static unsigned* counter_slot (int device)
+{
+    if (!g_counters[device])
+    {
+        unsigned *p = NULL;
+        if (cudaMalloc (&p, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
+        if (cudaMemset (p, 0, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
+        int sms = 0, b0 = 0, b1 = 0;
+        cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true>, RENDER_BLOCK, 0);
+        g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
+        g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
+        g_counters[device] = p;
+    }
+    return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
+}
+
 extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                               const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                               voxgpu_stream s)
@@ -544,10 +627,25 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
 
     const int ntiles = (df.w >> 3) * (df.rows >> 2);
     const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
-    if (d_leaf || d_pts)
-        k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
+    if (g_variant == 0)
+    {
+        if (d_leaf || d_pts)
+            k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
+        else
+            k_render<false><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL);
+    }
     else
-        k_render<false><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL);
+    {
+        unsigned *counters = counter_slot (t->device);
+        if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
+        const bool hits = d_leaf || d_pts;
+        int grid = g_render_blocks[t->device][hits ? 1 : 0];
+        if (grid > blocks) grid = blocks;
+        if (hits)
+            k_render_persistent<true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        else
+            k_render_persistent<false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+    }
     g_launches++;
     CU (cudaGetLastError ());
     return 0;

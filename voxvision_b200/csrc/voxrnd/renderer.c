@@ -178,6 +178,7 @@ void vox_render (struct vox_rnd_ctx *pub)
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
     SDL_Surface *s = pub->surface;
     ctx->timed = 0;
+    vox_set_error ("");
     if (!pub->camera) { vox_set_error ("vox_render: no camera"); return; }
     if (!pub->scene)
     {

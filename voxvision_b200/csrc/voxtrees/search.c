@@ -51,6 +51,7 @@ const struct vox_node*
 vox_ray_tree_intersection (const struct vox_node *tree, const vox_dot origin,
                            const vox_dot dir, vox_dot res)
 {
+    vox_set_error ("");
     if (!tree) return NULL;   /* search.c:22: an empty tree is never hit */
     if (!vox_node_valid (tree)) { vox_set_error ("vox_ray_tree_intersection: not a live tree"); return NULL; }
     voxgpu_tree *dev = vox_store_device (tree->store);
@@ -71,6 +72,7 @@ vox_ray_tree_intersection (const struct vox_node *tree, const vox_dot origin,
 
 int vox_tree_ball_collidep (const struct vox_node *tree, const vox_dot center, float radius)
 {
+    vox_set_error ("");
     if (!tree) return 0;      /* search.c:158 */
     if (!vox_node_valid (tree)) { vox_set_error ("vox_tree_ball_collidep: not a live tree"); return 0; }
     if (tree->id != 0) { vox_set_error ("vox_tree_ball_collidep: only whole trees are supported"); return 0; }
@@ -91,6 +93,7 @@ long vox_ray_tree_intersection_batch (const struct vox_node *tree,
                                       const vox_dot *origins, const vox_dot *dirs,
                                       size_t n, int32_t *leaf_ids, vox_dot *points, int32_t *voxels)
 {
+    vox_set_error ("");
     if (!tree)
     {
         if (leaf_ids) for (size_t i=0; i<n; i++) leaf_ids[i] = -1;
@@ -113,6 +116,7 @@ long vox_ray_tree_intersection_batch (const struct vox_node *tree,
 long vox_tree_ball_collidep_batch (const struct vox_node *tree, const vox_dot *centers,
                                    const float *radii, size_t n, uint8_t *out)
 {
+    vox_set_error ("");
     if (!tree) { memset (out, 0, n); return 0; }
     if (!vox_node_valid (tree) || tree->id != 0)
     { vox_set_error ("vox_tree_ball_collidep_batch: not a live whole tree"); return -1; }
