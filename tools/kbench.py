@@ -1,6 +1,10 @@
 #!/usr/bin/env python
-"""Kernel A/B harness: for each variant, render C2 frames into device memory,
-check them against the golden digests, and print CUDA-event kernel times."""
+"""Kernel A/B harness: for each variant, render the eight golden C2 frames,
+check them against the golden digests, and print CUDA-event kernel times with
+the frame going (a) to device memory and (b) to mapped pinned host memory.
+
+    python tools/kbench.py [variant ...]      variants: see voxgpu_set_variant
+"""
 import ctypes as C
 import json
 import hashlib
@@ -17,7 +21,7 @@ from tools import datasets as ds
 W, H = 1920, 1080
 sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 gold = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "golden.json")))
-variants = [int(a) for a in sys.argv[1:]] or [0, 1]
+variants = [int(a) for a in sys.argv[1:]] or [1]
 g = api.libs.gpu
 g.voxgpu_set_variant.argtypes = [C.c_int]
 tree = vv.Tree.build(ds.volume_voxels("skull"))
@@ -27,13 +31,26 @@ d_tex = vv.DeviceBuffer.from_array(ctx.texture())
 d_pix = vv.DeviceBuffer(W * H * 4)
 d_leaf = vv.DeviceBuffer(W * H * 4)
 d_pts = vv.DeviceBuffer(W * H * 16)
+h_pix = g.voxgpu_host_alloc(W * H * 4)
+m_pix = g.voxgpu_host_device_pointer(h_pix)
+h_view = np.ctypeslib.as_array(C.cast(h_pix, C.POINTER(C.c_uint32)), (H, W))
 cam = vv.Camera()
 fr = api.GpuFrame(W, H, 0, H, W, 0, ctx.pixfmt())
 t = vv.Timer()
 frames = sorted(int(k) for k in gold["c2"])
+
+
+def timed(gc, target, reps=9):
+    ms = []
+    for _ in range(reps):
+        t.start(); g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, target, None, None, None); t.stop()
+        ms.append(t.elapsed_ms())
+    return sorted(ms)
+
+
 for v in variants:
     g.voxgpu_set_variant(v)
-    total = 0.0
+    tot_d = tot_m = 0.0
     for f in frames:
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
         gc = cam.gpu_camera()
@@ -42,13 +59,16 @@ for v in variants:
         pix = d_pix.download(np.uint32, (H, W))
         want = gold["c2"][str(f)]
         m = leaf >= 0
-        ok = (sha(leaf) == want["leaf_sha"], sha(pts[m]) == want["hit_sha"], sha(pix) == want["pix_sha"])
-        ms = []
-        for _ in range(7):
-            t.start(); g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None); t.stop()
-            ms.append(t.elapsed_ms())
-        pix2 = d_pix.download(np.uint32, (H, W))
-        ok += (sha(pix2) == want["pix_sha"],)
-        total += min(ms)
-        print(f"variant {v} frame {f:3d} parity {ok} hits {int(m.sum())} ms min {min(ms):.4f} med {sorted(ms)[3]:.4f}", flush=True)
-    print(f"variant {v}: mean of per-frame minima {total/len(frames):.4f} ms -> {W*H/(total/len(frames))/1e3:.0f} Mrays/s", flush=True)
+        ok = [sha(leaf) == want["leaf_sha"], sha(pts[m]) == want["hit_sha"], sha(pix) == want["pix_sha"]]
+        md = timed(gc, d_pix.ptr)
+        ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
+        h_view[:] = 0xdeadbeef
+        mm = timed(gc, m_pix)
+        g.voxgpu_synchronize(None)
+        ok.append(sha(h_view) == want["pix_sha"])
+        tot_d += md[len(md) // 2]; tot_m += mm[len(mm) // 2]
+        print(f"variant {v} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
+              f"device min {md[0]:.4f} med {md[len(md)//2]:.4f} | mapped min {mm[0]:.4f} med {mm[len(mm)//2]:.4f} ms", flush=True)
+    n = len(frames)
+    print(f"variant {v}: mean of per-frame medians: device {tot_d/n:.4f} ms -> {W*H/(tot_d/n)/1e3:.0f} Mrays/s | "
+          f"mapped {tot_m/n:.4f} ms -> {W*H/(tot_m/n)/1e3:.0f} Mrays/s", flush=True)

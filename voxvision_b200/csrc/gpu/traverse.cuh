@@ -10,16 +10,19 @@
  * choice and hit points are bit-identical to the scalar reference build
  * compiled with -ffp-contract=off.
  *
- * Device tree layout (built by voxgpu_tree_upload):
- *   nodes[3*id+0] = { bb_min.xyz , meta }   meta: bits 0-1 kind (0 inner, 1 leaf, 2 dense leaf)
- *                                                  inner: bits 8-15 child mask
- *                                                  leaf : bits 2-31 number of dots
- *   nodes[3*id+1] = { bb_max.xyz , link }   inner: id of first non-NULL child (children are
- *                                                  consecutive, in subspace order)
- *                                            leaf : index of first dot in dots[]
- *   nodes[3*id+2] = { center.xyz , 0    }   inner only
- *   dots[i]       = { voxel min corner xyz, 0 }
- * Records are 48 B, 16-byte aligned: a node visit is two or three LDG.128.
+ * Device tree layout (built by voxgpu_tree_upload), node ids
+ * are breadth-first positions:
+ *   rec[id] (32 B, 32-byte aligned = one L2 sector, fetched by ONE 256-bit load,
+ *            LDG.E.256 -- sm_100 only):
+ *        lo = { bb_min.xyz , meta }   meta: bits 0-1 kind (0 inner, 1 leaf, 2 dense leaf)
+ *                                           inner: bits 8-15 child mask
+ *                                           leaf : bits 2-31 number of dots
+ *        hi = { bb_max.xyz , link }   inner: id of first non-NULL child (children are
+ *                                           consecutive, in subspace order)
+ *                                     leaf : index of first dot in dots[]
+ *   ctr[id]  = { center.xyz , 0 }     inner nodes only (16 B, one LDG.128)
+ *   dots[i]  = { voxel min corner xyz, 0 }
+ * Every node visit reads exactly one sector; an inner node adds half a sector.
  *
  * The recursion is turned into a stack of pending calls.  search.c returns as
  * soon as any recursive call hits, so a miss only ever means "go on with the
@@ -41,7 +44,7 @@
 #define VOXGPU_KIND_DENSE 2u
 
 #define VOXGPU_MAX_DEPTH 32                      /* root alone = 1 */
-#define VOXGPU_RAY_STACK (2*VOXGPU_MAX_DEPTH)    /* <= 2 pending entries per level */
+#define VOXGPU_RAY_STACK (3*VOXGPU_MAX_DEPTH)    /* <= 3 pending entries per level (eager form; the lazy form needs 2) */
 #define VOXGPU_BALL_STACK (7*VOXGPU_MAX_DEPTH+8) /* <= 7 pending siblings per level */
 #define VOXGPU_EXPAND_BIT 0x80000000u
 
@@ -50,12 +53,23 @@ struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3 (float4 q) { V3 r; r.x = q.x; r.y = q.y; r.z = q.z; return r; }
 __device__ __forceinline__ float comp (const V3 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
+struct __align__(32) NodeRec { float4 lo, hi; };
+
 struct TreeRef
 {
-    const float4 *nodes;
+    const NodeRec *rec;
+    const float4 *ctr;
     const float4 *dots;
     float vx, vy, vz;       /* vox_voxel captured at upload */
 };
+
+/* one 32-byte node record with a single 256-bit read-only load */
+__device__ __forceinline__ void load_rec (const NodeRec *p, float4 &lo, float4 &hi)
+{
+    asm ("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+         : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+         : "l"(p));
+}
 
 struct RayResult
 {
@@ -182,9 +196,9 @@ __device__ __forceinline__ void ray_tree (const TreeRef &tr, unsigned start, con
             {
                 /* search.c:99-148: first child missed; evaluate the dividing planes */
                 const unsigned id = tag & ~VOXGPU_EXPAND_BIT;
-                const float4 q0 = __ldg (tr.nodes + 3*(size_t)id);
-                const float4 q1 = __ldg (tr.nodes + 3*(size_t)id + 1);
-                const float4 q2 = __ldg (tr.nodes + 3*(size_t)id + 2);
+                float4 q0, q1;
+                load_rec (tr.rec + id, q0, q1);
+                const float4 q2 = __ldg (tr.ctr + id);
                 const V3 mn = v3 (q0), mx = v3 (q1), c = v3 (q2);
                 const unsigned mask = (__float_as_uint (q0.w) >> 8) & 0xffu;
                 const unsigned first = __float_as_uint (q1.w);
@@ -233,8 +247,8 @@ __device__ __forceinline__ void ray_tree (const TreeRef &tr, unsigned start, con
 
         /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
         have_call = false;
-        const float4 q0 = __ldg (tr.nodes + 3*(size_t)cur);
-        const float4 q1 = __ldg (tr.nodes + 3*(size_t)cur + 1);
+        float4 q0, q1;
+        load_rec (tr.rec + cur, q0, q1);
         const unsigned meta = __float_as_uint (q0.w);
         const unsigned link = __float_as_uint (q1.w);
         const unsigned kind = meta & 3u;
@@ -286,7 +300,7 @@ __device__ __forceinline__ void ray_tree (const TreeRef &tr, unsigned start, con
         /* inner node, search.c:83-97 */
         {
             if (STATS) cnt->inner++;
-            const float4 q2 = __ldg (tr.nodes + 3*(size_t)cur + 2);
+            const float4 q2 = __ldg (tr.ctr + cur);
             const unsigned mask = (meta >> 8) & 0xffu;
             const unsigned sub = subspace_corrected (v3 (q2), entry, d);
             float4 e;
@@ -328,16 +342,16 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
     const float rr = __fmul_rn (radius, radius);
     int sp = 0;
     {
-        const float4 q0 = __ldg (tr.nodes + 3*(size_t)start);
-        const float4 q1 = __ldg (tr.nodes + 3*(size_t)start + 1);
+        float4 q0, q1;
+        load_rec (tr.rec + start, q0, q1);
         if (!box_ball (v3 (q0), v3 (q1), c, rr)) return false;
         stack[sp++] = start;
     }
     while (sp > 0)
     {
         const unsigned id = stack[--sp];
-        const float4 q0 = __ldg (tr.nodes + 3*(size_t)id);
-        const float4 q1 = __ldg (tr.nodes + 3*(size_t)id + 1);
+        float4 q0, q1;
+        load_rec (tr.rec + id, q0, q1);
         const unsigned meta = __float_as_uint (q0.w);
         const unsigned link = __float_as_uint (q1.w);
         const unsigned kind = meta & 3u;
@@ -360,8 +374,8 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
         for (int j=nchild-1; j>=0; j--)
         {
             const unsigned ch = link + j;
-            const float4 c0 = __ldg (tr.nodes + 3*(size_t)ch);
-            const float4 c1 = __ldg (tr.nodes + 3*(size_t)ch + 1);
+            float4 c0, c1;
+            load_rec (tr.rec + ch, c0, c1);
             if (box_ball (v3 (c0), v3 (c1), c, rr))
             {
                 if ((__float_as_uint (c0.w) & 3u) == VOXGPU_KIND_DENSE) return true;
@@ -375,23 +389,34 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
 #endif
 
 /* ======================================================================
- * Production traversal.  Same search, same fp32 operations in the same
- * order as ray_tree<> above (which stays as the instrumented / readable
- * form and as an on-device cross-check), reorganised after the first ncu
- * profile (profiles/r01_*):
+ * Production traversal.  Same search, same fp32 operations on the same
+ * operands as ray_tree<> above (which stays as the readable, instrumented
+ * form that mirrors the reference's control flow one to one), reorganised
+ * around what the ncu profiles showed (profiles/r01_*): the kernel is bound
+ * by instruction issue at ~14 of 32 lanes active, not by memory.
  *
- *  - hit_box only divides on the axes where the origin was clamped.  On an
- *    unclamped axis the reference computes (o-o)/d = +-0 or NaN, which can
- *    never become the winning positive distance (geom.c:79-87), so the
- *    division -- which also fell into the IEEE slow path because of its zero
- *    numerator, 15% of all issued instructions -- is dropped without changing
- *    any result, NaN/inf inputs included.
- *  - the bound checks of hit_box / hit_plane_within_box are evaluated as
- *    predicates instead of early-exit branches.
- *  - one loop iteration = "take pending work until there is a call" followed
- *    by exactly one call, so the lanes of a warp meet at the (expensive) box
- *    test every iteration instead of drifting between call / pop / expand
- *    iterations.
+ *  - EAGER EXPANSION.  The reference evaluates an inner node's dividing
+ *    planes only after the search of the first child has missed
+ *    (search.c:99-148).  Whether and where the ray crosses them is a pure
+ *    function of (node, entry point, direction), so it can be computed when
+ *    the node is visited -- while all lanes of the warp are at "a node" --
+ *    and the resulting calls (child, plane hit point) parked on the stack in
+ *    the reference's order.  A warp then has ONE convergence point per
+ *    iteration (visit a node) instead of alternating call / pop / expand
+ *    phases that each ran at 12-19 lanes; the node record is not re-read and
+ *    the entry point is not stacked.  Work the reference would have skipped
+ *    (planes of nodes whose first child hits) costs thread-instructions but
+ *    no warp-instructions.
+ *  - The selection sort of search.c:115-134 is evaluated as a rank
+ *    computation on four comparisons and the pending calls are scattered to
+ *    their stack slots; nothing is moved between registers.  (Checked
+ *    exhaustively against the swap sequence, ties included.)
+ *  - hit_box divides only where the origin was clamped: on an unclamped axis
+ *    the reference computes (o-o)/d = +-0 or NaN, which can never become the
+ *    winning positive distance (geom.c:79-87).  Divisions are issued
+ *    unconditionally on a harmless numerator instead of under a branch, so the
+ *    three of a box test (and of the three planes) overlap.
+ *  - bound checks are predicates, not early-exit branches.
  * ====================================================================== */
 
 __device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3 o, const V3 d, V3 &res)
@@ -407,11 +432,15 @@ __device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3
     float cy = ly ? mn.y : (hy ? mx.y : o.y);
     float cz = lz ? mn.z : (hz ? mx.z : o.z);
 
+    /* numerator 1 on unclamped axes: 0/d would take the division's slow path */
+    const float tx = __fdiv_rn (kx ? __fsub_rn (cx, o.x) : 1.0f, d.x);
+    const float ty = __fdiv_rn (ky ? __fsub_rn (cy, o.y) : 1.0f, d.y);
+    const float tz = __fdiv_rn (kz ? __fsub_rn (cz, o.z) : 1.0f, d.z);
     int axis = 0;
     float tmax = -1.0f;
-    if (kx) { const float t = __fdiv_rn (__fsub_rn (cx, o.x), d.x); if (t > tmax) { tmax = t; axis = 0; } }
-    if (ky) { const float t = __fdiv_rn (__fsub_rn (cy, o.y), d.y); if (t > tmax) { tmax = t; axis = 1; } }
-    if (kz) { const float t = __fdiv_rn (__fsub_rn (cz, o.z), d.z); if (t > tmax) { tmax = t; axis = 2; } }
+    if (kx && tx > tmax) { tmax = tx; }
+    if (ky && ty > tmax) { tmax = ty; axis = 1; }
+    if (kz && tz > tmax) { tmax = tz; axis = 2; }
 
     const float px = __fadd_rn (o.x, __fmul_rn (tmax, d.x));
     const float py = __fadd_rn (o.y, __fmul_rn (tmax, d.y));
@@ -424,147 +453,142 @@ __device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3
     return ok;
 }
 
-/* geom.c:101-123; returns validity, point in res (garbage when invalid) */
-__device__ __forceinline__ bool ray_plane_fast (const V3 o, const V3 d, float plane, float oa, float da,
+/* geom.c:101-123; `neg` = (direction component < 0).  Returns validity, point in res. */
+__device__ __forceinline__ bool ray_plane_fast (const V3 o, const V3 d, float plane, float oa, float da, bool neg,
                                                 const V3 mn, const V3 mx, V3 &res)
 {
     float k = __fsub_rn (plane, oa);
-    const bool cand = !(k == 0.0f || ((da < 0.0f) != (k < 0.0f)));
-    if (!cand) return false;
-    k = __fdiv_rn (k, da);
+    const bool cand = !(k == 0.0f) && (neg == (k < 0.0f));
+    k = __fdiv_rn (cand ? k : 1.0f, da);
     res.x = __fadd_rn (o.x, __fmul_rn (k, d.x));
     res.y = __fadd_rn (o.y, __fmul_rn (k, d.y));
     res.z = __fadd_rn (o.z, __fmul_rn (k, d.z));
-    return !(res.x < mn.x || res.x > mx.x) & !(res.y < mn.y || res.y > mx.y) & !(res.z < mn.z || res.z > mx.z);
+    return cand & !(res.x < mn.x || res.x > mx.x) & !(res.y < mn.y || res.y > mx.y) & !(res.z < mn.z || res.z > mx.z);
+}
+
+/* geom.c:53-65 with the direction signs hoisted out of the loop */
+__device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool nx, bool ny, bool nz)
+{
+    const bool bx = (c.x > p.x) || (nx && c.x == p.x);
+    const bool by = (c.y > p.y) || (ny && c.y == p.y);
+    const bool bz = (c.z > p.z) || (nz && c.z == p.z);
+    return (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
 }
 
 __device__ __forceinline__ void ray_tree_fast (const TreeRef &tr, unsigned start, const V3 origin, const V3 d,
                                                float4 *stack, RayResult &out)
 {
+    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
     int sp = 0;
     unsigned cur = start;
     V3 org = origin;
-    bool have_call = true;
 
     out.leaf = -1;
     out.voxel = -1;
 
     for (;;)
     {
-        /* ---- pending work until there is a call to make ---- */
-        while (!have_call)
-        {
-            if (sp == 0) return;
-            const float4 e = stack[--sp];
-            const unsigned tag = __float_as_uint (e.w);
-            org.x = e.x; org.y = e.y; org.z = e.z;
-            if (!(tag & VOXGPU_EXPAND_BIT)) { cur = tag; have_call = true; break; }
-
-            /* search.c:99-148: the first child missed; evaluate the dividing planes */
-            const unsigned id = tag & ~VOXGPU_EXPAND_BIT;
-            const float4 q0 = __ldg (tr.nodes + 3*(size_t)id);
-            const float4 q1 = __ldg (tr.nodes + 3*(size_t)id + 1);
-            const float4 q2 = __ldg (tr.nodes + 3*(size_t)id + 2);
-            const V3 mn = v3 (q0), mx = v3 (q1), c = v3 (q2);
-            const unsigned mask = (__float_as_uint (q0.w) >> 8) & 0xffu;
-            const unsigned first = __float_as_uint (q1.w);
-
-            V3 p0, p1, p2;
-            const bool v0 = ray_plane_fast (org, d, c.x, org.x, d.x, mn, mx, p0);
-            const bool v1 = ray_plane_fast (org, d, c.y, org.y, d.y, mn, mx, p1);
-            const bool v2 = ray_plane_fast (org, d, c.z, org.z, d.z, mn, mx, p2);
-            /* compact the valid ones in axis order 0,1,2 (search.c:108-113) into slots A,B,C
-               (explicit selects: no dynamically indexed arrays, nothing spills to local memory) */
-            const int n = (int) v0 + (int) v1 + (int) v2;
-            if (n == 0) continue;
-            const float m0 = l1_metric (org, p0), m1 = l1_metric (org, p1), m2 = l1_metric (org, p2);
-            V3 pa, pb, pc = p2;
-            float ma, mb, mc = m2;
-            unsigned aa, ab, ac = 2u;
-            if (v0) { pa = p0; ma = m0; aa = 0u; } else if (v1) { pa = p1; ma = m1; aa = 1u; } else { pa = p2; ma = m2; aa = 2u; }
-            if (v0 & v1) { pb = p1; mb = m1; ab = 1u; } else { pb = p2; mb = m2; ab = 2u; }
-            /* search.c:115-134: selection sort, strict <, swap semantics */
-#define VOXGPU_SWAP(P, M, A, Q, N, B) do { V3 tp = P; P = Q; Q = tp; float tm = M; M = N; N = tm; \
-                                           unsigned ta = A; A = B; B = ta; } while (0)
-            if (n >= 2 && mb < ma) VOXGPU_SWAP (pa, ma, aa, pb, mb, ab);
-            if (n == 3)
-            {
-                if (mc < ma) VOXGPU_SWAP (pa, ma, aa, pc, mc, ac);
-                if (mc < mb) VOXGPU_SWAP (pb, mb, ab, pc, mc, ac);
-            }
-#undef VOXGPU_SWAP
-            const unsigned sub = subspace_corrected (c, org, d);
-            const unsigned s0 = sub ^ (1u << aa);
-            const unsigned s1 = (n > 1) ? s0 ^ (1u << ab) : 8u;
-            const unsigned s2 = (n > 2) ? s1 ^ (1u << ac) : 8u;
-            const bool e0 = (mask >> s0) & 1u, e1 = (mask >> s1) & 1u, e2 = (mask >> s2) & 1u;   /* mask has 8 bits: s=8 -> 0 */
-            /* nearest existing child is called now, the others wait on the stack (farthest deepest) */
-            if (e2 && (e0 | e1))
-                stack[sp++] = make_float4 (pc.x, pc.y, pc.z, __uint_as_float (child_id (first, mask, s2)));
-            if (e1 && e0)
-                stack[sp++] = make_float4 (pb.x, pb.y, pb.z, __uint_as_float (child_id (first, mask, s1)));
-            if (e0)      { cur = child_id (first, mask, s0); org = pa; have_call = true; }
-            else if (e1) { cur = child_id (first, mask, s1); org = pb; have_call = true; }
-            else if (e2) { cur = child_id (first, mask, s2); org = pc; have_call = true; }
-        }
-
         /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
-        have_call = false;
-        const float4 q0 = __ldg (tr.nodes + 3*(size_t)cur);
-        const float4 q1 = __ldg (tr.nodes + 3*(size_t)cur + 1);
+        float4 q0, q1;
+        load_rec (tr.rec + cur, q0, q1);
         const unsigned meta = __float_as_uint (q0.w);
         const unsigned link = __float_as_uint (q1.w);
         const unsigned kind = meta & 3u;
+        const V3 mn = v3 (q0), mx = v3 (q1);
+        bool descend = false;
 
         V3 entry;
-        if (!ray_box_fast (v3 (q0), v3 (q1), org, d, entry)) continue;
+        if (ray_box_fast (mn, mx, org, d, entry))
+        {
+            if (kind == VOXGPU_KIND_INNER)
+            {
+                const V3 c = v3 (__ldg (tr.ctr + cur));
+                const unsigned mask = (meta >> 8) & 0xffu;
+                const unsigned sub = subspace_fast (c, entry, nx, ny, nz);
 
-        if (kind == VOXGPU_KIND_INNER)
-        {
-            const float4 q2 = __ldg (tr.nodes + 3*(size_t)cur + 2);
-            const unsigned mask = (meta >> 8) & 0xffu;
-            const unsigned sub = subspace_corrected (v3 (q2), entry, d);
-            stack[sp++] = make_float4 (entry.x, entry.y, entry.z, __uint_as_float (cur | VOXGPU_EXPAND_BIT));
-            if (mask & (1u << sub))
-            {
-                cur = child_id (link, mask, sub);
-                org = entry;
-                have_call = true;
-            }
-            continue;
-        }
-        if (kind == VOXGPU_KIND_DENSE)
-        {
-            out.leaf = (int) cur; out.voxel = -1; out.point = entry;
-            return;
-        }
-        /* leaf, search.c:39-81 */
-        {
-            const unsigned n = meta >> 2;
-            float closest = __int_as_float (0x7f800000);
-            for (unsigned i=0; i<n; i++)
-            {
-                const float4 dq = __ldg (tr.dots + (size_t)link + i);
-                V3 vmin = v3 (dq), vmax, far;
-                vmax.x = __fadd_rn (vmin.x, tr.vx);
-                vmax.y = __fadd_rn (vmin.y, tr.vy);
-                vmax.z = __fadd_rn (vmin.z, tr.vz);
-                if (ray_box_fast (vmin, vmax, entry, d, far))
+                /* search.c:105-113: the three dividing planes, from the entry point */
+                V3 p0, p1, p2;
+                const bool v0 = ray_plane_fast (entry, d, c.x, entry.x, d.x, nx, mn, mx, p0);
+                const bool v1 = ray_plane_fast (entry, d, c.y, entry.y, d.y, ny, mn, mx, p1);
+                const bool v2 = ray_plane_fast (entry, d, c.z, entry.z, d.z, nz, mn, mx, p2);
+                if (v0 | v1 | v2)
                 {
-                    const float dist = l1_metric (entry, far);
-                    if (dist == 0.0f)
-                    {
-                        out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
-                        return;
-                    }
-                    if (dist < closest)
-                    {
-                        closest = dist;
-                        out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
-                    }
+                    /* search.c:115-134 as ranks.  Invalid planes get +inf and sort last. */
+                    const float inf = __int_as_float (0x7f800000);
+                    const float m0 = v0 ? l1_metric (entry, p0) : inf;
+                    const float m1 = v1 ? l1_metric (entry, p1) : inf;
+                    const float m2 = v2 ? l1_metric (entry, p2) : inf;
+                    const bool A = m1 < m0, B = m2 < m1, C = m2 < m0, D = m0 < m1;
+                    const bool b01 = !A && (!C || D);      /* plane 0 is tried before plane 1 */
+                    const bool b02 = !C && (!A || !B);
+                    const bool b12 = !B && (A || !C);
+                    /* search.c:137: the subspace flips of the planes tried so far accumulate */
+                    const unsigned s0 = sub ^ 1u ^ ((v1 && !b01) ? 2u : 0u) ^ ((v2 && !b02) ? 4u : 0u);
+                    const unsigned s1 = sub ^ 2u ^ ((v0 &&  b01) ? 1u : 0u) ^ ((v2 && !b12) ? 4u : 0u);
+                    const unsigned s2 = sub ^ 4u ^ ((v0 &&  b02) ? 1u : 0u) ^ ((v1 &&  b12) ? 2u : 0u);
+                    const bool e0 = v0 && ((mask >> s0) & 1u);
+                    const bool e1 = v1 && ((mask >> s1) & 1u);
+                    const bool e2 = v2 && ((mask >> s2) & 1u);
+                    /* the call tried first must be popped first: slot = number of later calls */
+                    if (e0) stack[sp + (int)(e1 && b01) + (int)(e2 && b02)] =
+                        make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
+                    if (e1) stack[sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
+                        make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
+                    if (e2) stack[sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
+                        make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
+                    sp += (int) e0 + (int) e1 + (int) e2;
+                }
+                /* search.c:83-97: the child the entry point lies in goes first */
+                if ((mask >> sub) & 1u)
+                {
+                    cur = child_id (link, mask, sub);
+                    org = entry;
+                    descend = true;
                 }
             }
-            if (out.leaf >= 0) return;
+            else if (kind == VOXGPU_KIND_DENSE)
+            {
+                out.leaf = (int) cur; out.voxel = -1; out.point = entry;
+                return;
+            }
+            else
+            {
+                /* leaf, search.c:39-81 */
+                const unsigned n = meta >> 2;
+                float closest = __int_as_float (0x7f800000);
+                for (unsigned i=0; i<n; i++)
+                {
+                    const float4 dq = __ldg (tr.dots + (size_t)link + i);
+                    V3 vmin = v3 (dq), vmax, far;
+                    vmax.x = __fadd_rn (vmin.x, tr.vx);
+                    vmax.y = __fadd_rn (vmin.y, tr.vy);
+                    vmax.z = __fadd_rn (vmin.z, tr.vz);
+                    if (ray_box_fast (vmin, vmax, entry, d, far))
+                    {
+                        const float dist = l1_metric (entry, far);
+                        if (dist == 0.0f)
+                        {
+                            out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
+                            return;
+                        }
+                        if (dist < closest)
+                        {
+                            closest = dist;
+                            out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
+                        }
+                    }
+                }
+                if (out.leaf >= 0) return;
+            }
+        }
+
+        if (!descend)
+        {
+            /* this call missed: go on with the nearest pending one */
+            if (sp == 0) return;
+            const float4 e = stack[--sp];
+            org.x = e.x; org.y = e.y; org.z = e.z;
+            cur = __float_as_uint (e.w);
         }
     }
 }

@@ -138,7 +138,8 @@ struct voxgpu_tree
     int device;
     uint64_t n_nodes, n_dots;
     uint32_t depth;
-    float4 *nodes;   /* 3 per node */
+    NodeRec *rec;    /* 32 B per node: box + meta + link */
+    float4 *ctr;     /* 16 B per node: split centre (inner nodes) */
     float4 *dots;
     float voxel[3];
 };
@@ -157,14 +158,17 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
     memcpy (t->voxel, f->voxel, sizeof t->voxel);
     if (cudaGetDevice (&t->device) != cudaSuccess) { fail ("no CUDA device: %s", cudaGetErrorString (cudaGetLastError ())); free (t); return NULL; }
 
-    const size_t node_bytes = (size_t) f->n_nodes * 3 * sizeof (float4);
+    const size_t rec_bytes = (size_t) f->n_nodes * sizeof (NodeRec);
+    const size_t ctr_bytes = (size_t) f->n_nodes * sizeof (float4);
     const size_t dot_bytes = (size_t) (f->n_dots ? f->n_dots : 1) * sizeof (float4);
-    float4 *stage = NULL;
+    size_t stage_bytes = rec_bytes > dot_bytes ? rec_bytes : dot_bytes;
+    void *stage_v = NULL;
     cudaStream_t s = NULL;
     cudaError_t e;
-    if ((e = cudaMalloc (&t->nodes, node_bytes)) != cudaSuccess ||
+    if ((e = cudaMalloc (&t->rec, rec_bytes)) != cudaSuccess ||
+        (e = cudaMalloc (&t->ctr, ctr_bytes)) != cudaSuccess ||
         (e = cudaMalloc (&t->dots, dot_bytes)) != cudaSuccess ||
-        (e = cudaHostAlloc (&stage, node_bytes > dot_bytes ? node_bytes : dot_bytes, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaHostAlloc (&stage_v, stage_bytes, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags (&s, cudaStreamNonBlocking)) != cudaSuccess)
     {
         fail ("voxgpu_tree_upload: %s", cudaGetErrorString (e));
@@ -172,45 +176,58 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
     }
 
     /* device records, written straight into the pinned staging buffer */
-    for (uint64_t id=0; id<f->n_nodes; id++)
     {
-        const uint32_t fl = f->flags[id];
-        uint32_t meta, link;
-        if (fl & VOXGPU_DENSE_LEAF) { meta = VOXGPU_KIND_DENSE; link = 0; }
-        else if (fl & VOXGPU_LEAF)
+        NodeRec *stage = (NodeRec*) stage_v;
+        for (uint64_t id=0; id<f->n_nodes; id++)
         {
-            if (f->dots_num[id] >= (1u << 30)) { fail ("leaf with %u dots", f->dots_num[id]); goto bad; }
-            meta = VOXGPU_KIND_LEAF | (f->dots_num[id] << 2);
-            link = (uint32_t) f->dots_off[id];
+            const uint32_t fl = f->flags[id];
+            uint32_t meta, link;
+            if (fl & VOXGPU_DENSE_LEAF) { meta = VOXGPU_KIND_DENSE; link = 0; }
+            else if (fl & VOXGPU_LEAF)
+            {
+                if (f->dots_num[id] >= (1u << 30)) { fail ("leaf with %u dots", f->dots_num[id]); goto bad; }
+                meta = VOXGPU_KIND_LEAF | (f->dots_num[id] << 2);
+                link = (uint32_t) f->dots_off[id];
+            }
+            else { meta = VOXGPU_KIND_INNER | ((f->child_mask[id] & 0xffu) << 8); link = f->first_child[id]; }
+            NodeRec r;
+            r.lo.x = f->bb_min[3*id]; r.lo.y = f->bb_min[3*id+1]; r.lo.z = f->bb_min[3*id+2];
+            memcpy (&r.lo.w, &meta, 4);
+            r.hi.x = f->bb_max[3*id]; r.hi.y = f->bb_max[3*id+1]; r.hi.z = f->bb_max[3*id+2];
+            memcpy (&r.hi.w, &link, 4);
+            stage[id] = r;
         }
-        else { meta = VOXGPU_KIND_INNER | ((f->child_mask[id] & 0xffu) << 8); link = f->first_child[id]; }
-        float4 q0, q1, q2;
-        q0.x = f->bb_min[3*id]; q0.y = f->bb_min[3*id+1]; q0.z = f->bb_min[3*id+2];
-        memcpy (&q0.w, &meta, 4);
-        q1.x = f->bb_max[3*id]; q1.y = f->bb_max[3*id+1]; q1.z = f->bb_max[3*id+2];
-        memcpy (&q1.w, &link, 4);
-        q2.x = f->center[3*id]; q2.y = f->center[3*id+1]; q2.z = f->center[3*id+2]; q2.w = 0;
-        stage[3*id] = q0; stage[3*id+1] = q1; stage[3*id+2] = q2;
     }
-    if ((e = cudaMemcpyAsync (t->nodes, stage, node_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+    if ((e = cudaMemcpyAsync (t->rec, stage_v, rec_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
         (e = cudaStreamSynchronize (s)) != cudaSuccess)
     { fail ("voxgpu_tree_upload: node copy: %s", cudaGetErrorString (e)); goto bad; }
-    for (uint64_t i=0; i<f->n_dots; i++)
     {
-        float4 q; q.x = f->dots[3*i]; q.y = f->dots[3*i+1]; q.z = f->dots[3*i+2]; q.w = 0;
-        stage[i] = q;
+        float4 *stage = (float4*) stage_v;
+        for (uint64_t id=0; id<f->n_nodes; id++)
+        {
+            float4 q; q.x = f->center[3*id]; q.y = f->center[3*id+1]; q.z = f->center[3*id+2]; q.w = 0;
+            stage[id] = q;
+        }
+        if ((e = cudaMemcpyAsync (t->ctr, stage_v, ctr_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+            (e = cudaStreamSynchronize (s)) != cudaSuccess)
+        { fail ("voxgpu_tree_upload: centre copy: %s", cudaGetErrorString (e)); goto bad; }
+        for (uint64_t i=0; i<f->n_dots; i++)
+        {
+            float4 q; q.x = f->dots[3*i]; q.y = f->dots[3*i+1]; q.z = f->dots[3*i+2]; q.w = 0;
+            stage[i] = q;
+        }
+        if (f->n_dots &&
+            ((e = cudaMemcpyAsync (t->dots, stage_v, f->n_dots * sizeof (float4), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+             (e = cudaStreamSynchronize (s)) != cudaSuccess))
+        { fail ("voxgpu_tree_upload: dots copy: %s", cudaGetErrorString (e)); goto bad; }
     }
-    if (f->n_dots &&
-        ((e = cudaMemcpyAsync (t->dots, stage, f->n_dots * sizeof (float4), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
-         (e = cudaStreamSynchronize (s)) != cudaSuccess))
-    { fail ("voxgpu_tree_upload: dots copy: %s", cudaGetErrorString (e)); goto bad; }
-    cudaFreeHost (stage);
+    cudaFreeHost (stage_v);
     cudaStreamDestroy (s);
     return t;
 bad:
-    if (stage) cudaFreeHost (stage);
+    if (stage_v) cudaFreeHost (stage_v);
     if (s) cudaStreamDestroy (s);
-    cudaFree (t->nodes); cudaFree (t->dots);
+    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots);
     free (t);
     return NULL;
 }
@@ -221,7 +238,7 @@ extern "C" void voxgpu_tree_free (voxgpu_tree *t)
     int cur = -1;
     cudaGetDevice (&cur);
     if (cur != t->device) cudaSetDevice (t->device);
-    cudaFree (t->nodes); cudaFree (t->dots);
+    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots);
     if (cur != t->device && cur >= 0) cudaSetDevice (cur);
     free (t);
 }
@@ -232,7 +249,7 @@ extern "C" int voxgpu_tree_device (const voxgpu_tree *t) { return t ? t->device 
 static TreeRef tree_ref (const voxgpu_tree *t)
 {
     TreeRef r;
-    r.nodes = t->nodes; r.dots = t->dots;
+    r.rec = t->rec; r.ctr = t->ctr; r.dots = t->dots;
     r.vx = t->voxel[0]; r.vy = t->voxel[1]; r.vz = t->voxel[2];
     return r;
 }
@@ -411,6 +428,7 @@ cleanup:
 /* -------------------------------------------------------------- K1: render */
 
 #define RENDER_BLOCK 128
+#define RENDER_STRIPS 64u
 
 struct DevCamera
 {
@@ -527,7 +545,7 @@ k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restri
  * frame is done.  The counter resets itself: the last warp to leave zeroes it,
  * so no memset precedes the launch.
  */
-template <bool OUT_HITS>
+template <bool OUT_HITS, unsigned STRIPS>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
@@ -540,12 +558,23 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
     float4 stack[VOXGPU_RAY_STACK];
     V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
 
+    /* Tiles are handed out strip-interleaved: consecutive tickets land in
+       RENDER_STRIPS different horizontal strips of the frame.  In raster order
+       the empty top and bottom of a frame (80% of a skull frame misses the root
+       box) are done in two bursts that only store pixels while the middle only
+       computes; interleaved, stores and traversal overlap for the whole kernel,
+       which matters when the pixels go to mapped host memory over PCIe. */
+    const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
+    const unsigned tickets = per_strip * STRIPS;
+
     for (;;)
     {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd (&counters[0], 1u);
-        tile = __shfl_sync (0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd (&counters[0], 1u);
+        ticket = __shfl_sync (0xffffffffu, ticket, 0);
+        if (ticket >= tickets) break;
+        const unsigned tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
+        if (tile >= ntiles) continue;
 
         const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
         const int ry = (int) (tile / tiles_x) * 4 + (lane >> 3);
@@ -591,8 +620,8 @@ static unsigned* counter_slot (int device)
         if (cudaMemset (p, 0, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
         int sms = 0, b0 = 0, b1 = 0;
         cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false, RENDER_STRIPS>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
         g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
         g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
         g_counters[device] = p;
@@ -641,10 +670,18 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
         const bool hits = d_leaf || d_pts;
         int grid = g_render_blocks[t->device][hits ? 1 : 0];
         if (grid > blocks) grid = blocks;
-        if (hits)
-            k_render_persistent<true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        cudaStream_t st = (cudaStream_t) s;
+        float4 *pts = (float4*) d_pts;
+        if (g_variant == 2)
+        {   /* raster tile order, kept for A/B measurements */
+            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters);
+            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+        }
         else
-            k_render_persistent<false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+        {
+            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters);
+            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+        }
     }
     g_launches++;
     CU (cudaGetLastError ());
