@@ -122,6 +122,8 @@ VOXGPU_EXPORT int   voxgpu_memcpy_d2h (void *hptr, const void *dptr, size_t byte
 VOXGPU_EXPORT int   voxgpu_memset (void *dptr, int value, size_t bytes, voxgpu_stream s);
 VOXGPU_EXPORT voxgpu_stream voxgpu_stream_create (void);
 VOXGPU_EXPORT void  voxgpu_stream_destroy (voxgpu_stream s);
+/** Work queued on `waiter` after this call starts only when everything queued on `other` so far is done. */
+VOXGPU_EXPORT int   voxgpu_stream_join (voxgpu_stream waiter, voxgpu_stream other);
 
 /* ---- tree ---- */
 /** Convert to the device layout and upload (cudaMemcpyAsync from pinned staging) on the current device. */
@@ -169,10 +171,37 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
                                  uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
                                  voxgpu_stream stream);
 
+/* ---- frames to host memory ----
+ * What vox_render + vox_redraw (renderer.c:200-327) use when the surface is in
+ * host memory: the frame is rendered into a device framebuffer in `bands`
+ * horizontal bands (0 = default, or $VOXGPU_BANDS), each on its own prioritised
+ * stream and each followed by a DMA copy into `host_pixels`, which must be
+ * page-locked (voxgpu_host_alloc / voxgpu_host_register).  _render returns as
+ * soon as the work is queued; _wait returns once every band has landed.
+ * frame->y0/y1/pitch_pixels are ignored (the whole frame is drawn). */
+typedef struct voxgpu_present voxgpu_present;
+VOXGPU_EXPORT voxgpu_present* voxgpu_present_create (int w, int h, int bands);
+VOXGPU_EXPORT void voxgpu_present_destroy (voxgpu_present *p);
+VOXGPU_EXPORT int voxgpu_present_bands (const voxgpu_present *p);
+VOXGPU_EXPORT int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *tree, const voxgpu_camera *camera,
+                                         const voxgpu_frame *frame, const uint8_t *d_texture,
+                                         void *host_pixels, size_t host_pitch_bytes);
+VOXGPU_EXPORT int voxgpu_present_wait (voxgpu_present *p);
+/** Device time from the first band's launch to the last band's arrival in host memory, ms (waits). */
+VOXGPU_EXPORT float voxgpu_present_last_ms (voxgpu_present *p);
+/** The device framebuffer the last frame was rendered into (w*h pixels, pitch w). */
+VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p);
+
 /** Development knob: 0 = the first, one-CTA-per-4-tiles render kernel with the
-    plain traversal (kept for A/B measurements), 1 = the persistent kernel with the
-    reorganised traversal (default).  Results are identical. */
+    plain (lazy, reference-shaped) traversal, 1 = the persistent kernel with the
+    eager traversal and strip-interleaved tile order (default), 2 = as 1 with
+    raster tile order.  Kept for A/B measurements; results are identical. */
 VOXGPU_EXPORT void voxgpu_set_variant (int variant);
+
+/** Development trace: when non-NULL, every following voxgpu_render launch (persistent
+    variants) records per 8x4 tile {start ns, end ns, smid<<32 | warp} (3 x uint64 per
+    tile of the launch's band, device memory supplied by the caller).  NULL switches it off. */
+VOXGPU_EXPORT void voxgpu_set_trace (void *d_trace);
 
 /** Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 VOXGPU_EXPORT unsigned long long voxgpu_launch_count (void);

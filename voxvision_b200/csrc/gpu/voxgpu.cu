@@ -108,6 +108,17 @@ extern "C" voxgpu_stream voxgpu_stream_create (void)
     return (voxgpu_stream) s;
 }
 extern "C" void voxgpu_stream_destroy (voxgpu_stream s) { if (s) cudaStreamDestroy ((cudaStream_t) s); }
+extern "C" int voxgpu_stream_join (voxgpu_stream waiter, voxgpu_stream other)
+{
+    /* everything queued on `other` so far must finish before what is queued on `waiter` next */
+    cudaEvent_t e;
+    CU (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+    cudaError_t rc = cudaEventRecord (e, (cudaStream_t) other);
+    if (rc == cudaSuccess) rc = cudaStreamWaitEvent ((cudaStream_t) waiter, e, 0);
+    cudaEventDestroy (e);
+    if (rc != cudaSuccess) return fail ("voxgpu_stream_join: %s", cudaGetErrorString (rc));
+    return 0;
+}
 
 /* ------------------------------------------------------------------- timer */
 
@@ -545,11 +556,24 @@ k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restri
  * frame is done.  The counter resets itself: the last warp to leave zeroes it,
  * so no memset precedes the launch.
  */
+__device__ __forceinline__ unsigned long long globaltimer_ns ()
+{
+    unsigned long long t;
+    asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned smid ()
+{
+    unsigned r;
+    asm ("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+
 template <bool OUT_HITS, unsigned STRIPS>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
-                     unsigned *counters)
+                     unsigned *counters, unsigned long long *trace)
 {
     const int tiles_x = fr.w >> 3;
     const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
@@ -576,6 +600,8 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         const unsigned tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
         if (tile >= ntiles) continue;
 
+        unsigned long long t0 = 0;
+        if (trace) t0 = globaltimer_ns ();
         const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
         const int ry = (int) (tile / tiles_x) * 4 + (lane >> 3);
         const int sy = fr.y0 + ry;
@@ -593,6 +619,13 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
             if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
         }
         __syncwarp ();
+        if (trace && lane == 0)
+        {
+            /* development trace (voxgpu_set_trace): when and where each tile ran */
+            trace[3*(size_t) tile] = t0;
+            trace[3*(size_t) tile + 1] = globaltimer_ns ();
+            trace[3*(size_t) tile + 2] = ((unsigned long long) smid () << 32) | (blockIdx.x * (RENDER_BLOCK/32) + (threadIdx.x >> 5));
+        }
     }
     if (lane == 0)
     {
@@ -608,6 +641,9 @@ static unsigned *g_counters[64] = {0};
 static int g_render_blocks[64][2] = {{0}};
 static std::atomic<unsigned> g_counter_seq{0};
 static int g_variant = 1;
+static unsigned long long *g_trace = NULL;
+
+extern "C" void voxgpu_set_trace (void *d_trace) { g_trace = (unsigned long long*) d_trace; }
 
 extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
 
@@ -674,16 +710,151 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
         float4 *pts = (float4*) d_pts;
         if (g_variant == 2)
         {   /* raster tile order, kept for A/B measurements */
-            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters);
-            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
+            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace);
         }
         else
         {
-            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters);
-            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters);
+            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
+            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace);
         }
     }
     g_launches++;
     CU (cudaGetLastError ());
     return 0;
 }
+
+/* --------------------------------------------------- frames to host memory */
+
+/*
+ * Presenter: what vox_render + vox_redraw need when the surface lives in host
+ * memory (north_star item 4).  Measured on B200 (tools/probes/pcie_probe.cu,
+ * tools/kbench.py): a kernel CAN store the frame straight into mapped pinned
+ * memory, but those stores back up the SM's memory pipeline behind PCIe and the
+ * traversal stalls with them -- the frame takes kernel time PLUS transfer time
+ * (0.25 + 0.15 ms) however the tiles are ordered.  So the frame is rendered into
+ * a device framebuffer in horizontal bands, one kernel per band on its own
+ * stream, and every band is followed on that stream by a DMA copy into the
+ * (page-locked) surface.  The streams have descending priorities: all band
+ * kernels are in flight at once, the block scheduler drains them in order, the
+ * tail of one band is back-filled by the next, and the copy engine moves band i
+ * while band i+1 renders.  Only the last band's copy is exposed.
+ */
+#define PRESENT_MAX_BANDS 16
+
+struct voxgpu_present
+{
+    int device, w, h, bands;
+    uint32_t *fb;                         /* device framebuffer, w*h */
+    cudaStream_t stream[PRESENT_MAX_BANDS];
+    cudaEvent_t done[PRESENT_MAX_BANDS];
+    cudaEvent_t start;
+    int in_flight;
+};
+
+extern "C" void voxgpu_present_destroy (voxgpu_present *p)
+{
+    if (!p) return;
+    for (int i=0; i<p->bands; i++)
+    {
+        if (p->stream[i]) { cudaStreamSynchronize (p->stream[i]); cudaStreamDestroy (p->stream[i]); }
+        if (p->done[i]) cudaEventDestroy (p->done[i]);
+    }
+    if (p->start) cudaEventDestroy (p->start);
+    cudaFree (p->fb);
+    free (p);
+}
+
+extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
+{
+    if (w <= 0 || h <= 0 || (w & 0xf) || (h & 0x3)) { fail ("voxgpu_present_create: bad geometry %dx%d", w, h); return NULL; }
+    if (bands <= 0)
+    {
+        const char *env = getenv ("VOXGPU_BANDS");
+        bands = env ? atoi (env) : 4;
+    }
+    if (bands < 1) bands = 1;
+    if (bands > PRESENT_MAX_BANDS) bands = PRESENT_MAX_BANDS;
+    if (bands > h / 4) bands = h / 4;
+    voxgpu_present *p = (voxgpu_present*) calloc (1, sizeof *p);
+    p->w = w; p->h = h; p->bands = bands;
+    int least = 0, greatest = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice (&p->device)) != cudaSuccess ||
+        (e = cudaDeviceGetStreamPriorityRange (&least, &greatest)) != cudaSuccess ||
+        (e = cudaMalloc (&p->fb, (size_t) w * h * 4)) != cudaSuccess ||
+        (e = cudaEventCreate (&p->start)) != cudaSuccess) goto bad;
+    for (int i=0; i<bands; i++)
+    {
+        int prio = greatest + i;            /* numerically lower = served first */
+        if (prio > least) prio = least;
+        if ((e = cudaStreamCreateWithPriority (&p->stream[i], cudaStreamNonBlocking, prio)) != cudaSuccess ||
+            (e = cudaEventCreate (&p->done[i])) != cudaSuccess) goto bad;
+    }
+    return p;
+bad:
+    fail ("voxgpu_present_create: %s", cudaGetErrorString (e));
+    voxgpu_present_destroy (p);
+    return NULL;
+}
+
+extern "C" int voxgpu_present_bands (const voxgpu_present *p) { return p ? p->bands : 0; }
+
+extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c,
+                                      const voxgpu_frame *f, const uint8_t *d_tex,
+                                      void *host_pixels, size_t host_pitch_bytes)
+{
+    if (!p || !f || !host_pixels) return fail ("voxgpu_present_render: NULL argument");
+    if (f->w != p->w || f->h != p->h) return fail ("voxgpu_present_render: frame is %dx%d, presenter %dx%d", f->w, f->h, p->w, p->h);
+    if (host_pitch_bytes < (size_t) p->w * 4) return fail ("voxgpu_present_render: pitch %zu too small", host_pitch_bytes);
+    int cur = -1;
+    CU (cudaGetDevice (&cur));
+    if (cur != p->device) return fail ("voxgpu_present_render: presenter lives on device %d, current device is %d", p->device, cur);
+
+    const int units = p->h / 4;             /* bands are multiples of 4 rows (renderer.c:97-100) */
+    CU (cudaEventRecord (p->start, p->stream[0]));
+    for (int i=0; i<p->bands; i++)
+    {
+        /* the later bands wait for the start mark so that the elapsed time covers all of them */
+        if (i) CU (cudaStreamWaitEvent (p->stream[i], p->start, 0));
+        const int y0 = (int) ((long long) units * i / p->bands) * 4;
+        const int y1 = (int) ((long long) units * (i + 1) / p->bands) * 4;
+        if (y1 <= y0) { CU (cudaEventRecord (p->done[i], p->stream[i])); continue; }
+        voxgpu_frame band = *f;
+        band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
+        uint32_t *src = p->fb + (size_t) y0 * p->w;
+        if (voxgpu_render (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i])) return -1;
+        char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
+        if (host_pitch_bytes == (size_t) p->w * 4)
+            CU (cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]));
+        else
+            CU (cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0,
+                                   cudaMemcpyDeviceToHost, p->stream[i]));
+        CU (cudaEventRecord (p->done[i], p->stream[i]));
+    }
+    p->in_flight = 1;
+    return 0;
+}
+
+extern "C" int voxgpu_present_wait (voxgpu_present *p)
+{
+    if (!p || !p->in_flight) return 0;
+    for (int i=0; i<p->bands; i++) CU (cudaEventSynchronize (p->done[i]));
+    return 0;
+}
+
+extern "C" float voxgpu_present_last_ms (voxgpu_present *p)
+{
+    if (!p || !p->in_flight) return -1.0f;
+    float worst = -1.0f;
+    for (int i=0; i<p->bands; i++)
+    {
+        float ms = 0.0f;
+        if (cudaEventSynchronize (p->done[i]) != cudaSuccess ||
+            cudaEventElapsedTime (&ms, p->start, p->done[i]) != cudaSuccess) { fail ("voxgpu_present_last_ms: event query failed"); return -1.0f; }
+        if (ms > worst) worst = ms;
+    }
+    return worst;
+}
+
+extern "C" const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p) { return p ? p->fb : NULL; }

@@ -31,9 +31,8 @@ struct vox_rnd_ctx_full
     unsigned int quality;
     int owns_surface;
     int registered;               /* we page-locked a foreign surface */
-    uint32_t *d_pixels;           /* device alias of surface->pixels */
-    voxgpu_stream stream;
-    voxgpu_timer *timer;
+    voxgpu_stream stream;         /* uploads (texture, tabulated directions) */
+    voxgpu_present *present;      /* device framebuffer + band streams -> surface->pixels */
     int timed;
     float *dir_table, *d_dir_table;   /* foreign cameras: tabulated screen2world */
     int device;

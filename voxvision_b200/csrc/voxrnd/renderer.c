@@ -1,8 +1,10 @@
 /*
  * renderer.c -- renderer context and vox_render / vox_redraw (reference:
- * src/voxrnd/renderer.c).  The per-block CPU loop of renderer.c:214-318 is one
- * kernel launch (voxgpu_render); the frame lands directly in the surface's
- * page-locked pixels, so copy_squares (copy-helper.c:5-40) has no counterpart.
+ * src/voxrnd/renderer.c).  The per-block CPU loop of renderer.c:214-318 is a
+ * handful of kernel launches (one per band of the frame, voxgpu_present_render);
+ * every band is DMA-copied into the surface's page-locked pixels in linear
+ * layout while the next band renders, so copy_squares (copy-helper.c:5-40) has
+ * no counterpart.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,11 +50,10 @@ static int context_device_init (struct vox_rnd_ctx_full *ctx)
         { vox_set_error ("cannot map surface pixels: %s", voxgpu_last_error ()); return 0; }
         ctx->registered = 1;
     }
-    ctx->d_pixels = voxgpu_host_device_pointer (s->pixels);
     ctx->d_texture = voxgpu_malloc (VOX_TEXTURE_SIZE);
     ctx->stream = voxgpu_stream_create ();
-    ctx->timer = voxgpu_timer_create ();
-    if (!ctx->d_pixels || !ctx->d_texture || !ctx->stream || !ctx->timer)
+    ctx->present = voxgpu_present_create (s->w, s->h, 0);
+    if (!ctx->d_texture || !ctx->stream || !ctx->present)
     { vox_set_error ("context device setup failed: %s", voxgpu_last_error ()); return 0; }
     ctx->device = voxgpu_get_device ();
     return 1;
@@ -87,12 +88,12 @@ void vox_destroy_context (struct vox_rnd_ctx *pub)
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
     if (!ctx) return;
     if (ctx->stream) voxgpu_synchronize (ctx->stream);
+    voxgpu_present_destroy (ctx->present);
     if (ctx->registered) voxgpu_host_unregister (pub->surface->pixels);
     if (ctx->owns_surface) vox_free_surface (pub->surface);
     voxgpu_free (ctx->d_texture);
     voxgpu_free (ctx->d_dir_table);
     voxgpu_host_free (ctx->dir_table);
-    voxgpu_timer_destroy (ctx->timer);
     voxgpu_stream_destroy (ctx->stream);
     free (ctx->texture);
     free (ctx);
@@ -145,7 +146,7 @@ float vox_context_last_kernel_ms (struct vox_rnd_ctx *pub)
 {
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
     if (!ctx->timed) return -1.0f;
-    return voxgpu_timer_elapsed_ms (ctx->timer);
+    return voxgpu_present_last_ms (ctx->present);
 }
 
 /* A camera without `describe`: evaluate its host screen2world for every pixel. */
@@ -167,7 +168,8 @@ static int tabulate_camera (struct vox_rnd_ctx_full *ctx, voxgpu_camera *cam)
             camera->iface->screen2world (camera, d, x, y);
             memcpy (ctx->dir_table + 4*((size_t) y*w + x), d, 3*sizeof (float));
         }
-    if (voxgpu_memcpy_h2d (ctx->d_dir_table, ctx->dir_table, bytes, ctx->stream)) return 0;
+    if (voxgpu_memcpy_h2d (ctx->d_dir_table, ctx->dir_table, bytes, ctx->stream) ||
+        voxgpu_synchronize (ctx->stream)) return 0;
     cam->kind = VOXGPU_CAMERA_TABLE;
     cam->dir_table = ctx->d_dir_table;
     return 1;
@@ -192,7 +194,8 @@ void vox_render (struct vox_rnd_ctx *pub)
 
     if (ctx->texture_dirty)
     {
-        if (voxgpu_memcpy_h2d (ctx->d_texture, ctx->texture, VOX_TEXTURE_SIZE, ctx->stream))
+        if (voxgpu_memcpy_h2d (ctx->d_texture, ctx->texture, VOX_TEXTURE_SIZE, ctx->stream) ||
+            voxgpu_synchronize (ctx->stream))
         { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
         ctx->texture_dirty = 0;
     }
@@ -225,10 +228,8 @@ void vox_render (struct vox_rnd_ctx *pub)
     fr.fmt.rloss = s->format->Rloss; fr.fmt.gloss = s->format->Gloss; fr.fmt.bloss = s->format->Bloss;
     fr.fmt.rshift = s->format->Rshift; fr.fmt.gshift = s->format->Gshift; fr.fmt.bshift = s->format->Bshift;
 
-    voxgpu_timer_start (ctx->timer, ctx->stream);
-    if (voxgpu_render (tree, &cam, &fr, ctx->d_texture, ctx->d_pixels, NULL, NULL, ctx->stream))
+    if (voxgpu_present_render (ctx->present, tree, &cam, &fr, ctx->d_texture, s->pixels, (size_t) s->pitch))
     { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
-    voxgpu_timer_stop (ctx->timer, ctx->stream);
     ctx->timed = 1;
 }
 
@@ -237,6 +238,6 @@ void vox_redraw (struct vox_rnd_ctx *pub)
     /* renderer.c:321-327: after this call surface->pixels holds the frame.
        There is no window to update. */
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
-    if (ctx->stream && voxgpu_synchronize (ctx->stream))
+    if (ctx->present && voxgpu_present_wait (ctx->present))
         vox_set_error ("vox_redraw: %s", voxgpu_last_error ());
 }
