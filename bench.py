@@ -226,7 +226,7 @@ def run_own(args):
     else:
         s_ptr = C.c_void_p(g.voxgpu_stream_create())
         streams = [s_ptr] + [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS - 1)]
-        marks = [vv.Timer() for _ in streams]
+        scheds = [C.c_void_p(g.voxgpu_sched_create()) for _ in streams]   # heavy-tiles-first, frame to frame
         bufs = [vv.DeviceBuffer(frame_bytes) for _ in range(RING)]
         ring_ptr = lambda i: bufs[i % RING].ptr
         d_tex_b = vv.DeviceBuffer.from_array(tex)
@@ -250,8 +250,8 @@ def run_own(args):
             for st in streams[1:]:
                 g.voxgpu_stream_join(st, s_ptr)  # the step's first mark / flush precedes every stream's frames
             for f in range(FRAMES):
-                rc = g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
-                                     streams[f % FRAME_STREAMS])
+                rc = g.voxgpu_render_sched(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
+                                           streams[f % FRAME_STREAMS], scheds[f % FRAME_STREAMS])
                 if rc:
                     raise vv.VoxError(g.voxgpu_last_error().decode())
             for st in streams[1:]:

@@ -171,6 +171,20 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
                                  uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
                                  voxgpu_stream stream);
 
+/** Frame-to-frame tile schedule for voxgpu_render_sched: tiles in whose neighbourhood the
+    previous launch on this schedule found expensive tiles are handed out first in the next
+    one (one extra small kernel per launch).  Launches sharing a schedule must
+    be ordered (same stream).  Purely a performance hint: results do not depend on it.
+    $VOXGPU_HEAVY_ITERS / $VOXGPU_MID_ITERS set the class thresholds (HEAVY = 0: off). */
+typedef struct voxgpu_sched voxgpu_sched;
+VOXGPU_EXPORT voxgpu_sched* voxgpu_sched_create (void);
+VOXGPU_EXPORT void voxgpu_sched_destroy (voxgpu_sched *sched);
+/** voxgpu_render with a schedule (NULL = none). */
+VOXGPU_EXPORT int voxgpu_render_sched (const voxgpu_tree *tree, const voxgpu_camera *camera,
+                                       const voxgpu_frame *frame, const uint8_t *d_texture,
+                                       uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
+                                       voxgpu_stream stream, voxgpu_sched *sched);
+
 /* ---- frames to host memory ----
  * What vox_render + vox_redraw (renderer.c:200-327) use when the surface is in
  * host memory: the frame is rendered into a device framebuffer in `bands`

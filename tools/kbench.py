@@ -40,17 +40,20 @@ t = vv.Timer()
 frames = sorted(int(k) for k in gold["c2"])
 
 
-def timed(gc, target, reps=9):
+sched = g.voxgpu_sched_create()
+
+
+def timed(gc, target, reps=9, sc=None):
     ms = []
     for _ in range(reps):
-        t.start(); g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, target, None, None, None); t.stop()
+        t.start(); g.voxgpu_render_sched(dev, C.byref(gc), C.byref(fr), d_tex.ptr, target, None, None, None, sc); t.stop()
         ms.append(t.elapsed_ms())
     return sorted(ms)
 
 
 for v in variants:
     g.voxgpu_set_variant(v)
-    tot_d = tot_m = 0.0
+    tot_d = tot_m = tot_s = 0.0
     for f in frames:
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
         gc = cam.gpu_camera()
@@ -62,13 +65,24 @@ for v in variants:
         ok = [sha(leaf) == want["leaf_sha"], sha(pts[m]) == want["hit_sha"], sha(pix) == want["pix_sha"]]
         md = timed(gc, d_pix.ptr)
         ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
+        # scheduled: as in an animation, every timed launch follows a launch of the frame one orbit step before
+        ds.setup_camera(cam, *ds.orbit_pose(f - 1), 1.2, W, H)
+        gprev = cam.gpu_camera()
+        ms_ = []
+        for _ in range(9):
+            g.voxgpu_render_sched(dev, C.byref(gprev), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None, sched)
+            ms_ += timed(gc, d_pix.ptr, reps=1, sc=sched)
+        ms_.sort()
+        ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
+        tot_s += ms_[len(ms_) // 2]
         h_view[:] = 0xdeadbeef
         mm = timed(gc, m_pix)
         g.voxgpu_synchronize(None)
         ok.append(sha(h_view) == want["pix_sha"])
         tot_d += md[len(md) // 2]; tot_m += mm[len(mm) // 2]
         print(f"variant {v} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
-              f"device min {md[0]:.4f} med {md[len(md)//2]:.4f} | mapped min {mm[0]:.4f} med {mm[len(mm)//2]:.4f} ms", flush=True)
+              f"device min {md[0]:.4f} med {md[len(md)//2]:.4f} | scheduled min {ms_[0]:.4f} med {ms_[len(ms_)//2]:.4f} | mapped min {mm[0]:.4f} med {mm[len(mm)//2]:.4f} ms", flush=True)
     n = len(frames)
     print(f"variant {v}: mean of per-frame medians: device {tot_d/n:.4f} ms -> {W*H/(tot_d/n)/1e3:.0f} Mrays/s | "
+          f"scheduled {tot_s/n:.4f} ms -> {W*H/(tot_s/n)/1e3:.0f} Mrays/s | "
           f"mapped {tot_m/n:.4f} ms -> {W*H/(tot_m/n)/1e3:.0f} Mrays/s", flush=True)

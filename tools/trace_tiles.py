@@ -30,11 +30,15 @@ for variant in [int(a) for a in sys.argv[1:]] or [1]:
     for f in (0, 90):
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
         gc = cam.gpu_camera()
+        sched = g.voxgpu_sched_create() if os.environ.get("TRACE_SCHED") else None
+        # with a schedule: warm it up on the frame 3 steps earlier on the orbit, like an animation would
+        ds.setup_camera(cam, *ds.orbit_pose(f - 1), 1.2, W, H)
+        gp = cam.gpu_camera()
         for _ in range(3):
             g.voxgpu_set_trace(None)
-            g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None)
+            g.voxgpu_render_sched(dev, C.byref(gp), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None, sched)
         g.voxgpu_set_trace(d_tr.ptr)
-        g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None)
+        g.voxgpu_render_sched(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None, sched)
         g.voxgpu_set_trace(None)
         tr = d_tr.download(np.uint64, (ntiles, 3))
         t0, t1 = tr[:, 0].astype(np.int64), tr[:, 1].astype(np.int64)
@@ -51,6 +55,15 @@ for variant in [int(a) for a in sys.argv[1:]] or [1]:
             ov = np.clip(np.minimum(t1, b) - np.maximum(t0, a), 0, None).sum() / (b - a)
             busy.append(ov)
         print("   busy warps per 2.5% slice:", " ".join(f"{x:.0f}" for x in busy))
-        late = np.argsort(t1)[-5:]
+        it = (tr[:, 2] & np.uint64(0xffffffff)).astype(np.int64)
+        print("   iterations per tile: median %d p90 %d p95 %d p99 %d max %d; tiles >= 24: %d, >= 40: %d, >= 64: %d, >= 100: %d" % (
+            np.median(it), np.percentile(it, 90), np.percentile(it, 95), np.percentile(it, 99), it.max(),
+            (it >= 24).sum(), (it >= 40).sum(), (it >= 64).sum(), (it >= 100).sum()))
+        late = np.argsort(t1)[-6:]
         for i in late:
-            print(f"   late tile {i} (x {i % (W//8)}, y {i // (W//8)}): start {t0[i]/1e3:.1f} end {t1[i]/1e3:.1f} us dur {dur[i]:.1f}")
+            print(f"   late tile {i} (x {i % (W//8)}, y {i // (W//8)}): start {t0[i]/1e3:.1f} end {t1[i]/1e3:.1f} us dur {dur[i]:.1f} iters {it[i]}")
+        for lo, hi in ((1, 2), (2, 8), (8, 16), (16, 24), (24, 32), (32, 40), (40, 64), (64, 1000)):
+            sel = (it >= lo) & (it < hi)
+            if sel.any():
+                print(f"   iters [{lo},{hi}): {int(sel.sum()):6d} tiles, dur us median {np.median(dur[sel]):7.1f} p90 {np.percentile(dur[sel], 90):7.1f} max {dur[sel].max():7.1f}, "
+                      f"median start {np.median(t0[sel])/1e3:6.1f} us, share of warp time {100*dur[sel].sum()/dur.sum():4.1f}%")

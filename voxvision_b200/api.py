@@ -162,6 +162,9 @@ class _Libs:
         g.voxgpu_rays_stats.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, C.POINTER(GpuStats)]
         g.voxgpu_balls_device.argtypes = [_vp, _vp, _vp, sz, _vp, _vp]
         g.voxgpu_render.argtypes = [_vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, _vp, _vp, _vp]
+        g.voxgpu_render_sched.argtypes = [_vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, _vp, _vp, _vp, _vp]
+        g.voxgpu_sched_create.restype = _vp
+        g.voxgpu_sched_destroy.argtypes = [_vp]
         g.voxgpu_launch_count.restype = C.c_ulonglong
         g.voxgpu_timer_create.restype = _vp
         g.voxgpu_timer_destroy.argtypes = [_vp]

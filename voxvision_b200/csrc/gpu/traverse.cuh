@@ -389,81 +389,146 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
 #endif
 
 /* ======================================================================
- * Production traversal.  Same search, same fp32 operations on the same
- * operands as ray_tree<> above (which stays as the readable, instrumented
- * form that mirrors the reference's control flow one to one), reorganised
- * around what the ncu profiles showed (profiles/r01_*): the kernel is bound
- * by instruction issue at ~14 of 32 lanes active, not by memory.
+ * Production traversal.  Same search, same fp32 results as ray_tree<> above
+ * (which stays as the readable, instrumented form that mirrors the
+ * reference's control flow one to one), reorganised around what the ncu
+ * profiles and the per-tile trace showed (profiles/r01_*): the
+ * kernel is bound by instruction issue at ~15 of 32 lanes active, and its
+ * duration by the few heaviest tiles, i.e. by instructions per iteration.
  *
  *  - EAGER EXPANSION.  The reference evaluates an inner node's dividing
  *    planes only after the search of the first child has missed
  *    (search.c:99-148).  Whether and where the ray crosses them is a pure
- *    function of (node, entry point, direction), so it can be computed when
- *    the node is visited -- while all lanes of the warp are at "a node" --
- *    and the resulting calls (child, plane hit point) parked on the stack in
- *    the reference's order.  A warp then has ONE convergence point per
- *    iteration (visit a node) instead of alternating call / pop / expand
- *    phases that each ran at 12-19 lanes; the node record is not re-read and
- *    the entry point is not stacked.  Work the reference would have skipped
- *    (planes of nodes whose first child hits) costs thread-instructions but
- *    no warp-instructions.
+ *    function of (node, entry point, direction), so it is computed when the
+ *    node is visited -- while all lanes of the warp are at "a node" -- and the
+ *    resulting calls (child, plane hit point) are parked on the stack in the
+ *    reference's order.  A warp has ONE convergence point per iteration
+ *    instead of alternating call / pop / expand phases; the node record is
+ *    not re-read and the entry point is not stacked.
  *  - The selection sort of search.c:115-134 is evaluated as a rank
  *    computation on four comparisons and the pending calls are scattered to
  *    their stack slots; nothing is moved between registers.  (Checked
  *    exhaustively against the swap sequence, ties included.)
+ *  - WARP-COOPERATIVE LEAVES.  A leaf holds up to 7 voxels that the reference
+ *    tests one after the other (search.c:51-79); typically 5 of 32 lanes are
+ *    at a leaf at the same time and the other 27 wait.  The tests are
+ *    independent, so the lanes at a leaf hand their voxels out: each group of
+ *    8 lanes serves one leaf (one voxel per lane), reduces to the reference's
+ *    winner -- smallest L1 distance, earliest voxel on ties, which is also what
+ *    the "distance == 0 ends the loop" shortcut of search.c:65-71 selects,
+ *    distances being non-negative -- and returns it to the owning lane.
+ *    The traversal is therefore warp-synchronous: all 32 lanes call it.
+ *  - DIVISION.  (c - o) / d with d fixed per ray: r = RN(1/d) once per ray,
+ *    then q = RN(x*r), q' = RN(q + (x - d*q)*r) with the residual exact by FMA
+ *    is the correctly rounded quotient (Markstein's theorem; checked against
+ *    x/d on 1.0e11 operand pairs, exhaustively in d's mantissa:
+ *    tools/probes/divtest.c) as long as nothing under- or overflows, which an
+ *    exponent-range test on x and (once per ray) on d guarantees; operands
+ *    outside the range take IEEE division (__fdiv_rn).  3 FMA-pipe
+ *    instructions instead of the ~11 of the generic sequence.
  *  - hit_box divides only where the origin was clamped: on an unclamped axis
  *    the reference computes (o-o)/d = +-0 or NaN, which can never become the
  *    winning positive distance (geom.c:79-87).  Divisions are issued
- *    unconditionally on a harmless numerator instead of under a branch, so the
- *    three of a box test (and of the three planes) overlap.
+ *    unconditionally on a harmless numerator instead of under a branch, so
+ *    the three of a box test (and of the three planes) overlap.
  *  - bound checks are predicates, not early-exit branches.
  * ====================================================================== */
 
-__device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3 o, const V3 d, V3 &res)
+struct RayK                 /* per-ray constants */
+{
+    V3 d;                   /* direction */
+    V3 r;                   /* RN(1/d) */
+    bool nx, ny, nz;        /* d < 0 */
+    bool dok;               /* every |d| in [2^-60, 2^61): div3 may use the FMA form */
+};
+
+#define VOXGPU_DIV_LO 8.6736173798840355e-19f   /* 2^-60 */
+#define VOXGPU_DIV_HI 2.305843009213694e+18f    /* 2^61 */
+
+__device__ __forceinline__ bool div_in_range (float x) { const float a = fabsf (x); return a >= VOXGPU_DIV_LO && a < VOXGPU_DIV_HI; }
+
+__device__ __forceinline__ RayK ray_constants (const V3 d)
+{
+    RayK k;
+    k.d = d;
+    k.nx = d.x < 0.0f; k.ny = d.y < 0.0f; k.nz = d.z < 0.0f;
+    k.dok = div_in_range (d.x) && div_in_range (d.y) && div_in_range (d.z);
+    k.r.x = __frcp_rn (d.x); k.r.y = __frcp_rn (d.y); k.r.z = __frcp_rn (d.z);
+    return k;
+}
+
+/* (x/d.x, y/d.y, z/d.z), correctly rounded */
+__device__ __forceinline__ void div3 (float x, float y, float z, const V3 d, const V3 r, bool dok,
+                                      float &qx, float &qy, float &qz)
+{
+    const float lo = fminf (fminf (fabsf (x), fabsf (y)), fabsf (z));
+    const float hi = fmaxf (fmaxf (fabsf (x), fabsf (y)), fabsf (z));
+    if (dok && lo >= VOXGPU_DIV_LO && hi < VOXGPU_DIV_HI)
+    {
+        const float ax = __fmul_rn (x, r.x), ay = __fmul_rn (y, r.y), az = __fmul_rn (z, r.z);
+        qx = __fmaf_rn (__fmaf_rn (-d.x, ax, x), r.x, ax);
+        qy = __fmaf_rn (__fmaf_rn (-d.y, ay, y), r.y, ay);
+        qz = __fmaf_rn (__fmaf_rn (-d.z, az, z), r.z, az);
+    }
+    else
+    {
+        qx = __fdiv_rn (x, d.x); qy = __fdiv_rn (y, d.y); qz = __fdiv_rn (z, d.z);
+    }
+}
+
+__device__ __forceinline__ bool ray_box_fast (const V3 mn, const V3 mx, const V3 o, const V3 d, const V3 r, bool dok, V3 &res)
 {
     const bool lx = o.x < mn.x, hx = o.x > mx.x;
     const bool ly = o.y < mn.y, hy = o.y > mx.y;
     const bool lz = o.z < mn.z, hz = o.z > mx.z;
     const bool kx = lx | hx, ky = ly | hy, kz = lz | hz;
-    res = o;
-    if (!(kx | ky | kz)) return true;                 /* origin inside: geom.c:73 */
+    bool ok = true;
+    res = o;                                            /* origin inside: geom.c:73 */
+    if (kx | ky | kz)
+    {
+        float cx = lx ? mn.x : (hx ? mx.x : o.x);
+        float cy = ly ? mn.y : (hy ? mx.y : o.y);
+        float cz = lz ? mn.z : (hz ? mx.z : o.z);
 
-    float cx = lx ? mn.x : (hx ? mx.x : o.x);
-    float cy = ly ? mn.y : (hy ? mx.y : o.y);
-    float cz = lz ? mn.z : (hz ? mx.z : o.z);
+        /* numerator 1 on unclamped axes: 0/d would take the slow path for nothing */
+        float tx, ty, tz;
+        div3 (kx ? __fsub_rn (cx, o.x) : 1.0f, ky ? __fsub_rn (cy, o.y) : 1.0f, kz ? __fsub_rn (cz, o.z) : 1.0f,
+              d, r, dok, tx, ty, tz);
+        int axis = 0;
+        float tmax = -1.0f;
+        if (kx && tx > tmax) { tmax = tx; }
+        if (ky && ty > tmax) { tmax = ty; axis = 1; }
+        if (kz && tz > tmax) { tmax = tz; axis = 2; }
 
-    /* numerator 1 on unclamped axes: 0/d would take the division's slow path */
-    const float tx = __fdiv_rn (kx ? __fsub_rn (cx, o.x) : 1.0f, d.x);
-    const float ty = __fdiv_rn (ky ? __fsub_rn (cy, o.y) : 1.0f, d.y);
-    const float tz = __fdiv_rn (kz ? __fsub_rn (cz, o.z) : 1.0f, d.z);
-    int axis = 0;
-    float tmax = -1.0f;
-    if (kx && tx > tmax) { tmax = tx; }
-    if (ky && ty > tmax) { tmax = ty; axis = 1; }
-    if (kz && tz > tmax) { tmax = tz; axis = 2; }
-
-    const float px = __fadd_rn (o.x, __fmul_rn (tmax, d.x));
-    const float py = __fadd_rn (o.y, __fmul_rn (tmax, d.y));
-    const float pz = __fadd_rn (o.z, __fmul_rn (tmax, d.z));
-    bool ok = tmax > 0.0f;
-    if (axis != 0) { ok &= !(px < mn.x || px > mx.x); cx = px; }
-    if (axis != 1) { ok &= !(py < mn.y || py > mx.y); cy = py; }
-    if (axis != 2) { ok &= !(pz < mn.z || pz > mx.z); cz = pz; }
-    res.x = cx; res.y = cy; res.z = cz;
+        const float px = __fadd_rn (o.x, __fmul_rn (tmax, d.x));
+        const float py = __fadd_rn (o.y, __fmul_rn (tmax, d.y));
+        const float pz = __fadd_rn (o.z, __fmul_rn (tmax, d.z));
+        ok = tmax > 0.0f;
+        if (axis != 0) { ok &= !(px < mn.x || px > mx.x); cx = px; }
+        if (axis != 1) { ok &= !(py < mn.y || py > mx.y); cy = py; }
+        if (axis != 2) { ok &= !(pz < mn.z || pz > mx.z); cz = pz; }
+        res.x = cx; res.y = cy; res.z = cz;
+    }
     return ok;
 }
 
-/* geom.c:101-123; `neg` = (direction component < 0).  Returns validity, point in res. */
-__device__ __forceinline__ bool ray_plane_fast (const V3 o, const V3 d, float plane, float oa, float da, bool neg,
-                                                const V3 mn, const V3 mx, V3 &res)
+/* geom.c:101-123 for the three dividing planes at once.  Validity in v*, points in p*. */
+__device__ __forceinline__ void ray_planes_fast (const V3 o, const RayK &k, const V3 c, const V3 mn, const V3 mx,
+                                                 bool &v0, bool &v1, bool &v2, V3 &p0, V3 &p1, V3 &p2)
 {
-    float k = __fsub_rn (plane, oa);
-    const bool cand = !(k == 0.0f) && (neg == (k < 0.0f));
-    k = __fdiv_rn (cand ? k : 1.0f, da);
-    res.x = __fadd_rn (o.x, __fmul_rn (k, d.x));
-    res.y = __fadd_rn (o.y, __fmul_rn (k, d.y));
-    res.z = __fadd_rn (o.z, __fmul_rn (k, d.z));
-    return cand & !(res.x < mn.x || res.x > mx.x) & !(res.y < mn.y || res.y > mx.y) & !(res.z < mn.z || res.z > mx.z);
+    const float k0 = __fsub_rn (c.x, o.x), k1 = __fsub_rn (c.y, o.y), k2 = __fsub_rn (c.z, o.z);
+    const bool c0 = !(k0 == 0.0f) && (k.nx == (k0 < 0.0f));
+    const bool c1 = !(k1 == 0.0f) && (k.ny == (k1 < 0.0f));
+    const bool c2 = !(k2 == 0.0f) && (k.nz == (k2 < 0.0f));
+    float t0, t1, t2;
+    div3 (c0 ? k0 : 1.0f, c1 ? k1 : 1.0f, c2 ? k2 : 1.0f, k.d, k.r, k.dok, t0, t1, t2);
+    const V3 d = k.d;
+    p0.x = __fadd_rn (o.x, __fmul_rn (t0, d.x)); p0.y = __fadd_rn (o.y, __fmul_rn (t0, d.y)); p0.z = __fadd_rn (o.z, __fmul_rn (t0, d.z));
+    p1.x = __fadd_rn (o.x, __fmul_rn (t1, d.x)); p1.y = __fadd_rn (o.y, __fmul_rn (t1, d.y)); p1.z = __fadd_rn (o.z, __fmul_rn (t1, d.z));
+    p2.x = __fadd_rn (o.x, __fmul_rn (t2, d.x)); p2.y = __fadd_rn (o.y, __fmul_rn (t2, d.y)); p2.z = __fadd_rn (o.z, __fmul_rn (t2, d.z));
+    v0 = c0 & !(p0.x < mn.x || p0.x > mx.x) & !(p0.y < mn.y || p0.y > mx.y) & !(p0.z < mn.z || p0.z > mx.z);
+    v1 = c1 & !(p1.x < mn.x || p1.x > mx.x) & !(p1.y < mn.y || p1.y > mx.y) & !(p1.z < mn.z || p1.z > mx.z);
+    v2 = c2 & !(p2.x < mn.x || p2.x > mx.x) & !(p2.y < mn.y || p2.y > mx.y) & !(p2.z < mn.z || p2.z > mx.z);
 }
 
 /* geom.c:53-65 with the direction signs hoisted out of the loop */
@@ -475,120 +540,224 @@ __device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool 
     return (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
 }
 
-__device__ __forceinline__ void ray_tree_fast (const TreeRef &tr, unsigned start, const V3 origin, const V3 d,
-                                               float4 *stack, RayResult &out)
+#define VOXGPU_FULL 0xffffffffu
+#define VOXGPU_DEAD 0xffffffffu
+#define VOXGPU_COOP_MAX_LANES 12     /* more lanes than this at a leaf: everyone loops over its own voxels */
+
+/*
+ * vox_ray_tree_intersection (search.c:8-153) for the 32 rays of a warp.
+ * WARP-SYNCHRONOUS: all 32 lanes must call it together; `has_ray` says whether
+ * this lane has a ray at all.  `stack` is VOXGPU_RAY_STACK float4 entries of
+ * per-thread scratch.  Returns the number of iterations the warp needed.
+ */
+__device__ __forceinline__ int ray_tree_warp (const TreeRef &tr, unsigned start, const V3 origin, const V3 dir,
+                                              bool has_ray, float4 *stack, RayResult &out)
 {
-    const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
+    /* what a lane does after the node visit of this iteration */
+    enum { IDLE = 0, GO = 1, POP = 2, LEAF = 3 };
+
+    const RayK k = ray_constants (dir);
+    const V3 d = dir;
+    const int lane = threadIdx.x & 31;
+    const float inf = __int_as_float (0x7f800000);
     int sp = 0;
-    unsigned cur = start;
+    unsigned cur = has_ray ? start : VOXGPU_DEAD;       /* VOXGPU_DEAD: this lane's search is over */
     V3 org = origin;
+    /* written only by a lane that is at a leaf; read (shuffled) only from such lanes */
+    V3 lf_e = origin;
+    unsigned lf_link = 0, lf_info = 0;
 
+    /* A finished ray's stack is dead: the hit point and voxel wait there (stack[0], stack[1])
+       instead of in five registers that every branch of the loop would have to carry. */
     out.leaf = -1;
-    out.voxel = -1;
+    int iterations = 0;             /* node visits of the slowest lane: the cost of this warp's rays */
 
-    for (;;)
+    while (__any_sync (VOXGPU_FULL, cur != VOXGPU_DEAD))
     {
-        /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
-        float4 q0, q1;
-        load_rec (tr.rec + cur, q0, q1);
-        const unsigned meta = __float_as_uint (q0.w);
-        const unsigned link = __float_as_uint (q1.w);
-        const unsigned kind = meta & 3u;
-        const V3 mn = v3 (q0), mx = v3 (q1);
-        bool descend = false;
-
-        V3 entry;
-        if (ray_box_fast (mn, mx, org, d, entry))
+        int st = IDLE;
+        iterations++;
+        if (cur != VOXGPU_DEAD)
         {
-            if (kind == VOXGPU_KIND_INNER)
-            {
-                const V3 c = v3 (__ldg (tr.ctr + cur));
-                const unsigned mask = (meta >> 8) & 0xffu;
-                const unsigned sub = subspace_fast (c, entry, nx, ny, nz);
+            /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
+            float4 q0, q1;
+            load_rec (tr.rec + cur, q0, q1);
+            const unsigned meta = __float_as_uint (q0.w);
+            const unsigned link = __float_as_uint (q1.w);
+            const unsigned kind = meta & 3u;
+            const V3 mn = v3 (q0), mx = v3 (q1);
+            V3 entry;
 
-                /* search.c:105-113: the three dividing planes, from the entry point */
-                V3 p0, p1, p2;
-                const bool v0 = ray_plane_fast (entry, d, c.x, entry.x, d.x, nx, mn, mx, p0);
-                const bool v1 = ray_plane_fast (entry, d, c.y, entry.y, d.y, ny, mn, mx, p1);
-                const bool v2 = ray_plane_fast (entry, d, c.z, entry.z, d.z, nz, mn, mx, p2);
-                if (v0 | v1 | v2)
+            st = POP;                                                               /* search.c:22-27 */
+            if (ray_box_fast (mn, mx, org, d, k.r, k.dok, entry))
+            {
+                if (kind == VOXGPU_KIND_INNER)
                 {
-                    /* search.c:115-134 as ranks.  Invalid planes get +inf and sort last. */
-                    const float inf = __int_as_float (0x7f800000);
-                    const float m0 = v0 ? l1_metric (entry, p0) : inf;
-                    const float m1 = v1 ? l1_metric (entry, p1) : inf;
-                    const float m2 = v2 ? l1_metric (entry, p2) : inf;
-                    const bool A = m1 < m0, B = m2 < m1, C = m2 < m0, D = m0 < m1;
-                    const bool b01 = !A && (!C || D);      /* plane 0 is tried before plane 1 */
-                    const bool b02 = !C && (!A || !B);
-                    const bool b12 = !B && (A || !C);
-                    /* search.c:137: the subspace flips of the planes tried so far accumulate */
-                    const unsigned s0 = sub ^ 1u ^ ((v1 && !b01) ? 2u : 0u) ^ ((v2 && !b02) ? 4u : 0u);
-                    const unsigned s1 = sub ^ 2u ^ ((v0 &&  b01) ? 1u : 0u) ^ ((v2 && !b12) ? 4u : 0u);
-                    const unsigned s2 = sub ^ 4u ^ ((v0 &&  b02) ? 1u : 0u) ^ ((v1 &&  b12) ? 2u : 0u);
-                    const bool e0 = v0 && ((mask >> s0) & 1u);
-                    const bool e1 = v1 && ((mask >> s1) & 1u);
-                    const bool e2 = v2 && ((mask >> s2) & 1u);
-                    /* the call tried first must be popped first: slot = number of later calls */
-                    if (e0) stack[sp + (int)(e1 && b01) + (int)(e2 && b02)] =
-                        make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
-                    if (e1) stack[sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
-                        make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
-                    if (e2) stack[sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
-                        make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
-                    sp += (int) e0 + (int) e1 + (int) e2;
+                    const V3 c = v3 (__ldg (tr.ctr + cur));
+                    const unsigned mask = (meta >> 8) & 0xffu;
+                    const unsigned sub = subspace_fast (c, entry, k.nx, k.ny, k.nz);
+
+                    /* search.c:105-113: the three dividing planes, from the entry point */
+                    V3 p0, p1, p2;
+                    bool v0, v1, v2;
+                    ray_planes_fast (entry, k, c, mn, mx, v0, v1, v2, p0, p1, p2);
+                    if (v0 | v1 | v2)
+                    {
+                        /* search.c:115-134 as ranks.  Invalid planes get +inf and sort last. */
+                        const float m0 = v0 ? l1_metric (entry, p0) : inf;
+                        const float m1 = v1 ? l1_metric (entry, p1) : inf;
+                        const float m2 = v2 ? l1_metric (entry, p2) : inf;
+                        const bool A = m1 < m0, B = m2 < m1, C = m2 < m0, D = m0 < m1;
+                        const bool b01 = !A && (!C || D);      /* plane 0 is tried before plane 1 */
+                        const bool b02 = !C && (!A || !B);
+                        const bool b12 = !B && (A || !C);
+                        /* search.c:137: the subspace flips of the planes tried so far accumulate */
+                        const unsigned s0 = sub ^ 1u ^ ((v1 && !b01) ? 2u : 0u) ^ ((v2 && !b02) ? 4u : 0u);
+                        const unsigned s1 = sub ^ 2u ^ ((v0 &&  b01) ? 1u : 0u) ^ ((v2 && !b12) ? 4u : 0u);
+                        const unsigned s2 = sub ^ 4u ^ ((v0 &&  b02) ? 1u : 0u) ^ ((v1 &&  b12) ? 2u : 0u);
+                        const bool e0 = v0 && ((mask >> s0) & 1u);
+                        const bool e1 = v1 && ((mask >> s1) & 1u);
+                        const bool e2 = v2 && ((mask >> s2) & 1u);
+                        /* the call tried first must be popped first: slot = number of later calls */
+                        if (e0) stack[sp + (int)(e1 && b01) + (int)(e2 && b02)] =
+                            make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
+                        if (e1) stack[sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
+                            make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
+                        if (e2) stack[sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
+                            make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
+                        sp += (int) e0 + (int) e1 + (int) e2;
+                    }
+                    /* search.c:83-97: the child the entry point lies in goes first */
+                    if ((mask >> sub) & 1u) { cur = child_id (link, mask, sub); org = entry; st = GO; }
                 }
-                /* search.c:83-97: the child the entry point lies in goes first */
-                if ((mask >> sub) & 1u)
+                else if (kind == VOXGPU_KIND_DENSE)
                 {
-                    cur = child_id (link, mask, sub);
-                    org = entry;
-                    descend = true;
+                    /* search.c:31-37 */
+                    out.leaf = (int) cur;
+                    stack[0] = make_float4 (entry.x, entry.y, entry.z, __int_as_float (-1));
+                    cur = VOXGPU_DEAD; st = IDLE;
+                }
+                else
+                {
+                    lf_e = entry; lf_link = link; lf_info = (meta >> 2) | (k.dok ? 0x80000000u : 0u);
+                    st = LEAF;
                 }
             }
-            else if (kind == VOXGPU_KIND_DENSE)
+        }
+
+        /* ---- leaves, search.c:39-81 ---- */
+        const unsigned leafmask = __ballot_sync (VOXGPU_FULL, st == LEAF);
+        if (leafmask)
+        {
+            float best = inf;           /* owner's result */
+            int best_i = 0;
+            V3 best_p = lf_e;
+            const bool coop = __popc (leafmask) <= VOXGPU_COOP_MAX_LANES &&
+                              !__any_sync (VOXGPU_FULL, st == LEAF && (lf_info & 0x7fffffffu) > 8u);
+            if (coop)
             {
-                out.leaf = (int) cur; out.voxel = -1; out.point = entry;
-                return;
+                const int group = lane >> 3, slot = lane & 7;
+                const int myrank = __popc (leafmask & ((1u << lane) - 1u));
+                unsigned m = leafmask;
+                for (int base = 0; m; base += 4)
+                {
+                    /* the four lowest remaining leaf lanes are served by the four groups of eight */
+                    const int l0 = __ffs (m) - 1; m &= m - 1;
+                    const int l1 = __ffs (m) - 1; m &= m - 1;
+                    const int l2 = __ffs (m) - 1; m &= m - 1;
+                    const int l3 = __ffs (m) - 1; m &= m - 1;
+                    const int src = group == 0 ? l0 : (group == 1 ? l1 : (group == 2 ? l2 : l3));
+                    const int from = src >= 0 ? src : lane;
+                    V3 e, dd, rr;
+                    e.x = __shfl_sync (VOXGPU_FULL, lf_e.x, from); e.y = __shfl_sync (VOXGPU_FULL, lf_e.y, from); e.z = __shfl_sync (VOXGPU_FULL, lf_e.z, from);
+                    dd.x = __shfl_sync (VOXGPU_FULL, d.x, from); dd.y = __shfl_sync (VOXGPU_FULL, d.y, from); dd.z = __shfl_sync (VOXGPU_FULL, d.z, from);
+                    rr.x = __shfl_sync (VOXGPU_FULL, k.r.x, from); rr.y = __shfl_sync (VOXGPU_FULL, k.r.y, from); rr.z = __shfl_sync (VOXGPU_FULL, k.r.z, from);
+                    const unsigned lnk = __shfl_sync (VOXGPU_FULL, lf_link, from);
+                    const unsigned info = __shfl_sync (VOXGPU_FULL, lf_info, from);
+                    float dist = inf;
+                    V3 far = e;
+                    if (src >= 0 && (unsigned) slot < (info & 0x7fffffffu))
+                    {
+                        const float4 dq = __ldg (tr.dots + (size_t) lnk + slot);
+                        V3 vmin = v3 (dq), vmax;
+                        vmax.x = __fadd_rn (vmin.x, tr.vx);
+                        vmax.y = __fadd_rn (vmin.y, tr.vy);
+                        vmax.z = __fadd_rn (vmin.z, tr.vz);
+                        if (ray_box_fast (vmin, vmax, e, dd, rr, (info >> 31) != 0, far))
+                        {
+                            const float t = l1_metric (e, far);
+                            if (t < inf) dist = t;              /* search.c:72: NaN and inf never win */
+                        }
+                    }
+                    /* smallest distance, earliest voxel on ties, within the group of eight */
+                    int idx = slot;
+                    #pragma unroll
+                    for (int off = 4; off; off >>= 1)
+                    {
+                        const float od = __shfl_xor_sync (VOXGPU_FULL, dist, off);
+                        const int oi = __shfl_xor_sync (VOXGPU_FULL, idx, off);
+                        if (od < dist || (od == dist && oi < idx)) { dist = od; idx = oi; }
+                    }
+                    /* back to the owner: the group that served lane rank myrank holds its answer */
+                    const int g = myrank - base;
+                    const bool mine = st == LEAF && g >= 0 && g < 4;
+                    const int head = mine ? 8 * g : lane;
+                    const float bd = __shfl_sync (VOXGPU_FULL, dist, head);
+                    const int bi = __shfl_sync (VOXGPU_FULL, idx, head);
+                    const int win = mine ? head + bi : lane;
+                    const float fx = __shfl_sync (VOXGPU_FULL, far.x, win);
+                    const float fy = __shfl_sync (VOXGPU_FULL, far.y, win);
+                    const float fz = __shfl_sync (VOXGPU_FULL, far.z, win);
+                    if (mine) { best = bd; best_i = bi; best_p.x = fx; best_p.y = fy; best_p.z = fz; }
+                }
             }
-            else
+            else if (st == LEAF)
             {
-                /* leaf, search.c:39-81 */
-                const unsigned n = meta >> 2;
-                float closest = __int_as_float (0x7f800000);
+                const unsigned n = lf_info & 0x7fffffffu;
                 for (unsigned i=0; i<n; i++)
                 {
-                    const float4 dq = __ldg (tr.dots + (size_t)link + i);
+                    const float4 dq = __ldg (tr.dots + (size_t) lf_link + i);
                     V3 vmin = v3 (dq), vmax, far;
                     vmax.x = __fadd_rn (vmin.x, tr.vx);
                     vmax.y = __fadd_rn (vmin.y, tr.vy);
                     vmax.z = __fadd_rn (vmin.z, tr.vz);
-                    if (ray_box_fast (vmin, vmax, entry, d, far))
+                    if (ray_box_fast (vmin, vmax, lf_e, d, k.r, k.dok, far))
                     {
-                        const float dist = l1_metric (entry, far);
-                        if (dist == 0.0f)
-                        {
-                            out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
-                            return;
-                        }
-                        if (dist < closest)
-                        {
-                            closest = dist;
-                            out.leaf = (int) cur; out.voxel = (int)(link + i); out.point = far;
-                        }
+                        const float dist = l1_metric (lf_e, far);
+                        if (dist < best) { best = dist; best_i = (int) i; best_p = far; }
+                        if (dist == 0.0f) break;                /* search.c:65-71 */
                     }
                 }
-                if (out.leaf >= 0) return;
+            }
+            if (st == LEAF)
+            {
+                if (best < inf)
+                {
+                    out.leaf = (int) cur;
+                    stack[0] = make_float4 (best_p.x, best_p.y, best_p.z, __uint_as_float (lf_link + (unsigned) best_i));
+                    cur = VOXGPU_DEAD;
+                }
+                else st = POP;
             }
         }
 
-        if (!descend)
+        if (st == POP)
         {
             /* this call missed: go on with the nearest pending one */
-            if (sp == 0) return;
-            const float4 e = stack[--sp];
-            org.x = e.x; org.y = e.y; org.z = e.z;
-            cur = __float_as_uint (e.w);
+            if (sp == 0) cur = VOXGPU_DEAD;
+            else
+            {
+                const float4 e = stack[--sp];
+                org.x = e.x; org.y = e.y; org.z = e.z;
+                cur = __float_as_uint (e.w);
+            }
         }
     }
+    out.voxel = -1;
+    if (out.leaf >= 0)
+    {
+        const float4 h = stack[0];
+        out.point.x = h.x; out.point.y = h.y; out.point.z = h.z;
+        out.voxel = __float_as_int (h.w);
+    }
+    return iterations;
 }

@@ -286,13 +286,15 @@ k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const f
         unsigned long long *stats)
 {
     const size_t i = (size_t) blockIdx.x * RAYS_BLOCK + threadIdx.x;
-    if (i >= n) return;
+    const bool live = i < n;            /* the production traversal is warp-synchronous: nobody leaves early */
     float4 stack[VOXGPU_RAY_STACK];
-    const float4 o = __ldg (origins + i), d = __ldg (dirs + i);
+    const float4 o = live ? __ldg (origins + i) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+    const float4 d = live ? __ldg (dirs + i) : make_float4 (1.0f, 1.0f, 1.0f, 0.0f);
     RayResult r;
     RayCounters c = {0, 0, 0, 0, 0, 0, 0};
-    if (STATS) ray_tree<true> (tr, start, v3 (o), v3 (d), stack, r, &c);
-    else ray_tree_fast (tr, start, v3 (o), v3 (d), stack, r);
+    if (STATS) { if (live) ray_tree<true> (tr, start, v3 (o), v3 (d), stack, r, &c); }
+    else ray_tree_warp (tr, start, v3 (o), v3 (d), live, stack, r);
+    if (!live) return;
     if (leaf_ids) leaf_ids[i] = r.leaf;
     if (voxels) voxels[i] = r.voxel;
     if (points && r.leaf >= 0) points[i] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
@@ -569,11 +571,67 @@ __device__ __forceinline__ unsigned smid ()
     return r;
 }
 
+/*
+ * Expensive-tiles-first scheduling across consecutive frames.  A few percent of
+ * the tiles of a frame (rays grazing along a surface) take 30-100 times longer
+ * than the median tile; when such a tile is handed out late the whole GPU waits
+ * for it (the per-tile trace showed the last 40% of the kernel to be a tail).
+ * Frames of an animation are coherent, so every launch records the cost of each
+ * tile (iterations of its warp), and before the next launch on the same schedule
+ * a small kernel sorts the tiles into three classes by the largest cost seen in
+ * their 5x5-tile neighbourhood (exactly which tile is expensive changes with the
+ * slightest camera move; that its neighbourhood is does not).  The render kernel
+ * then hands out class 0, 1, 2 in that order.  A pure performance hint: every
+ * tile is still rendered exactly once and results do not depend on it.
+ */
+struct DevSched
+{
+    const unsigned *list[3];      /* tiles by class, filled by k_sched_build */
+    unsigned *count;              /* [3]; zeroed again by the render kernel's last warp */
+    unsigned char *cost_next;     /* per tile, written by this launch */
+};
+
+#define SCHED_RADIUS 2
+
+__global__ void k_sched_build (const unsigned char * __restrict__ cost_prev, int tiles_x, int tiles_y,
+                               unsigned t_heavy, unsigned t_mid,
+                               unsigned *list0, unsigned *list1, unsigned *list2, unsigned *count)
+{
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntiles = tiles_x * tiles_y;
+    unsigned cls = 3;
+    if (tile < ntiles)
+    {
+        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        unsigned m = 0;
+        for (int dy=-SCHED_RADIUS; dy<=SCHED_RADIUS; dy++)
+            for (int dx=-SCHED_RADIUS; dx<=SCHED_RADIUS; dx++)
+            {
+                const int x = tx + dx, y = ty + dy;
+                if (x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) m = max (m, (unsigned) __ldg (cost_prev + y * tiles_x + x));
+            }
+        cls = m >= t_heavy ? 0u : (m >= t_mid ? 1u : 2u);
+    }
+    /* warp-aggregated append to the three lists */
+    const int lane = threadIdx.x & 31;
+    unsigned *lists[3] = {list0, list1, list2};
+    #pragma unroll
+    for (unsigned c=0; c<3; c++)
+    {
+        const unsigned m = __ballot_sync (0xffffffffu, cls == c);
+        if (!m) continue;
+        unsigned base = 0;
+        if (lane == __ffs (m) - 1) base = atomicAdd (count + c, (unsigned) __popc (m));
+        base = __shfl_sync (0xffffffffu, base, __ffs (m) - 1);
+        if (cls == c) lists[c][base + __popc (m & ((1u << lane) - 1u))] = (unsigned) tile;
+    }
+}
+
 template <bool OUT_HITS, unsigned STRIPS>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
-                     unsigned *counters, unsigned long long *trace)
+                     unsigned *counters, unsigned long long *trace, DevSched sch)
 {
     const int tiles_x = fr.w >> 3;
     const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
@@ -589,7 +647,9 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
        computes; interleaved, stores and traversal overlap for the whole kernel,
        which matters when the pixels go to mapped host memory over PCIe. */
     const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
-    const unsigned tickets = per_strip * STRIPS;
+    unsigned n0 = 0, n1 = 0;
+    if (sch.count) { n0 = sch.count[0]; n1 = n0 + sch.count[1]; }
+    const unsigned tickets = sch.count ? ntiles : per_strip * STRIPS;
 
     for (;;)
     {
@@ -597,8 +657,14 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         if (lane == 0) ticket = atomicAdd (&counters[0], 1u);
         ticket = __shfl_sync (0xffffffffu, ticket, 0);
         if (ticket >= tickets) break;
-        const unsigned tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
-        if (tile >= ntiles) continue;
+        unsigned tile;
+        if (sch.count)
+            tile = ticket < n0 ? sch.list[0][ticket] : (ticket < n1 ? sch.list[1][ticket - n0] : sch.list[2][ticket - n1]);
+        else
+        {
+            tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
+            if (tile >= ntiles) continue;
+        }
 
         unsigned long long t0 = 0;
         if (trace) t0 = globaltimer_ns ();
@@ -607,7 +673,8 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         const int sy = fr.y0 + ry;
         const V3 dir = screen2world (cam, sx, sy, fr.w);
         RayResult r;
-        ray_tree_fast (tr, 0, origin, dir, stack, r);
+        const int iterations = ray_tree_warp (tr, 0, origin, dir, true, stack, r);
+        if (sch.cost_next && lane == 0) sch.cost_next[tile] = (unsigned char) min (iterations, 255);
 
         unsigned color = 0;
         if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
@@ -624,13 +691,18 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
             /* development trace (voxgpu_set_trace): when and where each tile ran */
             trace[3*(size_t) tile] = t0;
             trace[3*(size_t) tile + 1] = globaltimer_ns ();
-            trace[3*(size_t) tile + 2] = ((unsigned long long) smid () << 32) | (blockIdx.x * (RENDER_BLOCK/32) + (threadIdx.x >> 5));
+            trace[3*(size_t) tile + 2] = ((unsigned long long) smid () << 32) | (unsigned) iterations;
         }
     }
     if (lane == 0)
     {
         const unsigned done = atomicAdd (&counters[1], 1u);
-        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
+        if (done + 1 == total_warps)
+        {
+            counters[0] = 0; counters[1] = 0;
+            if (sch.count) { sch.count[0] = 0; sch.count[1] = 0; sch.count[2] = 0; }   /* for the next k_sched_build */
+            __threadfence ();
+        }
     }
 }
 
@@ -665,9 +737,89 @@ static unsigned* counter_slot (int device)
     return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
 }
 
+struct voxgpu_sched
+{
+    int device;
+    int w, y0, rows;              /* geometry the recorded costs refer to */
+    unsigned cap;                 /* tiles the buffers can hold */
+    unsigned *list[3];
+    unsigned *count;
+    unsigned char *cost[2];
+    int cur;                      /* cost buffer the next launch reads */
+    unsigned t_heavy, t_mid;
+};
+
+extern "C" voxgpu_sched* voxgpu_sched_create (void)
+{
+    voxgpu_sched *sc = (voxgpu_sched*) calloc (1, sizeof *sc);
+    const char *e1 = getenv ("VOXGPU_HEAVY_ITERS"), *e2 = getenv ("VOXGPU_MID_ITERS");
+    sc->t_heavy = e1 ? (unsigned) atoi (e1) : 24u;
+    sc->t_mid = e2 ? (unsigned) atoi (e2) : 8u;
+    sc->device = -1;
+    return sc;
+}
+
+static void sched_release (voxgpu_sched *sc)
+{
+    for (int i=0; i<3; i++) { cudaFree (sc->list[i]); sc->list[i] = NULL; }
+    cudaFree (sc->cost[0]); cudaFree (sc->cost[1]); cudaFree (sc->count);
+    sc->cost[0] = sc->cost[1] = NULL; sc->count = NULL; sc->cap = 0;
+}
+
+extern "C" void voxgpu_sched_destroy (voxgpu_sched *sc)
+{
+    if (!sc) return;
+    sched_release (sc);
+    free (sc);
+}
+
+/* Sort the tiles for this launch from the costs the previous one recorded
+   (all zero after a change of geometry: plain order). */
+static int sched_prepare (voxgpu_sched *sc, int device, int w, int y0, int rows, cudaStream_t st, DevSched *out)
+{
+    const int tiles_x = w >> 3, tiles_y = rows >> 2;
+    const unsigned ntiles = (unsigned) (tiles_x * tiles_y);
+    const bool restart = sc->device != device || sc->w != w || sc->y0 != y0 || sc->rows != rows || !sc->count;
+    if (restart)
+    {
+        if (sc->cap < ntiles || sc->device != device)
+        {
+            sched_release (sc);
+            for (int i=0; i<3; i++) CU (cudaMalloc (&sc->list[i], (size_t) ntiles * sizeof (unsigned)));
+            for (int i=0; i<2; i++) CU (cudaMalloc (&sc->cost[i], ntiles));
+            CU (cudaMalloc (&sc->count, 3 * sizeof (unsigned)));
+            sc->cap = ntiles;
+        }
+        CU (cudaMemsetAsync (sc->count, 0, 3 * sizeof (unsigned), st));
+        CU (cudaMemsetAsync (sc->cost[0], 0, ntiles, st));
+        sc->device = device; sc->w = w; sc->y0 = y0; sc->rows = rows; sc->cur = 0;
+    }
+    const int p = sc->cur, q = p ^ 1;
+    k_sched_build<<<(ntiles + 255) / 256, 256, 0, st>>> (sc->cost[p], tiles_x, tiles_y, sc->t_heavy, sc->t_mid,
+                                                         sc->list[0], sc->list[1], sc->list[2], sc->count);
+    g_launches++;
+    CU (cudaGetLastError ());
+    out->list[0] = sc->list[0]; out->list[1] = sc->list[1]; out->list[2] = sc->list[2];
+    out->count = sc->count;
+    out->cost_next = sc->cost[q];
+    sc->cur = q;
+    return 0;
+}
+
+extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                                    const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                                    voxgpu_stream s, voxgpu_sched *sched);
+
 extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                               const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                               voxgpu_stream s)
+{
+    return voxgpu_render_sched (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, NULL);
+}
+
+extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                                    const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                                    voxgpu_stream s, voxgpu_sched *sched)
 {
     if (check_tree (t, 0, "voxgpu_render")) return -1;
     if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
@@ -708,15 +860,19 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
         if (grid > blocks) grid = blocks;
         cudaStream_t st = (cudaStream_t) s;
         float4 *pts = (float4*) d_pts;
+        DevSched sch;
+        memset (&sch, 0, sizeof sch);
+        if (sched && g_variant == 1 && sched->t_heavy &&
+            sched_prepare (sched, t->device, df.w, df.y0, df.rows, st, &sch)) return -1;
         if (g_variant == 2)
         {   /* raster tile order, kept for A/B measurements */
-            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
-            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace);
+            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
+            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
         }
         else
         {
-            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
-            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace);
+            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
+            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
         }
     }
     g_launches++;
@@ -748,6 +904,7 @@ struct voxgpu_present
     uint32_t *fb;                         /* device framebuffer, w*h */
     cudaStream_t stream[PRESENT_MAX_BANDS];
     cudaEvent_t done[PRESENT_MAX_BANDS];
+    voxgpu_sched *sched[PRESENT_MAX_BANDS];  /* heavy-first tile order, frame to frame */
     cudaEvent_t start;
     int in_flight;
 };
@@ -759,6 +916,7 @@ extern "C" void voxgpu_present_destroy (voxgpu_present *p)
     {
         if (p->stream[i]) { cudaStreamSynchronize (p->stream[i]); cudaStreamDestroy (p->stream[i]); }
         if (p->done[i]) cudaEventDestroy (p->done[i]);
+        voxgpu_sched_destroy (p->sched[i]);
     }
     if (p->start) cudaEventDestroy (p->start);
     cudaFree (p->fb);
@@ -790,6 +948,7 @@ extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
         if (prio > least) prio = least;
         if ((e = cudaStreamCreateWithPriority (&p->stream[i], cudaStreamNonBlocking, prio)) != cudaSuccess ||
             (e = cudaEventCreate (&p->done[i])) != cudaSuccess) goto bad;
+        p->sched[i] = voxgpu_sched_create ();
     }
     return p;
 bad:
@@ -823,7 +982,7 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
         uint32_t *src = p->fb + (size_t) y0 * p->w;
-        if (voxgpu_render (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i])) return -1;
+        if (voxgpu_render_sched (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], p->sched[i])) return -1;
         char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
         if (host_pitch_bytes == (size_t) p->w * 4)
             CU (cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]));
