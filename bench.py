@@ -212,69 +212,67 @@ def run_own(args):
     frame_desc = api.GpuFrame(W, H, 0, H, W, vv.QUALITY_BEST, fmt)
 
     # ---- device-resident leg ------------------------------------------------
+    # The frames of the path are independent: FRAME_STREAMS of them are in flight per GPU
+    # (frame f on stream f % FRAME_STREAMS, each into its own framebuffer), so the long tail
+    # of one frame's kernel (a few expensive tiles) is filled by the next frame's tiles.
     frame_bytes = W * H * 4
     if world > 1:
-        render_stream = torch.cuda.Stream()
+        from voxvision_b200 import multi
+        tstreams = [torch.cuda.Stream() for _ in range(FRAME_STREAMS)]
         comm_stream = torch.cuda.Stream()
-        s_ptr = C.c_void_p(render_stream.cuda_stream)
+        streams = [C.c_void_p(t.cuda_stream) for t in tstreams]
         ring = torch.empty((2, GATHER_BATCH, H, W), dtype=torch.int32, device="cuda")
         ring_ptr = lambda i: ring[(i // GATHER_BATCH) % 2, i % GATHER_BATCH].data_ptr()
-        gathered = ([torch.empty_like(ring[0]) for _ in range(world)] if rank == 0 else None)
+        gather = multi.FrameGather(ring[0], dst=0)
         d_tex_t = torch.from_numpy(tex.copy()).cuda()
         d_tex = d_tex_t.data_ptr()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     else:
-        s_ptr = C.c_void_p(g.voxgpu_stream_create())
-        streams = [s_ptr] + [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS - 1)]
-        scheds = [C.c_void_p(g.voxgpu_sched_create()) for _ in streams]   # heavy-tiles-first, frame to frame
+        streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS)]
         bufs = [vv.DeviceBuffer(frame_bytes) for _ in range(RING)]
         ring_ptr = lambda i: bufs[i % RING].ptr
         d_tex_b = vv.DeviceBuffer.from_array(tex)
         d_tex = d_tex_b.ptr
         flush_b = vv.DeviceBuffer(256 << 20)
+    s_ptr = streams[0]
+    # the frame-to-frame tile schedule (voxgpu_sched) is off here: with several frames in flight the
+    # tails it removes are already filled, and its sorting kernel costs 6 us per frame (profiles/)
+    scheds = [None for _ in streams]
 
     def flush_l2():
         if world > 1:
-            with torch.cuda.stream(render_stream):
+            with torch.cuda.stream(tstreams[0]):
                 flush.zero_()
         else:
             g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)
 
     def device_step():
-        """360 launches back to back.  N=1: the frames are independent, so FRAME_STREAMS of them are
-        in flight at once (frame f on stream f % FRAME_STREAMS, its own framebuffer): the long tail of
-        one frame's kernel (a few heavy tiles) is filled by the next frame's tiles.
-        N>1: every GATHER_BATCH frames go to GPU 0 on the side stream."""
+        """360 launches back to back.  N>1: every GATHER_BATCH finished
+        frames go to GPU 0 with NCCL on a side stream while the next batch renders."""
         flush_l2()
-        if world == 1:
-            for st in streams[1:]:
-                g.voxgpu_stream_join(st, s_ptr)  # the step's first mark / flush precedes every stream's frames
-            for f in range(FRAMES):
-                rc = g.voxgpu_render_sched(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
-                                           streams[f % FRAME_STREAMS], scheds[f % FRAME_STREAMS])
-                if rc:
-                    raise vv.VoxError(g.voxgpu_last_error().decode())
-            for st in streams[1:]:
-                g.voxgpu_stream_join(s_ptr, st)  # stream 0 (where the timer marks go) ends after all of them
-            return
+        for st in streams[1:]:
+            g.voxgpu_stream_join(st, s_ptr)      # the step's first mark / flush precedes every stream's frames
         batch_done = []
         for f in range(FRAMES):
-            if world > 1 and f % GATHER_BATCH == 0 and f >= 2 * GATHER_BATCH:
-                render_stream.wait_event(batch_done[f // GATHER_BATCH - 2])   # ring slot free again
-            rc = g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None, s_ptr)
+            k = f % FRAME_STREAMS
+            if world > 1 and f >= 2 * GATHER_BATCH and f % GATHER_BATCH < FRAME_STREAMS:
+                tstreams[k].wait_event(batch_done[f // GATHER_BATCH - 2])      # this half of the ring is free again
+            rc = g.voxgpu_render_sched(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
+                                       streams[k], scheds[k])
             if rc:
                 raise vv.VoxError(g.voxgpu_last_error().decode())
             if world > 1 and f % GATHER_BATCH == GATHER_BATCH - 1:
-                ev = torch.cuda.Event()
-                ev.record(render_stream)
+                for t in tstreams:
+                    comm_stream.wait_stream(t)                                  # the whole batch is rendered
                 with torch.cuda.stream(comm_stream):
-                    comm_stream.wait_event(ev)
-                    dist.gather(ring[(f // GATHER_BATCH) % 2], gathered, dst=0)
+                    gather(ring[(f // GATHER_BATCH) % 2])
                     done = torch.cuda.Event()
                     done.record(comm_stream)
                 batch_done.append(done)
+        for st in streams[1:]:
+            g.voxgpu_stream_join(s_ptr, st)      # stream 0 (where the timer marks go) ends after all of them
         if world > 1:
-            render_stream.wait_stream(comm_stream)
+            tstreams[0].wait_stream(comm_stream)
 
     def sync_all():
         if world > 1:
