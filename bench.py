@@ -216,52 +216,71 @@ def run_own(args):
     # (frame f on stream f % FRAME_STREAMS, each into its own framebuffer), so the long tail
     # of one frame's kernel (a few expensive tiles) is filled by the next frame's tiles.
     frame_bytes = W * H * 4
+    streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS)]
+    s_ptr = streams[0]
+    d_tex_b = vv.DeviceBuffer.from_array(tex)
+    d_tex = d_tex_b.ptr
+    flush_b = vv.DeviceBuffer(256 << 20)
+    gather_mode, gather_base, peer_base = "none", None, None
     if world > 1:
+        # The gather to GPU 0 is fused into the render kernel's store: rank 0 owns a buffer with room
+        # for every rank's 360 frames, the other ranks map it (CUDA IPC) and render straight into it
+        # over NVLink.  No copy kernel, no NCCL kernel competing with the persistent render CTAs for SMs.
         from voxvision_b200 import multi
-        tstreams = [torch.cuda.Stream() for _ in range(FRAME_STREAMS)]
-        comm_stream = torch.cuda.Stream()
-        streams = [C.c_void_p(t.cuda_stream) for t in tstreams]
+        region_bytes = FRAMES * frame_bytes
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            gather_base = g.voxgpu_malloc(world * region_bytes)
+            if not gather_base:
+                raise vv.VoxError(g.voxgpu_last_error().decode())
+            hb = (C.c_ubyte * 64)()
+            ok = g.voxgpu_ipc_export(gather_base, hb) == 0
+            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+        dist.broadcast(handle, 0)
+        if rank == 0:
+            peer_base = gather_base
+        else:
+            hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            peer_base = g.voxgpu_ipc_open(hb)
+        flag = torch.tensor([1 if peer_base else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_mode = "peer-store" if int(flag.item()) else "nccl"
+    if gather_mode == "peer-store":
+        my_region = peer_base + rank * region_bytes
+        ring_ptr = lambda i: my_region + (i % FRAMES) * frame_bytes
+    elif gather_mode == "nccl":
+        # fallback when peer mapping is unavailable: local ring, batches gathered with NCCL
+        tstreams = [torch.cuda.ExternalStream(st.value) for st in streams]
+        comm_stream = torch.cuda.Stream(priority=-1)
         ring = torch.empty((2, GATHER_BATCH, H, W), dtype=torch.int32, device="cuda")
         ring_ptr = lambda i: ring[(i // GATHER_BATCH) % 2, i % GATHER_BATCH].data_ptr()
         gather = multi.FrameGather(ring[0], dst=0)
-        d_tex_t = torch.from_numpy(tex.copy()).cuda()
-        d_tex = d_tex_t.data_ptr()
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     else:
-        streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS)]
         bufs = [vv.DeviceBuffer(frame_bytes) for _ in range(RING)]
         ring_ptr = lambda i: bufs[i % RING].ptr
-        d_tex_b = vv.DeviceBuffer.from_array(tex)
-        d_tex = d_tex_b.ptr
-        flush_b = vv.DeviceBuffer(256 << 20)
-    s_ptr = streams[0]
     # the frame-to-frame tile schedule (voxgpu_sched) is off here: with several frames in flight the
     # tails it removes are already filled, and its sorting kernel costs 6 us per frame (profiles/)
     scheds = [None for _ in streams]
 
     def flush_l2():
-        if world > 1:
-            with torch.cuda.stream(tstreams[0]):
-                flush.zero_()
-        else:
-            g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)
+        g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)
 
     def device_step():
-        """360 launches back to back.  N>1: every GATHER_BATCH finished
-        frames go to GPU 0 with NCCL on a side stream while the next batch renders."""
+        """360 launches back to back, FRAME_STREAMS frames in flight.  N>1: the pixels land in GPU 0's
+        memory as they are produced (peer stores); fallback: NCCL gather of every GATHER_BATCH frames."""
         flush_l2()
         for st in streams[1:]:
             g.voxgpu_stream_join(st, s_ptr)      # the step's first mark / flush precedes every stream's frames
         batch_done = []
         for f in range(FRAMES):
             k = f % FRAME_STREAMS
-            if world > 1 and f >= 2 * GATHER_BATCH and f % GATHER_BATCH < FRAME_STREAMS:
+            if gather_mode == "nccl" and f >= 2 * GATHER_BATCH and f % GATHER_BATCH < FRAME_STREAMS:
                 tstreams[k].wait_event(batch_done[f // GATHER_BATCH - 2])      # this half of the ring is free again
             rc = g.voxgpu_render_sched(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
                                        streams[k], scheds[k])
             if rc:
                 raise vv.VoxError(g.voxgpu_last_error().decode())
-            if world > 1 and f % GATHER_BATCH == GATHER_BATCH - 1:
+            if gather_mode == "nccl" and f % GATHER_BATCH == GATHER_BATCH - 1:
                 for t in tstreams:
                     comm_stream.wait_stream(t)                                  # the whole batch is rendered
                 with torch.cuda.stream(comm_stream):
@@ -271,7 +290,7 @@ def run_own(args):
                 batch_done.append(done)
         for st in streams[1:]:
             g.voxgpu_stream_join(s_ptr, st)      # stream 0 (where the timer marks go) ends after all of them
-        if world > 1:
+        if gather_mode == "nccl":
             tstreams[0].wait_stream(comm_stream)
 
     def sync_all():
@@ -304,12 +323,29 @@ def run_own(args):
         ms_total = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # N>1: what landed on GPU 0 must be the frames the ranks rendered
+    gather_check = None
+    if gather_mode == "peer-store" and rank == 0:
+        scratch = vv.DeviceBuffer(frame_bytes)
+        got = np.empty((H, W), np.uint32)
+        bad = 0
+        for r in range(world):
+            for f in (0, FRAMES // 2, FRAMES - 1):
+                ds.setup_camera(cam, *frame_pose(ds, f, r, world), FOV, W, H)
+                gc = cam.gpu_camera()
+                g.voxgpu_render(dev_tree, C.byref(gc), C.byref(frame_desc), d_tex, scratch.ptr, None, None, None)
+                g.voxgpu_memcpy_d2h(got.ctypes.data, gather_base + r * region_bytes + f * frame_bytes, frame_bytes, None)
+                g.voxgpu_synchronize(None)
+                bad += int(not np.array_equal(got, scratch.download(np.uint32, (H, W))))
+        gather_check = "ok" if bad == 0 else f"{bad} of {3 * world} sampled frames differ"
+
     # kernel-only duration (no gather, no flush): CUDA events around each launch, same stream
     kt = vv.Timer()
+    kscratch = vv.DeviceBuffer(frame_bytes)
     kernel_ms = []
     for f in range(0, FRAMES, 4):
         kt.start(s_ptr)
-        g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None, s_ptr)
+        g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, kscratch.ptr, None, None, s_ptr)
         kt.stop(s_ptr)
         kernel_ms.append(kt.elapsed_ms())
     sync_all()
@@ -387,8 +423,9 @@ def run_own(args):
                 "scripted 360-frame orbit camera",
         "config": {"workload": "C2: skull 1920x1080, 360-frame orbit, quality BEST, simple-camera",
                    "frames_per_step_per_gpu": FRAMES, "rays_per_frame": RAYS_PER_FRAME,
-                   "frames_in_flight_per_gpu": FRAME_STREAMS if world == 1 else 1,
-                   "parallelism": f"frames x{world} (tree replicated" + (", NCCL gather to GPU 0 in the timed region)" if world > 1 else ")"),
+                   "frames_in_flight_per_gpu": FRAME_STREAMS,
+                   "parallelism": f"frames x{world} (tree replicated" + (f", frames gathered on GPU 0 in the timed region: {gather_mode})" if world > 1 else ")"),
+                   "gather": gather_mode, "gather_check": gather_check,
                    "l2": "256 MB L2 flush at the start of every step; within a step the 18 MB tree stays "
                          "L2-resident across frames by design (every frame has a different camera and its own framebuffer)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s",

@@ -125,6 +125,14 @@ VOXGPU_EXPORT void  voxgpu_stream_destroy (voxgpu_stream s);
 /** Work queued on `waiter` after this call starts only when everything queued on `other` so far is done. */
 VOXGPU_EXPORT int   voxgpu_stream_join (voxgpu_stream waiter, voxgpu_stream other);
 
+/* ---- peer memory: another process's device buffer as a render target ----
+ * export on the owner (memory from voxgpu_malloc), ship the 64 bytes to the other
+ * process by any means, open there; the returned address is valid as d_pixels. */
+#define VOXGPU_IPC_HANDLE_BYTES 64
+VOXGPU_EXPORT int   voxgpu_ipc_export (const void *dptr, unsigned char handle[VOXGPU_IPC_HANDLE_BYTES]);
+VOXGPU_EXPORT void* voxgpu_ipc_open (const unsigned char handle[VOXGPU_IPC_HANDLE_BYTES]);
+VOXGPU_EXPORT int   voxgpu_ipc_close (void *dptr);
+
 /* ---- tree ---- */
 /** Convert to the device layout and upload (cudaMemcpyAsync from pinned staging) on the current device. */
 VOXGPU_EXPORT voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *flat);

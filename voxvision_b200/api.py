@@ -157,6 +157,9 @@ class _Libs:
         g.voxgpu_stream_create.restype = _vp
         g.voxgpu_stream_destroy.argtypes = [_vp]
         g.voxgpu_stream_join.argtypes = [_vp, _vp]
+        g.voxgpu_ipc_export.argtypes = [_vp, _vp]
+        g.voxgpu_ipc_open.restype = _vp; g.voxgpu_ipc_open.argtypes = [_vp]
+        g.voxgpu_ipc_close.argtypes = [_vp]
         g.voxgpu_tree_device_bytes.restype = sz; g.voxgpu_tree_device_bytes.argtypes = [_vp]
         g.voxgpu_rays_device.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, _vp]
         g.voxgpu_rays_stats.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, C.POINTER(GpuStats)]

@@ -120,6 +120,30 @@ extern "C" int voxgpu_stream_join (voxgpu_stream waiter, voxgpu_stream other)
     return 0;
 }
 
+/* ------------------------------------------------ peer memory (multi-GPU) */
+
+/* One process per GPU: rank 0 exports a cudaMalloc'ed buffer, the other ranks map it and
+   hand the mapped address to voxgpu_render as the framebuffer -- the render kernel then
+   stores its pixels straight into GPU 0's memory over NVLink (the "gather" of the
+   multi-GPU path, fused into K1's store). */
+extern "C" int voxgpu_ipc_export (const void *dptr, unsigned char handle[VOXGPU_IPC_HANDLE_BYTES])
+{
+    static_assert (sizeof (cudaIpcMemHandle_t) == VOXGPU_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CU (cudaIpcGetMemHandle (&h, (void*) dptr));
+    memcpy (handle, &h, sizeof h);
+    return 0;
+}
+extern "C" void* voxgpu_ipc_open (const unsigned char handle[VOXGPU_IPC_HANDLE_BYTES])
+{
+    cudaIpcMemHandle_t h;
+    void *p = NULL;
+    memcpy (&h, handle, sizeof h);
+    CU_NULL (cudaIpcOpenMemHandle (&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return p;
+}
+extern "C" int voxgpu_ipc_close (void *dptr) { CU (cudaIpcCloseMemHandle (dptr)); return 0; }
+
 /* ------------------------------------------------------------------- timer */
 
 struct voxgpu_timer { cudaEvent_t a, b; };
