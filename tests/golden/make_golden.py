@@ -117,6 +117,12 @@ def main():
     for kind, name, pos in ((orc.CAMERA_SIMPLE, "simple", (128, 128, 400)), (orc.CAMERA_DOOM, "doom", (100, -250, 180))):
         cam = ds.setup_camera(R.camera(kind), pos, (128, 128, 128), 1.2, 800, 600)
         meta["c1"][name] = frame_digest(T["bonsai"].render(cam, 800, 600, orc.QUALITY_BEST, tex, threads=threads))
+    # the reference's other quality modes (renderer.c:240-316), pixels only
+    cam = ds.setup_camera(R.camera(orc.CAMERA_SIMPLE), (128, 128, 400), (128, 128, 128), 1.2, 800, 600)
+    meta["c1"]["modes"] = {}
+    for qname, q in (("fast", 1), ("adaptive", 2), ("adaptive+merge", 2 | 4), ("adaptive+merge_accurate", 2 | 8)):
+        pix = T["bonsai"].render(cam, 800, 600, q, tex, threads=threads, want_hits=False)
+        meta["c1"]["modes"][qname] = sha(pix)
 
     # ---- raw vectors: 4096 rays and 4096 balls against skull
     o, d = ds.random_rays(4096, side=256)

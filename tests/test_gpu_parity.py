@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 THREADS = os.cpu_count() or 1
 
 
-def render_device(vv, tree, cam, w, h, tex, fmt, y0=0, y1=None, want_hits=True, gcam=None):
+def render_device(vv, tree, cam, w, h, tex, fmt, y0=0, y1=None, want_hits=True, gcam=None, quality=0):
     """voxgpu_render into device buffers (the entry multi-GPU drivers use)."""
     api = vv.api
     y1 = h if y1 is None else y1
@@ -26,7 +26,7 @@ def render_device(vv, tree, cam, w, h, tex, fmt, y0=0, y1=None, want_hits=True, 
     d_pts = vv.DeviceBuffer(w * rows * 16)
     api.libs.gpu.voxgpu_memset(d_pix.ptr, 0xff, w * rows * 4, None)
     gc = gcam or cam.gpu_camera()
-    fr = api.GpuFrame(w, h, y0, y1, w, 0, fmt)
+    fr = api.GpuFrame(w, h, y0, y1, w, quality, fmt)
     rc = api.libs.gpu.voxgpu_render(tree.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr,
                                     d_leaf.ptr if want_hits else None, d_pts.ptr if want_hits else None, None)
     assert rc == 0, api.libs.gpu.voxgpu_last_error()
@@ -269,6 +269,62 @@ def test_c1_bonsai_both_cameras(gpu, checker, golden, bonsai, ds, name, kind, po
     opix, oleaf, ohit = checker.tree(bonsai).render(ocam, 800, 600, 0, ctx.texture(), threads=THREADS)
     assert np.array_equal(leaf, oleaf) and np.array_equal(pix, opix)
     assert np.array_equal(bits(pts[oleaf >= 0]), bits(ohit[oleaf >= 0]))
+
+
+QUALITIES = {"fast": 1, "adaptive": 2, "adaptive+merge": 2 | 4, "adaptive+merge_accurate": 2 | 8}
+
+
+@pytest.mark.parametrize("qname", list(QUALITIES))
+@pytest.mark.parametrize("scene", ["bonsai", "skull_far"])
+def test_quality_modes_match_the_reference_block_loop(gpu, checker, golden, bonsai, skull, ds, qname, scene):
+    """FAST / ADAPTIVE / ray merge (renderer.c:240-316): the reference's default modes, in which the
+    pixels of a 4x4 block depend on each other.  Pixels, leaf ids and hit points of every written
+    pixel must equal the reference's block loop; unwritten pixels stay 0 / -1."""
+    q = QUALITIES[qname]
+    if scene == "bonsai":
+        vox, w, h, pos, look = bonsai, 800, 600, (128, 128, 400), (128, 128, 128)
+    else:       # far enough for the MAX_DIST = 150 ray-merge criterion to fire (renderer.c:198,274)
+        vox, w, h, pos, look = skull, 640, 360, (128, 128, -330), (128, 128, 128)
+    t = gpu.Tree.build(vox)
+    ctx = gpu.Context(w, h)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    ocam = ds.setup_camera(checker.camera(0), pos, look, 1.2, w, h)
+    pix, leaf, pts = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt(), quality=q)
+    opix, oleaf, ohit = checker.tree(vox).render(ocam, w, h, q, ctx.texture(), threads=THREADS)
+    assert (opix != 0).sum() > 10000
+    assert np.array_equal(leaf, oleaf), f"{int((leaf != oleaf).sum())} leaf ids differ"
+    assert np.array_equal(pix, opix), f"{int((pix != opix).sum())} pixels differ"
+    m = oleaf >= 0
+    assert np.array_equal(bits(pts[m]), bits(ohit[m]))
+    if scene == "bonsai" and qname in meta_modes(golden):
+        assert sha(pix) == meta_modes(golden)[qname]
+    # row bands (the presenter, multi-GPU) give the same pixels
+    band = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt(), 120, 240, quality=q)
+    assert np.array_equal(band[0], pix[120:240]) and np.array_equal(band[1], leaf[120:240])
+    # and so does the reference-facing API, whose contexts default to ADAPTIVE (renderer.c:78)
+    ctx.set_scene(t); ctx.set_camera(cam)
+    assert ctx.set_quality(q)
+    ctx.render(); ctx.redraw()
+    assert gpu.last_error() == "" and np.array_equal(ctx.pixels(), opix)
+
+
+def meta_modes(golden):
+    meta, _ = golden
+    return meta.get("c1", {}).get("modes", {})
+
+
+def test_default_quality_is_adaptive_like_the_reference(gpu, checker, skull, ds):
+    t = gpu.Tree.build(skull)
+    w, h = 320, 160
+    pos, look = ds.orbit_pose(77)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    ocam = ds.setup_camera(checker.camera(0), pos, look, 1.2, w, h)
+    ctx = gpu.Context(w, h)                      # quality untouched
+    ctx.set_scene(t); ctx.set_camera(cam)
+    ctx.render(); ctx.redraw()
+    opix = checker.tree(skull).render(ocam, w, h, 2, ctx.texture(), threads=THREADS, want_hits=False)
+    assert np.array_equal(ctx.pixels(), opix)
+    assert not ctx.set_quality(1 | 4) and not ctx.set_quality(3)     # renderer.c:179-195
 
 
 def test_row_bands_tile_the_frame(gpu, skull, ds):

@@ -730,11 +730,192 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
     }
 }
 
+/*
+ * K1b: the reference's FAST / ADAPTIVE / ray-merge quality modes, pixel for pixel
+ * (renderer.c:214-318).  In those modes the pixels of a 4x4 block depend on each other --
+ * pixel i+1 is first searched inside the leaf pixel i hit, ADAPTIVE decides per block from
+ * two corner rays, ray-merge copies the previous pixel's colour -- so a block is sequential.
+ * One LANE owns one block and walks its 16 pixels in the reference's Z-order; the 32 lanes of
+ * a warp (8x4 blocks = 32x16 pixels) advance together, one pixel index at a time, through
+ * the warp-synchronous search with per-lane start nodes.  On the GPU this is the SLOW path:
+ * BEST has 16 times the parallelism and is what to ask for when speed matters.
+ */
+__constant__ int c_rendering_order[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};   /* renderer.c:23-25 */
+
+/* geom.c:133-139 / 141-147: ((0 + a*a) + b*b) + c*c */
+__device__ __forceinline__ float sqr_metric3 (const V3 a, const V3 b)
+{
+    const float x = __fsub_rn (a.x, b.x), y = __fsub_rn (a.y, b.y), z = __fsub_rn (a.z, b.z);
+    return __fadd_rn (__fadd_rn (__fmul_rn (x, x), __fmul_rn (y, y)), __fmul_rn (z, z));
+}
+__device__ __forceinline__ float sqr_norm3 (const V3 a)
+{
+    return __fadd_rn (__fadd_rn (__fmul_rn (a.x, a.x), __fmul_rn (a.y, a.y)), __fmul_rn (a.z, a.z));
+}
+
+template <bool OUT_HITS>
+__global__ void __launch_bounds__(RENDER_BLOCK)
+k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const unsigned char * __restrict__ tex,
+                 unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
+                 unsigned *counters)
+{
+    const int bw = fr.w >> 2, bh = fr.rows >> 2;               /* 4x4 blocks */
+    const int tiles_x = (bw + 7) >> 3, tiles_y = (bh + 3) >> 2;
+    const unsigned ntiles = (unsigned) (tiles_x * tiles_y);
+    const int lane = threadIdx.x & 31;
+    const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
+    const unsigned rnd_mode = quality & 3u, merge_mode = quality & 12u;
+    const bool adaptive = rnd_mode == 2u;
+    float4 stack[VOXGPU_RAY_STACK];
+    unsigned sq[16];
+    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
+
+    for (;;)
+    {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd (&counters[0], 1u);
+        tile = __shfl_sync (0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+
+        const int bx = (int) (tile % tiles_x) * 8 + (lane & 7);
+        const int by = (int) (tile / tiles_x) * 4 + (lane >> 3);
+        const bool valid = bx < bw && by < bh;
+        const int xstart = bx << 2, ystart = by << 2;          /* ystart: row inside the band */
+        #pragma unroll
+        for (int p=0; p<16; p++) sq[p] = 0;                    /* vox_redraw's memset, renderer.c:324 */
+        if (OUT_HITS && valid && leaf_ids)
+            for (int p=0; p<16; p++) leaf_ids[(size_t) (ystart + (p >> 2)) * fr.w + xstart + (p & 3)] = -1;
+
+        /* renderer.c:216-239 */
+        unsigned blk_mode = adaptive ? 1u : rnd_mode;          /* 0 BEST, 1 FAST */
+        bool blk_merge = adaptive && merge_mode == 4u;
+        int istart = adaptive ? 1 : 0, iend = 16;
+        int leaf = -1;                                         /* node id of the previous hit, -1 = NULL */
+        V3 inter = origin;                                     /* inter1 */
+        V3 dir_c1 = origin, inter_c1 = origin;
+        bool c1 = false;
+        int prev_p = 0;
+
+        /* step 0, 1: the two corner rays of ADAPTIVE (renderer.c:240-281);
+           step 2+2i: pixel i searched inside the previous leaf (FAST), step 3+2i: from the root */
+        for (int step = adaptive ? 0 : 2; step < 34; step++)
+        {
+            const int i = (step - 2) >> 1;
+            const bool phase_leaf = step >= 2 && !(step & 1);
+            int p = 0, px = xstart, py = ystart;
+            bool merge = false, in_range = false;
+            if (step == 1) { px += 3; py += 3; }
+            if (step >= 2)
+            {
+                p = c_rendering_order[i];
+                px += p & 3; py += p >> 2;
+                merge = blk_merge && (i & 1);
+                in_range = valid && i >= istart && i < iend;
+            }
+            bool want;
+            unsigned start = 0;
+            if (step == 0) want = valid;
+            else if (step == 1) want = valid && c1;
+            else if (phase_leaf) { want = in_range && !merge && blk_mode == 1u && leaf >= 0; start = leaf >= 0 ? (unsigned) leaf : 0u; }
+            else want = in_range && !merge && (blk_mode == 0u || leaf < 0);
+
+            RayResult r;
+            r.leaf = -1;
+            V3 dir = origin;
+            if (__any_sync (0xffffffffu, want))
+            {
+                dir = screen2world (cam, valid ? px : 0, fr.y0 + (valid ? py : 0), fr.w);
+                ray_tree_warp (tr, start, origin, dir, want, stack, r);
+            }
+
+            if (step == 0)
+            {
+                if (want)
+                {
+                    leaf = r.leaf; dir_c1 = dir;
+                    if (r.leaf >= 0)
+                    {
+                        c1 = true; iend = 15; inter = r.point; inter_c1 = r.point;
+                        sq[0] = shade (tr, fr, tex, r.point);
+                        if (OUT_HITS)
+                        {
+                            const size_t pos = (size_t) ystart * fr.w + xstart;
+                            if (leaf_ids) leaf_ids[pos] = r.leaf;
+                            if (points) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+                        }
+                    }
+                }
+            }
+            else if (step == 1)
+            {
+                if (want && r.leaf >= 0)
+                {
+                    sq[15] = shade (tr, fr, tex, r.point);
+                    if (OUT_HITS)
+                    {
+                        const size_t pos = (size_t) (ystart + 3) * fr.w + xstart + 3;
+                        if (leaf_ids) leaf_ids[pos] = r.leaf;
+                        if (points) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+                    }
+                    /* renderer.c:262-278 */
+                    const float d1 = sqr_metric3 (inter_c1, origin);
+                    const float d2 = sqr_norm3 (dir_c1);
+                    const float criteria = __fmul_rn (__fdiv_rn (d1, d2), sqr_metric3 (dir_c1, dir));
+                    const float dist = sqr_metric3 (inter_c1, r.point);
+                    if ((double) __fdiv_rn (dist, criteria) > 1.69) blk_mode = 0u;
+                    if (d1 > 22500.0f) blk_merge = (blk_mode == 1u && merge_mode == 8u) ? true : blk_merge;
+                    else blk_merge = false;
+                }
+            }
+            else
+            {
+                if (want)
+                {
+                    leaf = r.leaf;
+                    if (r.leaf >= 0) inter = r.point;
+                }
+                if (!phase_leaf)
+                {
+                    /* renderer.c:310-315, once both searches of pixel i are done */
+                    if (in_range)
+                    {
+                        if (leaf >= 0)
+                        {
+                            sq[p] = merge ? sq[prev_p] : shade (tr, fr, tex, inter);
+                            if (OUT_HITS)
+                            {
+                                const size_t pos = (size_t) py * fr.w + px;
+                                if (leaf_ids) leaf_ids[pos] = leaf;
+                                if (points) points[pos] = make_float4 (inter.x, inter.y, inter.z, 0.0f);
+                            }
+                        }
+                        prev_p = p;
+                    }
+                }
+            }
+        }
+
+        if (valid)
+        {
+            #pragma unroll
+            for (int row=0; row<4; row++)
+                *(uint4*) (pixels + (size_t) (ystart + row) * fr.pitch + xstart) =
+                    make_uint4 (sq[4*row], sq[4*row+1], sq[4*row+2], sq[4*row+3]);
+        }
+        __syncwarp ();
+    }
+    if (lane == 0)
+    {
+        const unsigned done = atomicAdd (&counters[1], 1u);
+        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
+    }
+}
+
 /* Per-device pool of self-resetting tile counters; launches rotate through the
    slots so that renders in flight on different streams never share one. */
 #define COUNTER_SLOTS 64
 static unsigned *g_counters[64] = {0};
-static int g_render_blocks[64][2] = {{0}};
+static int g_render_blocks[64][3] = {{0}};
 static std::atomic<unsigned> g_counter_seq{0};
 static int g_variant = 1;
 static unsigned long long *g_trace = NULL;
@@ -756,6 +937,9 @@ static unsigned* counter_slot (int device)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
         g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
         g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
+        int b2 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true>, RENDER_BLOCK, 0);
+        g_render_blocks[device][2] = sms * (b2 > 0 ? b2 : 1);
         g_counters[device] = p;
     }
     return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
@@ -868,7 +1052,25 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
 
     const int ntiles = (df.w >> 3) * (df.rows >> 2);
     const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
-    if (g_variant == 0)
+    if ((f->quality & 3u) != 0u)
+    {
+        /* FAST / ADAPTIVE (+ ray merge): the block-sequential kernel */
+        if ((f->quality & 3u) > 2u || (f->quality & 12u) > 8u || ((f->quality & 12u) && (f->quality & 3u) != 2u))
+            return fail ("voxgpu_render: invalid quality %u (renderer.c:179-195)", f->quality);
+        if (((size_t) d_pixels & 15) || (df.pitch & 3))
+            return fail ("voxgpu_render: quality modes other than BEST need 16-byte aligned rows");
+        unsigned *counters = counter_slot (t->device);
+        if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
+        const int warps = (((df.w >> 2) + 7) >> 3) * (((df.rows >> 2) + 3) >> 2);
+        int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
+        const int cap = g_render_blocks[t->device][2];
+        if (grid > cap) grid = cap;
+        if (d_leaf || d_pts)
+            k_render_blocks<true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        else
+            k_render_blocks<false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters);
+    }
+    else if (g_variant == 0)
     {
         if (d_leaf || d_pts)
             k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
