@@ -217,8 +217,11 @@ VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present 
 /** Development knob: 0 = the first, one-CTA-per-4-tiles render kernel with the
     plain (lazy, reference-shaped) traversal, 1 = the persistent kernel with the
     eager traversal and strip-interleaved tile order (default), 2 = as 1 with
-    raster tile order.  Kept for A/B measurements; results are identical. */
+    raster tile order, 3 = per-lane work refill (k_render_stream).  Kept for A/B
+    measurements; results are identical. */
 VOXGPU_EXPORT void voxgpu_set_variant (int variant);
+/** Variant 3: refill a warp as soon as this many of its 32 lanes are idle (1..32). */
+VOXGPU_EXPORT void voxgpu_set_refill_min (int lanes);
 
 /** Development trace: when non-NULL, every following voxgpu_render launch (persistent
     variants) records per 8x4 tile {start ns, end ns, smid<<32 | warp} (3 x uint64 per

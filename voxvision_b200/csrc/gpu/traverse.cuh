@@ -545,6 +545,234 @@ __device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool 
 #define VOXGPU_COOP_MAX_LANES 12     /* more lanes than this at a leaf: everyone loops over its own voxels */
 
 /*
+ * One lane's search state between node visits.  `cur` is the node of the pending call
+ * (VOXGPU_DEAD: this lane's search is over), `org` the origin that call is made with.
+ * A finished ray's stack is dead: the hit point and voxel wait there (stack[0]) instead
+ * of in registers that every branch of the loop would have to carry.
+ */
+struct LaneSearch
+{
+    unsigned cur;
+    V3 org;
+    int sp;
+    int leaf;               /* result: breadth-first id of the hit leaf, -1 = none */
+    /* written only by a lane that is at a leaf; read (shuffled) only from such lanes */
+    V3 lf_e;
+    unsigned lf_link, lf_info;
+};
+
+__device__ __forceinline__ void lane_search_begin (LaneSearch &s, unsigned start, const V3 origin, bool has_ray)
+{
+    s.cur = has_ray ? start : VOXGPU_DEAD;
+    s.org = origin;
+    s.sp = 0;
+    s.leaf = -1;
+    s.lf_e = origin; s.lf_link = 0; s.lf_info = 0;
+}
+
+/*
+ * ONE node visit of vox_ray_tree_intersection (search.c:8-153) for every live lane of
+ * the warp, followed by the cooperative leaf tests and the pop of the next pending call.
+ * WARP-SYNCHRONOUS: all 32 lanes must call it together.
+ */
+__device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK &k, LaneSearch &s, float4 *stack, const int lane)
+{
+    /* what a lane does after the node visit of this iteration */
+    enum { IDLE = 0, GO = 1, POP = 2, LEAF = 3 };
+    const float inf = __int_as_float (0x7f800000);
+    const V3 d = k.d;
+    int st = IDLE;
+    if (s.cur != VOXGPU_DEAD)
+    {
+        /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
+        float4 q0, q1;
+        load_rec (tr.rec + s.cur, q0, q1);
+        const unsigned meta = __float_as_uint (q0.w);
+        const unsigned link = __float_as_uint (q1.w);
+        const unsigned kind = meta & 3u;
+        const V3 mn = v3 (q0), mx = v3 (q1);
+        V3 entry;
+
+        st = POP;                                                               /* search.c:22-27 */
+        if (ray_box_fast (mn, mx, s.org, d, k.r, k.dok, entry))
+        {
+            if (kind == VOXGPU_KIND_INNER)
+            {
+                const V3 c = v3 (__ldg (tr.ctr + s.cur));
+                const unsigned mask = (meta >> 8) & 0xffu;
+                const unsigned sub = subspace_fast (c, entry, k.nx, k.ny, k.nz);
+
+                /* search.c:105-113: the three dividing planes, from the entry point */
+                V3 p0, p1, p2;
+                bool v0, v1, v2;
+                ray_planes_fast (entry, k, c, mn, mx, v0, v1, v2, p0, p1, p2);
+                if (v0 | v1 | v2)
+                {
+                    /* search.c:115-134 as ranks.  Invalid planes get +inf and sort last. */
+                    const float m0 = v0 ? l1_metric (entry, p0) : inf;
+                    const float m1 = v1 ? l1_metric (entry, p1) : inf;
+                    const float m2 = v2 ? l1_metric (entry, p2) : inf;
+                    const bool A = m1 < m0, B = m2 < m1, C = m2 < m0, D = m0 < m1;
+                    const bool b01 = !A && (!C || D);      /* plane 0 is tried before plane 1 */
+                    const bool b02 = !C && (!A || !B);
+                    const bool b12 = !B && (A || !C);
+                    /* search.c:137: the subspace flips of the planes tried so far accumulate */
+                    const unsigned s0 = sub ^ 1u ^ ((v1 && !b01) ? 2u : 0u) ^ ((v2 && !b02) ? 4u : 0u);
+                    const unsigned s1 = sub ^ 2u ^ ((v0 &&  b01) ? 1u : 0u) ^ ((v2 && !b12) ? 4u : 0u);
+                    const unsigned s2 = sub ^ 4u ^ ((v0 &&  b02) ? 1u : 0u) ^ ((v1 &&  b12) ? 2u : 0u);
+                    const bool e0 = v0 && ((mask >> s0) & 1u);
+                    const bool e1 = v1 && ((mask >> s1) & 1u);
+                    const bool e2 = v2 && ((mask >> s2) & 1u);
+                    /* the call tried first must be popped first: slot = number of later calls */
+                    if (e0) stack[s.sp + (int)(e1 && b01) + (int)(e2 && b02)] =
+                        make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
+                    if (e1) stack[s.sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
+                        make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
+                    if (e2) stack[s.sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
+                        make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
+                    s.sp += (int) e0 + (int) e1 + (int) e2;
+                }
+                /* search.c:83-97: the child the entry point lies in goes first */
+                if ((mask >> sub) & 1u) { s.cur = child_id (link, mask, sub); s.org = entry; st = GO; }
+            }
+            else if (kind == VOXGPU_KIND_DENSE)
+            {
+                /* search.c:31-37 */
+                s.leaf = (int) s.cur;
+                stack[0] = make_float4 (entry.x, entry.y, entry.z, __int_as_float (-1));
+                s.cur = VOXGPU_DEAD; st = IDLE;
+            }
+            else
+            {
+                s.lf_e = entry; s.lf_link = link; s.lf_info = (meta >> 2) | (k.dok ? 0x80000000u : 0u);
+                st = LEAF;
+            }
+        }
+    }
+
+    /* ---- leaves, search.c:39-81 ---- */
+    const unsigned leafmask = __ballot_sync (VOXGPU_FULL, st == LEAF);
+    if (leafmask)
+    {
+        float best = inf;           /* owner's result */
+        int best_i = 0;
+        V3 best_p = s.lf_e;
+        const bool coop = __popc (leafmask) <= VOXGPU_COOP_MAX_LANES &&
+                          !__any_sync (VOXGPU_FULL, st == LEAF && (s.lf_info & 0x7fffffffu) > 8u);
+        if (coop)
+        {
+            const int group = lane >> 3, slot = lane & 7;
+            const int myrank = __popc (leafmask & ((1u << lane) - 1u));
+            unsigned m = leafmask;
+            for (int base = 0; m; base += 4)
+            {
+                /* the four lowest remaining leaf lanes are served by the four groups of eight */
+                const int l0 = __ffs (m) - 1; m &= m - 1;
+                const int l1 = __ffs (m) - 1; m &= m - 1;
+                const int l2 = __ffs (m) - 1; m &= m - 1;
+                const int l3 = __ffs (m) - 1; m &= m - 1;
+                const int src = group == 0 ? l0 : (group == 1 ? l1 : (group == 2 ? l2 : l3));
+                const int from = src >= 0 ? src : lane;
+                V3 e, dd, rr;
+                e.x = __shfl_sync (VOXGPU_FULL, s.lf_e.x, from); e.y = __shfl_sync (VOXGPU_FULL, s.lf_e.y, from); e.z = __shfl_sync (VOXGPU_FULL, s.lf_e.z, from);
+                dd.x = __shfl_sync (VOXGPU_FULL, d.x, from); dd.y = __shfl_sync (VOXGPU_FULL, d.y, from); dd.z = __shfl_sync (VOXGPU_FULL, d.z, from);
+                rr.x = __shfl_sync (VOXGPU_FULL, k.r.x, from); rr.y = __shfl_sync (VOXGPU_FULL, k.r.y, from); rr.z = __shfl_sync (VOXGPU_FULL, k.r.z, from);
+                const unsigned lnk = __shfl_sync (VOXGPU_FULL, s.lf_link, from);
+                const unsigned info = __shfl_sync (VOXGPU_FULL, s.lf_info, from);
+                float dist = inf;
+                V3 far = e;
+                if (src >= 0 && (unsigned) slot < (info & 0x7fffffffu))
+                {
+                    const float4 dq = __ldg (tr.dots + (size_t) lnk + slot);
+                    V3 vmin = v3 (dq), vmax;
+                    vmax.x = __fadd_rn (vmin.x, tr.vx);
+                    vmax.y = __fadd_rn (vmin.y, tr.vy);
+                    vmax.z = __fadd_rn (vmin.z, tr.vz);
+                    if (ray_box_fast (vmin, vmax, e, dd, rr, (info >> 31) != 0, far))
+                    {
+                        const float t = l1_metric (e, far);
+                        if (t < inf) dist = t;              /* search.c:72: NaN and inf never win */
+                    }
+                }
+                /* smallest distance, earliest voxel on ties, within the group of eight */
+                int idx = slot;
+                #pragma unroll
+                for (int off = 4; off; off >>= 1)
+                {
+                    const float od = __shfl_xor_sync (VOXGPU_FULL, dist, off);
+                    const int oi = __shfl_xor_sync (VOXGPU_FULL, idx, off);
+                    if (od < dist || (od == dist && oi < idx)) { dist = od; idx = oi; }
+                }
+                /* back to the owner: the group that served lane rank myrank holds its answer */
+                const int g = myrank - base;
+                const bool mine = st == LEAF && g >= 0 && g < 4;
+                const int head = mine ? 8 * g : lane;
+                const float bd = __shfl_sync (VOXGPU_FULL, dist, head);
+                const int bi = __shfl_sync (VOXGPU_FULL, idx, head);
+                const int win = mine ? head + bi : lane;
+                const float fx = __shfl_sync (VOXGPU_FULL, far.x, win);
+                const float fy = __shfl_sync (VOXGPU_FULL, far.y, win);
+                const float fz = __shfl_sync (VOXGPU_FULL, far.z, win);
+                if (mine) { best = bd; best_i = bi; best_p.x = fx; best_p.y = fy; best_p.z = fz; }
+            }
+        }
+        else if (st == LEAF)
+        {
+            const unsigned n = s.lf_info & 0x7fffffffu;
+            for (unsigned i=0; i<n; i++)
+            {
+                const float4 dq = __ldg (tr.dots + (size_t) s.lf_link + i);
+                V3 vmin = v3 (dq), vmax, far;
+                vmax.x = __fadd_rn (vmin.x, tr.vx);
+                vmax.y = __fadd_rn (vmin.y, tr.vy);
+                vmax.z = __fadd_rn (vmin.z, tr.vz);
+                if (ray_box_fast (vmin, vmax, s.lf_e, d, k.r, k.dok, far))
+                {
+                    const float dist = l1_metric (s.lf_e, far);
+                    if (dist < best) { best = dist; best_i = (int) i; best_p = far; }
+                    if (dist == 0.0f) break;                /* search.c:65-71 */
+                }
+            }
+        }
+        if (st == LEAF)
+        {
+            if (best < inf)
+            {
+                s.leaf = (int) s.cur;
+                stack[0] = make_float4 (best_p.x, best_p.y, best_p.z, __uint_as_float (s.lf_link + (unsigned) best_i));
+                s.cur = VOXGPU_DEAD;
+            }
+            else st = POP;
+        }
+    }
+
+    if (st == POP)
+    {
+        /* this call missed: go on with the nearest pending one */
+        if (s.sp == 0) s.cur = VOXGPU_DEAD;
+        else
+        {
+            const float4 e = stack[--s.sp];
+            s.org.x = e.x; s.org.y = e.y; s.org.z = e.z;
+            s.cur = __float_as_uint (e.w);
+        }
+    }
+}
+
+/* the result of a finished lane (s.cur == VOXGPU_DEAD) */
+__device__ __forceinline__ void lane_search_result (const LaneSearch &s, const float4 *stack, RayResult &out)
+{
+    out.leaf = s.leaf;
+    out.voxel = -1;
+    if (s.leaf >= 0)
+    {
+        const float4 h = stack[0];
+        out.point.x = h.x; out.point.y = h.y; out.point.z = h.z;
+        out.voxel = __float_as_int (h.w);
+    }
+}
+
+/*
  * vox_ray_tree_intersection (search.c:8-153) for the 32 rays of a warp.
  * WARP-SYNCHRONOUS: all 32 lanes must call it together; `has_ray` says whether
  * this lane has a ray at all.  `stack` is VOXGPU_RAY_STACK float4 entries of
@@ -553,211 +781,16 @@ __device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool 
 __device__ __forceinline__ int ray_tree_warp (const TreeRef &tr, unsigned start, const V3 origin, const V3 dir,
                                               bool has_ray, float4 *stack, RayResult &out)
 {
-    /* what a lane does after the node visit of this iteration */
-    enum { IDLE = 0, GO = 1, POP = 2, LEAF = 3 };
-
     const RayK k = ray_constants (dir);
-    const V3 d = dir;
     const int lane = threadIdx.x & 31;
-    const float inf = __int_as_float (0x7f800000);
-    int sp = 0;
-    unsigned cur = has_ray ? start : VOXGPU_DEAD;       /* VOXGPU_DEAD: this lane's search is over */
-    V3 org = origin;
-    /* written only by a lane that is at a leaf; read (shuffled) only from such lanes */
-    V3 lf_e = origin;
-    unsigned lf_link = 0, lf_info = 0;
-
-    /* A finished ray's stack is dead: the hit point and voxel wait there (stack[0], stack[1])
-       instead of in five registers that every branch of the loop would have to carry. */
-    out.leaf = -1;
+    LaneSearch s;
+    lane_search_begin (s, start, origin, has_ray);
     int iterations = 0;             /* node visits of the slowest lane: the cost of this warp's rays */
-
-    while (__any_sync (VOXGPU_FULL, cur != VOXGPU_DEAD))
+    while (__any_sync (VOXGPU_FULL, s.cur != VOXGPU_DEAD))
     {
-        int st = IDLE;
         iterations++;
-        if (cur != VOXGPU_DEAD)
-        {
-            /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
-            float4 q0, q1;
-            load_rec (tr.rec + cur, q0, q1);
-            const unsigned meta = __float_as_uint (q0.w);
-            const unsigned link = __float_as_uint (q1.w);
-            const unsigned kind = meta & 3u;
-            const V3 mn = v3 (q0), mx = v3 (q1);
-            V3 entry;
-
-            st = POP;                                                               /* search.c:22-27 */
-            if (ray_box_fast (mn, mx, org, d, k.r, k.dok, entry))
-            {
-                if (kind == VOXGPU_KIND_INNER)
-                {
-                    const V3 c = v3 (__ldg (tr.ctr + cur));
-                    const unsigned mask = (meta >> 8) & 0xffu;
-                    const unsigned sub = subspace_fast (c, entry, k.nx, k.ny, k.nz);
-
-                    /* search.c:105-113: the three dividing planes, from the entry point */
-                    V3 p0, p1, p2;
-                    bool v0, v1, v2;
-                    ray_planes_fast (entry, k, c, mn, mx, v0, v1, v2, p0, p1, p2);
-                    if (v0 | v1 | v2)
-                    {
-                        /* search.c:115-134 as ranks.  Invalid planes get +inf and sort last. */
-                        const float m0 = v0 ? l1_metric (entry, p0) : inf;
-                        const float m1 = v1 ? l1_metric (entry, p1) : inf;
-                        const float m2 = v2 ? l1_metric (entry, p2) : inf;
-                        const bool A = m1 < m0, B = m2 < m1, C = m2 < m0, D = m0 < m1;
-                        const bool b01 = !A && (!C || D);      /* plane 0 is tried before plane 1 */
-                        const bool b02 = !C && (!A || !B);
-                        const bool b12 = !B && (A || !C);
-                        /* search.c:137: the subspace flips of the planes tried so far accumulate */
-                        const unsigned s0 = sub ^ 1u ^ ((v1 && !b01) ? 2u : 0u) ^ ((v2 && !b02) ? 4u : 0u);
-                        const unsigned s1 = sub ^ 2u ^ ((v0 &&  b01) ? 1u : 0u) ^ ((v2 && !b12) ? 4u : 0u);
-                        const unsigned s2 = sub ^ 4u ^ ((v0 &&  b02) ? 1u : 0u) ^ ((v1 &&  b12) ? 2u : 0u);
-                        const bool e0 = v0 && ((mask >> s0) & 1u);
-                        const bool e1 = v1 && ((mask >> s1) & 1u);
-                        const bool e2 = v2 && ((mask >> s2) & 1u);
-                        /* the call tried first must be popped first: slot = number of later calls */
-                        if (e0) stack[sp + (int)(e1 && b01) + (int)(e2 && b02)] =
-                            make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
-                        if (e1) stack[sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
-                            make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
-                        if (e2) stack[sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
-                            make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
-                        sp += (int) e0 + (int) e1 + (int) e2;
-                    }
-                    /* search.c:83-97: the child the entry point lies in goes first */
-                    if ((mask >> sub) & 1u) { cur = child_id (link, mask, sub); org = entry; st = GO; }
-                }
-                else if (kind == VOXGPU_KIND_DENSE)
-                {
-                    /* search.c:31-37 */
-                    out.leaf = (int) cur;
-                    stack[0] = make_float4 (entry.x, entry.y, entry.z, __int_as_float (-1));
-                    cur = VOXGPU_DEAD; st = IDLE;
-                }
-                else
-                {
-                    lf_e = entry; lf_link = link; lf_info = (meta >> 2) | (k.dok ? 0x80000000u : 0u);
-                    st = LEAF;
-                }
-            }
-        }
-
-        /* ---- leaves, search.c:39-81 ---- */
-        const unsigned leafmask = __ballot_sync (VOXGPU_FULL, st == LEAF);
-        if (leafmask)
-        {
-            float best = inf;           /* owner's result */
-            int best_i = 0;
-            V3 best_p = lf_e;
-            const bool coop = __popc (leafmask) <= VOXGPU_COOP_MAX_LANES &&
-                              !__any_sync (VOXGPU_FULL, st == LEAF && (lf_info & 0x7fffffffu) > 8u);
-            if (coop)
-            {
-                const int group = lane >> 3, slot = lane & 7;
-                const int myrank = __popc (leafmask & ((1u << lane) - 1u));
-                unsigned m = leafmask;
-                for (int base = 0; m; base += 4)
-                {
-                    /* the four lowest remaining leaf lanes are served by the four groups of eight */
-                    const int l0 = __ffs (m) - 1; m &= m - 1;
-                    const int l1 = __ffs (m) - 1; m &= m - 1;
-                    const int l2 = __ffs (m) - 1; m &= m - 1;
-                    const int l3 = __ffs (m) - 1; m &= m - 1;
-                    const int src = group == 0 ? l0 : (group == 1 ? l1 : (group == 2 ? l2 : l3));
-                    const int from = src >= 0 ? src : lane;
-                    V3 e, dd, rr;
-                    e.x = __shfl_sync (VOXGPU_FULL, lf_e.x, from); e.y = __shfl_sync (VOXGPU_FULL, lf_e.y, from); e.z = __shfl_sync (VOXGPU_FULL, lf_e.z, from);
-                    dd.x = __shfl_sync (VOXGPU_FULL, d.x, from); dd.y = __shfl_sync (VOXGPU_FULL, d.y, from); dd.z = __shfl_sync (VOXGPU_FULL, d.z, from);
-                    rr.x = __shfl_sync (VOXGPU_FULL, k.r.x, from); rr.y = __shfl_sync (VOXGPU_FULL, k.r.y, from); rr.z = __shfl_sync (VOXGPU_FULL, k.r.z, from);
-                    const unsigned lnk = __shfl_sync (VOXGPU_FULL, lf_link, from);
-                    const unsigned info = __shfl_sync (VOXGPU_FULL, lf_info, from);
-                    float dist = inf;
-                    V3 far = e;
-                    if (src >= 0 && (unsigned) slot < (info & 0x7fffffffu))
-                    {
-                        const float4 dq = __ldg (tr.dots + (size_t) lnk + slot);
-                        V3 vmin = v3 (dq), vmax;
-                        vmax.x = __fadd_rn (vmin.x, tr.vx);
-                        vmax.y = __fadd_rn (vmin.y, tr.vy);
-                        vmax.z = __fadd_rn (vmin.z, tr.vz);
-                        if (ray_box_fast (vmin, vmax, e, dd, rr, (info >> 31) != 0, far))
-                        {
-                            const float t = l1_metric (e, far);
-                            if (t < inf) dist = t;              /* search.c:72: NaN and inf never win */
-                        }
-                    }
-                    /* smallest distance, earliest voxel on ties, within the group of eight */
-                    int idx = slot;
-                    #pragma unroll
-                    for (int off = 4; off; off >>= 1)
-                    {
-                        const float od = __shfl_xor_sync (VOXGPU_FULL, dist, off);
-                        const int oi = __shfl_xor_sync (VOXGPU_FULL, idx, off);
-                        if (od < dist || (od == dist && oi < idx)) { dist = od; idx = oi; }
-                    }
-                    /* back to the owner: the group that served lane rank myrank holds its answer */
-                    const int g = myrank - base;
-                    const bool mine = st == LEAF && g >= 0 && g < 4;
-                    const int head = mine ? 8 * g : lane;
-                    const float bd = __shfl_sync (VOXGPU_FULL, dist, head);
-                    const int bi = __shfl_sync (VOXGPU_FULL, idx, head);
-                    const int win = mine ? head + bi : lane;
-                    const float fx = __shfl_sync (VOXGPU_FULL, far.x, win);
-                    const float fy = __shfl_sync (VOXGPU_FULL, far.y, win);
-                    const float fz = __shfl_sync (VOXGPU_FULL, far.z, win);
-                    if (mine) { best = bd; best_i = bi; best_p.x = fx; best_p.y = fy; best_p.z = fz; }
-                }
-            }
-            else if (st == LEAF)
-            {
-                const unsigned n = lf_info & 0x7fffffffu;
-                for (unsigned i=0; i<n; i++)
-                {
-                    const float4 dq = __ldg (tr.dots + (size_t) lf_link + i);
-                    V3 vmin = v3 (dq), vmax, far;
-                    vmax.x = __fadd_rn (vmin.x, tr.vx);
-                    vmax.y = __fadd_rn (vmin.y, tr.vy);
-                    vmax.z = __fadd_rn (vmin.z, tr.vz);
-                    if (ray_box_fast (vmin, vmax, lf_e, d, k.r, k.dok, far))
-                    {
-                        const float dist = l1_metric (lf_e, far);
-                        if (dist < best) { best = dist; best_i = (int) i; best_p = far; }
-                        if (dist == 0.0f) break;                /* search.c:65-71 */
-                    }
-                }
-            }
-            if (st == LEAF)
-            {
-                if (best < inf)
-                {
-                    out.leaf = (int) cur;
-                    stack[0] = make_float4 (best_p.x, best_p.y, best_p.z, __uint_as_float (lf_link + (unsigned) best_i));
-                    cur = VOXGPU_DEAD;
-                }
-                else st = POP;
-            }
-        }
-
-        if (st == POP)
-        {
-            /* this call missed: go on with the nearest pending one */
-            if (sp == 0) cur = VOXGPU_DEAD;
-            else
-            {
-                const float4 e = stack[--sp];
-                org.x = e.x; org.y = e.y; org.z = e.z;
-                cur = __float_as_uint (e.w);
-            }
-        }
+        warp_search_step (tr, k, s, stack, lane);
     }
-    out.voxel = -1;
-    if (out.leaf >= 0)
-    {
-        const float4 h = stack[0];
-        out.point.x = h.x; out.point.y = h.y; out.point.z = h.z;
-        out.voxel = __float_as_int (h.w);
-    }
+    lane_search_result (s, stack, out);
     return iterations;
 }

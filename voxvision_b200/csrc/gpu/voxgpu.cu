@@ -731,6 +731,120 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
 }
 
 /*
+ * K1 with per-LANE work refill (the form voxgpu_render launches for BEST).  In the
+ * tile form above a warp keeps its 32 rays until the slowest has finished: on C2 the
+ * average instruction ran with 21 of 32 lanes, most of the missing ones being lanes whose
+ * ray was already done.  Here the ticket counter hands out PIXELS (in tile order, so
+ * that rays fetched together are neighbours): whenever at least `refill_min` lanes of
+ * a warp are idle, they retire their finished pixels, draw new ones with one warp-
+ * aggregated atomicAdd (ballot + popc rank), generate their rays and join the search
+ * at the root while the other lanes carry on where they were.  The traversal itself
+ * is warp_search_step, unchanged; results do not depend on which lane or in which
+ * company a ray is searched.
+ */
+#define STREAM_BATCH 64u
+template <bool OUT_HITS, unsigned STRIPS>
+__global__ void __launch_bounds__(RENDER_BLOCK, 7)
+k_render_stream (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
+                 unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
+                 unsigned *counters, int refill_min)
+{
+    const int tiles_x = fr.w >> 3;
+    const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
+    const int lane = threadIdx.x & 31;
+    const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
+    const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
+    const unsigned tickets = per_strip * STRIPS * 32u;     /* pixel tickets; some map to no tile */
+    float4 stack[VOXGPU_RAY_STACK];
+    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
+
+    LaneSearch s;
+    lane_search_begin (s, 0, origin, false);
+    RayK k = ray_constants (origin);
+    int pix_x = -1, pix_y = 0;          /* the pixel this lane is working on, -1 = none */
+    /* warp-uniform: the warp's batch of pixel tickets [next, next + have), and whether the
+       global counter has run out.  One atomic per STREAM_BATCH pixels, so that lanes in
+       the middle of a long search do not wait for one every time their neighbours refill. */
+    unsigned next = 0, have = 0;
+    bool dry = false;
+
+    for (;;)
+    {
+        unsigned idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
+        if ((have || !dry) && __popc (idle) >= refill_min)
+        {
+            /* retire */
+            if (s.cur == VOXGPU_DEAD && pix_x >= 0)
+            {
+                RayResult r;
+                lane_search_result (s, stack, r);
+                unsigned color = 0;
+                if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+                pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
+                if (OUT_HITS)
+                {
+                    const size_t pos = (size_t) pix_y * fr.w + pix_x;
+                    if (leaf_ids) leaf_ids[pos] = r.leaf;
+                    if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+                }
+                pix_x = -1;
+            }
+            if (have == 0)
+            {
+                if (lane == 0) next = atomicAdd (&counters[0], STREAM_BATCH);
+                next = __shfl_sync (0xffffffffu, next, 0);
+                if (next >= tickets) dry = true; else have = STREAM_BATCH;     /* tickets is a multiple of the batch */
+            }
+            const unsigned n = (unsigned) __popc (idle);
+            const unsigned take = n < have ? n : have;
+            const unsigned rank = (unsigned) __popc (idle & ((1u << lane) - 1u));
+            if (s.cur == VOXGPU_DEAD && rank < take)
+            {
+                const unsigned ticket = next + rank;
+                const unsigned tt = ticket >> 5;
+                const unsigned tile = (tt % STRIPS) * per_strip + tt / STRIPS;
+                if (tile < ntiles)
+                {
+                    const unsigned in = ticket & 31u;
+                    pix_x = (int) (tile % tiles_x) * 8 + (int) (in & 7u);
+                    pix_y = (int) (tile / tiles_x) * 4 + (int) (in >> 3);
+                    const V3 dir = screen2world (cam, pix_x, fr.y0 + pix_y, fr.w);
+                    k = ray_constants (dir);
+                    lane_search_begin (s, 0, origin, true);
+                }
+            }
+            next += take; have -= take;
+            idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
+        }
+        if (idle == 0xffffffffu)
+        {
+            if (!have && dry) break;
+            continue;                   /* only tickets without a tile were drawn, or the batch ran out */
+        }
+        warp_search_step (tr, k, s, stack, lane);
+    }
+    if (pix_x >= 0)
+    {
+        RayResult r;
+        lane_search_result (s, stack, r);
+        unsigned color = 0;
+        if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+        pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
+        if (OUT_HITS)
+        {
+            const size_t pos = (size_t) pix_y * fr.w + pix_x;
+            if (leaf_ids) leaf_ids[pos] = r.leaf;
+            if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+        }
+    }
+    if (lane == 0)
+    {
+        const unsigned done = atomicAdd (&counters[1], 1u);
+        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
+    }
+}
+
+/*
  * K1b: the reference's FAST / ADAPTIVE / ray-merge quality modes, pixel for pixel
  * (renderer.c:214-318).  In those modes the pixels of a 4x4 block depend on each other --
  * pixel i+1 is first searched inside the leaf pixel i hit, ADAPTIVE decides per block from
@@ -915,14 +1029,16 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
    slots so that renders in flight on different streams never share one. */
 #define COUNTER_SLOTS 64
 static unsigned *g_counters[64] = {0};
-static int g_render_blocks[64][3] = {{0}};
+static int g_render_blocks[64][5] = {{0}};
 static std::atomic<unsigned> g_counter_seq{0};
 static int g_variant = 1;
+static int g_refill_min = 8;
 static unsigned long long *g_trace = NULL;
 
 extern "C" void voxgpu_set_trace (void *d_trace) { g_trace = (unsigned long long*) d_trace; }
 
 extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
+extern "C" void voxgpu_set_refill_min (int n) { g_refill_min = n < 1 ? 1 : (n > 32 ? 32 : n); }
 
 static unsigned* counter_slot (int device)
 {
@@ -940,6 +1056,11 @@ static unsigned* counter_slot (int device)
         int b2 = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true>, RENDER_BLOCK, 0);
         g_render_blocks[device][2] = sms * (b2 > 0 ? b2 : 1);
+        int b3 = 0, b4 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b3, k_render_stream<false, RENDER_STRIPS>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b4, k_render_stream<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
+        g_render_blocks[device][3] = sms * (b3 > 0 ? b3 : 1);
+        g_render_blocks[device][4] = sms * (b4 > 0 ? b4 : 1);
         g_counters[device] = p;
     }
     return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
@@ -1090,7 +1211,15 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         memset (&sch, 0, sizeof sch);
         if (sched && g_variant == 1 && sched->t_heavy &&
             sched_prepare (sched, t->device, df.w, df.y0, df.rows, st, &sch)) return -1;
-        if (g_variant == 2)
+        if (g_variant >= 3)
+        {   /* per-lane refill; g_variant - 2 = refill threshold when >= 3 ... */
+            const int rmin = g_refill_min;
+            grid = g_render_blocks[t->device][hits ? 4 : 3];
+            if (grid > blocks) grid = blocks;
+            if (hits) k_render_stream<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, rmin);
+            else      k_render_stream<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, rmin);
+        }
+        else if (g_variant == 2)
         {   /* raster tile order, kept for A/B measurements */
             if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
             else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
