@@ -50,6 +50,7 @@ METRIC = "Mrays/s primary-ray render (skull 1080p)"
 GATHER_BATCH = 8          # frames per NCCL gather
 RING = 2 * GATHER_BATCH   # device framebuffers per rank
 FRAME_STREAMS = 4         # frames in flight per GPU (independent frames of the scripted path)
+E2E_CONTEXTS = int(os.environ.get("VOX_E2E_CONTEXTS", "4"))          # render contexts (host surfaces) taking the frames round-robin in the e2e leg
 
 
 def rank_env():
@@ -350,30 +351,56 @@ def run_own(args):
         kernel_ms.append(kt.elapsed_ms())
     sync_all()
 
-    # ---- end-to-end leg: the reference-facing API with a host surface --------
-    def e2e_step():
-        for f in range(FRAMES):
-            pos, look = poses[f]
-            cam.set_position(pos)
-            cam.look_at(look)
-            ctx.set_camera(cam)
-            ctx.render()
-            ctx.redraw()            # frame f is now in surface->pixels (host memory)
-        return int(ctx.pixels()[H // 2, W // 2])
+    # ---- end-to-end leg: the reference-facing API with host surfaces ----------
+    # Every frame: camera setters -> vox_context_set_camera -> vox_render -> vox_redraw, the frame
+    # ends up in surface->pixels (host memory) and one pixel of it is read by the host.
+    # E2E_CONTEXTS contexts (each with its own page-locked surface, like a swap chain) take the
+    # frames round-robin, so frame f+1.. render while frame f crosses PCIe; with one context
+    # (`e2e.single_context`) render and copy-out of consecutive frames cannot overlap.
+    def make_ctx():
+        c = vv.Context(W, H)
+        c.set_scene(tree)
+        c.set_quality(vv.QUALITY_BEST)
+        return c, vv.Camera("simple-camera")
 
-    ctx.set_camera(cam)
-    e2e_step()
-    sync_all()
+    def e2e_step(ring):
+        k, acc = len(ring), 0
+        for f in range(FRAMES):
+            c, cm = ring[f % k]
+            if f >= k:
+                c.redraw()                                   # frame f-k is now in its surface->pixels
+                acc ^= int(c.pixels()[H // 2, W // 2])
+            pos, look = poses[f]
+            cm.set_position(pos)
+            cm.look_at(look)
+            c.set_camera(cm)
+            c.render()
+        for f in range(FRAMES, FRAMES + k):
+            c, _ = ring[f % k]
+            c.redraw()
+            acc ^= int(c.pixels()[H // 2, W // 2])
+        return acc
+
+    def time_e2e(ring, steps):
+        for _, cm in ring:
+            cm.set_fov(FOV)
+        e2e_step(ring)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step(ring)
+        sync_all()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
     e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    ring = [make_ctx() for _ in range(E2E_CONTEXTS)]
+    e2e_single_s = time_e2e(ring[:1], e2e_steps)
+    e2e_s = time_e2e(ring, e2e_steps)
     if vv.last_error():
         raise vv.VoxError(vv.last_error())
 
@@ -431,7 +458,9 @@ def run_own(args):
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s",
                 "h2d_bytes_per_step": FRAMES * (C.sizeof(api.GpuCamera) + C.sizeof(api.GpuFrame)),
                 "d2h_bytes_per_step": FRAMES * frame_bytes, "steps": e2e_steps,
-                "path": "vox_render + vox_redraw per frame: band kernels into a device framebuffer, each band DMA-copied into the page-locked surface while the next renders"},
+                "contexts_in_flight": E2E_CONTEXTS,
+                "single_context": round(world * e2e_steps * FRAMES * RAYS_PER_FRAME / e2e_single_s / 1e6, 2),
+                "path": "vox_render + vox_redraw per frame on a ring of contexts (each with its own page-locked surface): band kernels into a device framebuffer, each band DMA-copied into the surface while the next band / next frame renders"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

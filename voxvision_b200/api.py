@@ -548,11 +548,11 @@ class Context:
             pass
 
     def set_scene(self, tree):
-        self._keep.append(tree)
+        self._scene = tree
         libs.rnd.vox_context_set_scene(self.h, tree.h if tree is not None else None)
 
     def set_camera(self, cam):
-        self._keep.append(cam)
+        self._camera = cam
         libs.rnd.vox_context_set_camera(self.h, cam.h)
 
     def set_quality(self, q):

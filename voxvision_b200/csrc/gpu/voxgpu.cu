@@ -1261,8 +1261,16 @@ struct voxgpu_present
     cudaEvent_t done[PRESENT_MAX_BANDS];
     voxgpu_sched *sched[PRESENT_MAX_BANDS];  /* heavy-first tile order, frame to frame */
     cudaEvent_t start;
-    int in_flight;
+    int in_flight;                        /* a frame has been queued and not yet waited for */
+    int used_bands;                       /* bands of the frame in flight */
+    int fixed_bands;                      /* band count was asked for explicitly: never adapt */
 };
+
+/* Presenters with a frame in flight, process-wide.  A caller that keeps several contexts
+   in flight (a swap chain of surfaces) already overlaps one frame's copy-out with the next
+   frame's kernels; splitting such frames into bands only adds launches (measured on C2:
+   6 contexts x 1 band 12.0 Grays/s, x 2 bands 11.4; one context: 4 bands 6.0, 1 band 5.0). */
+static std::atomic<int> g_presents_in_flight (0);
 
 extern "C" void voxgpu_present_destroy (voxgpu_present *p)
 {
@@ -1274,6 +1282,7 @@ extern "C" void voxgpu_present_destroy (voxgpu_present *p)
         voxgpu_sched_destroy (p->sched[i]);
     }
     if (p->start) cudaEventDestroy (p->start);
+    if (p->in_flight) g_presents_in_flight--;
     cudaFree (p->fb);
     free (p);
 }
@@ -1281,16 +1290,18 @@ extern "C" void voxgpu_present_destroy (voxgpu_present *p)
 extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
 {
     if (w <= 0 || h <= 0 || (w & 0xf) || (h & 0x3)) { fail ("voxgpu_present_create: bad geometry %dx%d", w, h); return NULL; }
+    int fixed = bands > 0;
     if (bands <= 0)
     {
         const char *env = getenv ("VOXGPU_BANDS");
         bands = env ? atoi (env) : 4;
+        fixed = env != NULL;
     }
     if (bands < 1) bands = 1;
     if (bands > PRESENT_MAX_BANDS) bands = PRESENT_MAX_BANDS;
     if (bands > h / 4) bands = h / 4;
     voxgpu_present *p = (voxgpu_present*) calloc (1, sizeof *p);
-    p->w = w; p->h = h; p->bands = bands;
+    p->w = w; p->h = h; p->bands = bands; p->fixed_bands = fixed;
     int least = 0, greatest = 0;
     cudaError_t e;
     if ((e = cudaGetDevice (&p->device)) != cudaSuccess ||
@@ -1328,13 +1339,16 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     if (cur != p->device) return fail ("voxgpu_present_render: presenter lives on device %d, current device is %d", p->device, cur);
 
     const int units = p->h / 4;             /* bands are multiples of 4 rows (renderer.c:97-100) */
+    if (p->in_flight && voxgpu_present_wait (p)) return -1;   /* the previous frame owns fb and the events */
+    const int others = g_presents_in_flight.load ();
+    const int nbands = (!p->fixed_bands && others > 0) ? 1 : p->bands;
     CU (cudaEventRecord (p->start, p->stream[0]));
-    for (int i=0; i<p->bands; i++)
+    for (int i=0; i<nbands; i++)
     {
         /* the later bands wait for the start mark so that the elapsed time covers all of them */
         if (i) CU (cudaStreamWaitEvent (p->stream[i], p->start, 0));
-        const int y0 = (int) ((long long) units * i / p->bands) * 4;
-        const int y1 = (int) ((long long) units * (i + 1) / p->bands) * 4;
+        const int y0 = (int) ((long long) units * i / nbands) * 4;
+        const int y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
         if (y1 <= y0) { CU (cudaEventRecord (p->done[i], p->stream[i])); continue; }
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
@@ -1348,22 +1362,26 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
                                    cudaMemcpyDeviceToHost, p->stream[i]));
         CU (cudaEventRecord (p->done[i], p->stream[i]));
     }
+    p->used_bands = nbands;
     p->in_flight = 1;
+    g_presents_in_flight++;
     return 0;
 }
 
 extern "C" int voxgpu_present_wait (voxgpu_present *p)
 {
     if (!p || !p->in_flight) return 0;
-    for (int i=0; i<p->bands; i++) CU (cudaEventSynchronize (p->done[i]));
+    for (int i=0; i<p->used_bands; i++) CU (cudaEventSynchronize (p->done[i]));
+    p->in_flight = 0;
+    g_presents_in_flight--;
     return 0;
 }
 
 extern "C" float voxgpu_present_last_ms (voxgpu_present *p)
 {
-    if (!p || !p->in_flight) return -1.0f;
+    if (!p || !p->used_bands) return -1.0f;
     float worst = -1.0f;
-    for (int i=0; i<p->bands; i++)
+    for (int i=0; i<p->used_bands; i++)
     {
         float ms = 0.0f;
         if (cudaEventSynchronize (p->done[i]) != cudaSuccess ||
