@@ -32,6 +32,44 @@ VOX_EXPORT size_t vox_voxels_in_tree (const struct vox_node *tree);
 /** \brief Bounding box of the (sub)tree (tree.h:77). **/
 VOX_EXPORT void vox_bounding_box (const struct vox_node *tree, struct vox_box *box);
 
+/**
+   \brief Rebuild a tree from its voxels (tree.h:78-86, tree.c:366-435).
+
+   Returns a NEW, freshly balanced tree; the old one stays valid and must still
+   be destroyed by the caller.
+**/
+VOX_EXPORT struct vox_node* vox_rebuild_tree (const struct vox_node *tree);
+
+/**
+   \brief Insert a voxel on the fly (tree.h:88-96, tree.c:437-621).
+
+   `*tree_ptr` is the root (or NULL for an empty tree) and is updated.  `voxel`
+   is aligned to the voxel grid in place.  The edited tree has the shape the
+   reference's tree has after the same edit.  The GPU copy of the tree is
+   refreshed lazily: the next query or vox_render() after a burst of edits
+   re-flattens the tree and uploads it once.  As in the reference, edits must
+   not overlap searches or renders of the same tree, and node pointers returned
+   by earlier searches are dead after an edit.
+
+   \return 1 on success, 0 if the voxel was already in the tree.
+**/
+VOX_EXPORT int vox_insert_voxel (struct vox_node **tree_ptr, vox_dot voxel);
+/** \brief vox_insert_voxel() by coordinates (tree.h:98-104, tree.c:623-633). **/
+VOX_EXPORT int vox_insert_voxel_coord (struct vox_node **tree_ptr, float x, float y, float z);
+
+/**
+   \brief Delete a voxel on the fly (tree.h:106-114, tree.c:635-855).
+
+   When the last voxel goes, the tree is destroyed and `*tree_ptr` becomes NULL.
+   \return 1 on success, 0 if there was no such voxel in the tree.
+**/
+VOX_EXPORT int vox_delete_voxel (struct vox_node **tree_ptr, vox_dot voxel);
+/** \brief vox_delete_voxel() by coordinates (tree.h:116-122, tree.c:857-866). **/
+VOX_EXPORT int vox_delete_voxel_coord (struct vox_node **tree_ptr, float x, float y, float z);
+
+/** \brief Print a (sub)tree to stdout; node ids are breadth-first positions (tree.h:124-130, tree.c:868-918). **/
+VOX_EXPORT void vox_dump_tree (const struct vox_node *tree);
+
 /** \brief A tree that is one solid box (tree.h:135, tree.c:229-240). **/
 VOX_EXPORT struct vox_node* vox_make_dense_leaf (const struct vox_box *box);
 

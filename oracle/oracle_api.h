@@ -105,6 +105,14 @@ ORC_EXPORT orc_tree* orc_tree_build (const float *xyz, size_t n);
 /* Tree built by successive vox_insert_voxel calls (tree.c:506-650); reference
  * glue only -- the port returns NULL (insertion is out of scope). */
 ORC_EXPORT orc_tree* orc_tree_build_by_insertion (const float *xyz, size_t n);
+/* Online edits: entry i inserts (insert[i] != 0) or deletes voxel xyz[3i..] with
+ * vox_insert_voxel / vox_delete_voxel (tree.c:613-621, 847-855); result[i] = their return
+ * value.  Returns 0 if unsupported (the port).  orc_tree_rebuild = vox_rebuild_tree
+ * (tree.c:424-435), NULL if unsupported. */
+/* A tree from flat arrays in the orc_flat layout (copied). */
+ORC_EXPORT orc_tree* orc_tree_from_flat (const orc_flat *flat, uint64_t n_nodes);
+ORC_EXPORT int orc_tree_edit (orc_tree *t, const uint8_t *insert, const float *xyz, size_t n, uint8_t *result);
+ORC_EXPORT orc_tree* orc_tree_rebuild (orc_tree *t);
 ORC_EXPORT void orc_tree_free (orc_tree *t);
 ORC_EXPORT void orc_tree_info_get (orc_tree *t, orc_tree_info *info);
 ORC_EXPORT void orc_tree_flatten (orc_tree *t, orc_flat *out);

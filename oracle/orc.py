@@ -92,6 +92,12 @@ class Oracle:
         L.orc_tree_build_by_insertion.restype = vp
         L.orc_tree_build_by_insertion.argtypes = [vp, sz]
         L.orc_tree_free.argtypes = [vp]
+        L.orc_tree_from_flat.restype = vp
+        L.orc_tree_from_flat.argtypes = [C.POINTER(Flat), C.c_uint64]
+        L.orc_tree_edit.restype = i
+        L.orc_tree_edit.argtypes = [vp, vp, vp, sz, vp]
+        L.orc_tree_rebuild.restype = vp
+        L.orc_tree_rebuild.argtypes = [vp]
         L.orc_tree_info_get.argtypes = [vp, C.POINTER(TreeInfo)]
         L.orc_tree_flatten.argtypes = [vp, C.POINTER(Flat)]
         L.orc_tree_reordered_set.argtypes = [vp, vp]
@@ -120,13 +126,22 @@ class Oracle:
     def tree(self, xyz, by_insertion=False):
         return OracleTree(self, xyz, by_insertion)
 
+    def tree_from_flat(self, a):
+        """A tree from canonical flat arrays (dict as OracleTree.flatten() / vv.Tree.export())."""
+        keep = {k: np.ascontiguousarray(a[k]) for k, _ in Flat._fields_}
+        fl = Flat(*[keep[k].ctypes.data for k, _ in Flat._fields_])
+        return OracleTree(self, None, _handle=self.lib.orc_tree_from_flat(C.byref(fl), keep["flags"].shape[0]))
+
     def camera(self, kind=CAMERA_SIMPLE):
         return OracleCamera(self, kind)
 
 
 class OracleTree:
-    def __init__(self, orc, xyz, by_insertion=False):
+    def __init__(self, orc, xyz, by_insertion=False, _handle=None):
         self.orc = orc
+        if _handle is not None:
+            self.h, self.n = _handle, 0
+            return
         xyz = _f32(xyz).reshape(-1, 3)
         self.n = xyz.shape[0]
         fn = orc.lib.orc_tree_build_by_insertion if by_insertion else orc.lib.orc_tree_build
@@ -138,6 +153,21 @@ class OracleTree:
         if getattr(self, "h", None):
             self.orc.lib.orc_tree_free(self.h)
             self.h = None
+
+    def edit(self, insert, xyz):
+        """vox_insert_voxel (insert[i] true) / vox_delete_voxel per row of xyz; their return values."""
+        xyz = _f32(xyz).reshape(-1, 3)
+        ins = np.ascontiguousarray(np.broadcast_to(np.asarray(insert, np.uint8), (xyz.shape[0],)))
+        res = np.zeros(xyz.shape[0], np.uint8)
+        if not self.orc.lib.orc_tree_edit(self.h, ins.ctypes.data, xyz.ctypes.data, xyz.shape[0], res.ctypes.data):
+            raise RuntimeError("this oracle cannot edit trees (reference glue only)")
+        return res
+
+    def rebuild(self):
+        h = self.orc.lib.orc_tree_rebuild(self.h)
+        if not h:
+            raise RuntimeError("this oracle cannot rebuild trees (reference glue only)")
+        return OracleTree(self.orc, None, _handle=h)
 
     def info(self):
         ti = TreeInfo()

@@ -113,6 +113,72 @@ orc_tree* orc_tree_build_by_insertion (const float *xyz, size_t n)
     return t;
 }
 
+/* A tree given as flat arrays (orc_flat layout), rebuilt as the reference's heap nodes
+   (tree.h:22-38; allocation sizes as node_alloc, tree.c:212-227). */
+orc_tree* orc_tree_from_flat (const orc_flat *f, uint64_t n_nodes)
+{
+    orc_tree *t = calloc (1, sizeof *t);
+    if (!n_nodes) return t;
+    struct vox_node **byid = malloc (n_nodes * sizeof *byid);
+    for (uint64_t id=0; id<n_nodes; id++)
+    {
+        struct vox_node *n = byid[id] = vox_alloc (sizeof (struct vox_node));
+        memset (n, 0, sizeof *n);
+        DOT_IN (n->bounding_box.min, f->bb_min + 3*id);
+        DOT_IN (n->bounding_box.max, f->bb_max + 3*id);
+        n->flags = f->flags[id];
+        n->dots_num = f->dots_num[id];
+        if (n->flags & VOX_DENSE_LEAF) continue;
+        if (n->flags & VOX_LEAF)
+        {
+            size_t cap = n->dots_num > VOX_MAX_DOTS ? n->dots_num : VOX_MAX_DOTS;
+            n->data.dots = vox_alloc (cap * sizeof (vox_dot));
+            for (unsigned k=0; k<n->dots_num; k++) DOT_IN (n->data.dots[k], f->dots + 3*(f->dots_off[id] + k));
+        }
+        else DOT_IN (n->data.inner.center, f->center + 3*id);
+    }
+    for (uint64_t id=0; id<n_nodes; id++)
+    {
+        if (f->flags[id] & VOX_LEAF_MASK) continue;
+        uint32_t next = f->first_child[id];
+        for (int s=0; s<VOX_NS; s++) if (f->child_mask[id] & (1u << s)) byid[id]->data.inner.children[s] = byid[next++];
+    }
+    t->root = byid[0];
+    free (byid);
+    return t;
+}
+
+static void drop_index (orc_tree *t)
+{
+    free (t->bfs); free (t->dots_off); free (t->ids);
+    t->bfs = NULL; t->dots_off = NULL; t->ids = NULL;
+    t->indexed = 0;
+}
+
+/* vox_insert_voxel / vox_delete_voxel (tree.c:613-621, 847-855), one call per entry. */
+int orc_tree_edit (orc_tree *t, const uint8_t *insert, const float *xyz, size_t n, uint8_t *result)
+{
+    drop_index (t);
+    for (size_t i=0; i<n; i++)
+    {
+        vox_dot d;
+        DOT_IN (d, xyz + 3*i);
+        int r = insert[i] ? vox_insert_voxel (&t->root, d) : vox_delete_voxel (&t->root, d);
+        if (result) result[i] = (uint8_t) r;
+    }
+    return 1;
+}
+
+/* vox_rebuild_tree (tree.c:424-435) */
+orc_tree* orc_tree_rebuild (orc_tree *t)
+{
+    orc_tree *r = calloc (1, sizeof *r);
+    r->root = vox_rebuild_tree (t->root);
+    r->n = 0;
+    r->set = NULL;
+    return r;
+}
+
 void orc_tree_free (orc_tree *t)
 {
     if (!t) return;

@@ -400,6 +400,51 @@ orc_tree* orc_tree_build_by_insertion (const float *xyz, size_t n)
     return NULL; /* tree mutation is out of scope */
 }
 
+/* A tree given as flat arrays (orc_flat layout), e.g. one that was edited elsewhere. */
+orc_tree* orc_tree_from_flat (const orc_flat *f, uint64_t n_nodes)
+{
+    orc_tree *t = calloc (1, sizeof *t);
+    if (!n_nodes) return t;
+    onode **byid = malloc (n_nodes * sizeof *byid);
+    for (uint64_t id=0; id<n_nodes; id++)
+    {
+        onode *n = byid[id] = calloc (1, sizeof *n);
+        memcpy (n->bb_min, f->bb_min + 3*id, sizeof (vec3));
+        memcpy (n->bb_max, f->bb_max + 3*id, sizeof (vec3));
+        n->flags = f->flags[id];
+        n->dots_num = f->dots_num[id];
+        if (n->flags & ORC_DENSE_LEAF) continue;
+        if (n->flags & ORC_LEAF)
+        {
+            size_t cap = n->dots_num > MAX_DOTS ? n->dots_num : MAX_DOTS;
+            n->dots = malloc (cap * sizeof (vec3));
+            memcpy (n->dots, f->dots + 3*f->dots_off[id], n->dots_num * sizeof (vec3));
+        }
+        else memcpy (n->center, f->center + 3*id, sizeof (vec3));
+    }
+    for (uint64_t id=0; id<n_nodes; id++)
+    {
+        if (f->flags[id] & 3u) continue;
+        uint32_t next = f->first_child[id];
+        for (int s=0; s<NS; s++) if (f->child_mask[id] & (1u << s)) byid[id]->children[s] = byid[next++];
+    }
+    t->root = byid[0];
+    free (byid);
+    return t;
+}
+
+int orc_tree_edit (orc_tree *t, const uint8_t *insert, const float *xyz, size_t n, uint8_t *result)
+{
+    (void) t; (void) insert; (void) xyz; (void) n; (void) result;
+    return 0; /* reference glue only: the port keeps to the search / render path */
+}
+
+orc_tree* orc_tree_rebuild (orc_tree *t)
+{
+    (void) t;
+    return NULL;
+}
+
 void orc_tree_free (orc_tree *t)
 {
     if (!t) return;

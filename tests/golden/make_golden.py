@@ -134,6 +134,20 @@ def main():
     meta["skull_rays_hits"] = int((leaf >= 0).sum())
     meta["skull_balls_hits"] = int(arrays["skull_balls"].sum())
 
+    # ---- online edits (tree.c:437-866): the tree after a scripted burst of insertions / deletions,
+    #      its rays, and the tree vox_rebuild_tree makes of it
+    vox, ins, pts = ds.edit_script()
+    te = R.tree(vox)
+    arrays["edit_results"] = te.edit(ins, pts)
+    ef = te.flatten()
+    meta["edits"] = {"tree": tree_digest(ef), "applied": int(arrays["edit_results"].sum()),
+                     "voxels": int(ef["dots_num"][0]), "rebuilt": tree_digest(te.rebuild().flatten())}
+    oo, dd = ds.random_rays(4096, side=48)
+    oo -= 24
+    l, h, _ = te.rays(oo, dd)
+    arrays["edit_rays_leaf"], arrays["edit_rays_hit"] = l, h
+    meta["edits"]["ray_hits"] = int((l >= 0).sum())
+
     # reference benchmark known answers (benchmarks/voxtrees/hit-box.c:16-27, ball-intersection.c:14-23)
     one = R.tree(np.array([[0, 10, 0]], np.float32), by_insertion=True)
     j = np.arange(10, dtype=np.float32)

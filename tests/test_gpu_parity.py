@@ -401,6 +401,76 @@ def test_collision_detector(gpu, skull):
     r.vox_destroy_cd(cd)
 
 
+# ------------------------------------------------- online edits (f-3): the device copy follows
+
+def test_edited_tree_on_device(gpu, checker, golden, ds):
+    """vox_insert_voxel / vox_delete_voxel between queries: every burst of edits is followed by
+    ray and ball batches that must see the edited tree (re-flattened and re-uploaded lazily)."""
+    meta, arr = golden
+    vox, ins, pts = ds.edit_script()
+    t = gpu.Tree.build(vox)
+    o, d = ds.random_rays(4096, side=48)
+    o -= 24
+    assert_rays_equal(t.rays(o, d), checker.tree(vox).rays(o, d))     # device copy of the unedited tree exists now
+    for lo in range(0, len(ins), 750):
+        t.edit(ins[lo:lo + 750], pts[lo:lo + 750])
+        ot = checker.tree_from_flat(t.export())
+        assert_rays_equal(t.rays(o, d), ot.rays(o, d))
+        c, r = ds.random_balls(2048, *t.bounding_box())
+        assert np.array_equal(t.balls(c, r), ot.balls(c, r))
+    leaf, hit, _ = t.rays(o, d)
+    assert np.array_equal(leaf, arr["edit_rays_leaf"])                 # the reference's own edited tree, via golden
+    m = leaf >= 0
+    assert int(m.sum()) == meta["edits"]["ray_hits"]
+    assert np.array_equal(bits(hit[m]), bits(arr["edit_rays_hit"][m]))
+    # single-query API on the edited tree, including a search restarted inside a returned leaf
+    i = int(np.flatnonzero(m)[0])
+    lid, p = t.ray(o[i], d[i])
+    assert lid == leaf[i] and np.array_equal(bits(p), bits(hit[i]))
+    lid2, p2 = t.ray(o[i], d[i], start=t.node(lid))
+    assert lid2 == lid
+
+
+def test_render_follows_edits(gpu, checker, ds):
+    """A context keeps its scene pointer across edits (the root handle is stable): the next
+    vox_render shows the edited tree; then vox_rebuild_tree's tree as a new scene."""
+    vox = ball_voxels(20)
+    t = gpu.Tree.build(vox)
+    w, h = 256, 128
+    cam = ds.setup_camera(gpu.Camera("simple-camera"), (5, -70, 10), (0, 0, 0), 1.0, w, h)
+    ctx = gpu.Context(w, h)
+    ctx.set_scene(t)
+    ctx.set_camera(cam)
+    ctx.set_quality(gpu.QUALITY_BEST)
+
+    def frame():
+        ctx.render()
+        ctx.redraw()
+        assert gpu.last_error() == ""
+        return ctx.pixels().copy()
+
+    def oracle_frame(tree):
+        ocam = ds.setup_camera(checker.camera(0), (5, -70, 10), (0, 0, 0), 1.0, w, h)
+        return checker.tree_from_flat(tree.export()).render(ocam, w, h, 0, ctx.texture(), want_hits=False)
+
+    p0 = frame()
+    assert np.array_equal(p0, oracle_frame(t))
+    # drill a tunnel along the view axis and float a slab in front of the ball
+    g = np.arange(-2, 3)
+    tunnel = np.stack(np.meshgrid(g, np.arange(-20, 20), g + 2, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    slab = np.stack(np.meshgrid(np.arange(-12, -4), [-30.0], np.arange(-3, 9), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    assert t.delete(tunnel).sum() > 500
+    assert t.insert(slab).sum() == len(slab)
+    p1 = frame()
+    assert not np.array_equal(p0, p1)
+    assert np.array_equal(p1, oracle_frame(t))
+    rb = t.rebuild()
+    ctx.set_scene(rb)
+    p2 = frame()
+    assert np.array_equal(p2, oracle_frame(rb))
+    assert rb.voxels() == t.voxels()                   # same voxels, differently shaped tree
+
+
 # ------------------------------------------------- full-size configs, by properties
 
 def test_c3_full_size_properties(gpu, port, ds):

@@ -135,6 +135,29 @@ def ball_union_voxels(side=1024, n_balls=4096, seed=SEED + 2, rmin=8.0, rmax=28.
 
 # ------------------------------------------------------------------ cameras
 
+def edit_script(n_edits=3000, seed=SEED + 3):
+    """A deterministic online-edit workload (f-3): start from a radius-12 voxel ball plus a solid
+    6x6x6 box and a sparse cloud, then insert / delete voxels -- deletions mostly of present voxels,
+    insertions mostly next to the solid parts (the dense-leaf rules of tree.c:461-503, 641-756).
+    Returns (voxels, insert flags, points); points are un-aligned on purpose (vox_align)."""
+    g = np.arange(-12, 12)
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    v = np.stack([x, y, z], -1).reshape(-1, 3)
+    ball = v[(v * v).sum(1) < 144]
+    g = np.arange(0, 6)
+    box = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) + np.array([14, -3, -3])
+    u = uniform01(0, 3 * 400 + 5 * n_edits, seed)
+    cloud = np.floor(u[:1200].reshape(400, 3) * 30 - np.array([15, 15, -14])).astype(np.int64)
+    vox = np.unique(np.concatenate([ball, box, cloud]), axis=0).astype(np.float32)
+    e = u[1200:].reshape(n_edits, 5)
+    ins = e[:, 0] < 0.5
+    pts = (e[:, 1:4] * np.array([40, 34, 46]) - np.array([16, 17, 17])).astype(np.float32)
+    pick = (e[:, 4] * len(vox)).astype(np.int64)
+    use_existing = ~ins & (e[:, 4] < 0.8)
+    pts[use_existing] = vox[(pick[use_existing] * 5) % len(vox)] + np.float32(0.25)
+    return vox, ins, pts
+
+
 def orbit_pose(frame, frames=360, centre=(128.0, 128.0, 128.0), radius=328.0):
     """C2 camera path: position on the xz orbit, looking at the centre.
     Frame 0 is exactly examples/scene1.cfg's camera (128,128,-200)."""

@@ -182,6 +182,12 @@ class _Libs:
         t.vox_bounding_box.argtypes = [_vp, C.POINTER(_Box)]
         t.vox_make_dense_leaf.restype = _vp; t.vox_make_dense_leaf.argtypes = [C.POINTER(_Box)]
         t.vox_set_voxel_size.argtypes = [_f, _f, _f]
+        t.vox_insert_voxel.restype = _i; t.vox_insert_voxel.argtypes = [C.POINTER(_vp), _vp]
+        t.vox_delete_voxel.restype = _i; t.vox_delete_voxel.argtypes = [C.POINTER(_vp), _vp]
+        t.vox_insert_voxel_coord.restype = _i; t.vox_insert_voxel_coord.argtypes = [C.POINTER(_vp), _f, _f, _f]
+        t.vox_delete_voxel_coord.restype = _i; t.vox_delete_voxel_coord.argtypes = [C.POINTER(_vp), _f, _f, _f]
+        t.vox_rebuild_tree.restype = _vp; t.vox_rebuild_tree.argtypes = [_vp]
+        t.vox_dump_tree.argtypes = [_vp]
         t.vox_tree_get_info.argtypes = [_vp, C.POINTER(_TreeInfo)]
         t.vox_tree_export.argtypes = [_vp, C.POINTER(_TreeArrays)]
         t.vox_tree_import.restype = _vp; t.vox_tree_import.argtypes = [C.POINTER(_TreeArrays), u64, u64]
@@ -405,6 +411,33 @@ class Tree:
 
     def node(self, node_id):
         return libs.trees.vox_tree_node(self.h, node_id)
+
+    # ---- online edits (host; the device copy is refreshed by the next query) ----
+    def edit(self, insert, xyz):
+        """vox_insert_voxel (insert[i] true) / vox_delete_voxel per row of xyz -> their return values.
+        The root pointer is passed by reference as in C; an emptied tree leaves self.h = None."""
+        d = dots4(xyz)
+        ins = np.broadcast_to(np.asarray(insert, bool), (d.shape[0],))
+        res = np.zeros(d.shape[0], np.uint8)
+        root = _vp(self.h)
+        for i in range(d.shape[0]):
+            fn = libs.trees.vox_insert_voxel if ins[i] else libs.trees.vox_delete_voxel
+            res[i] = fn(C.byref(root), d[i].ctypes.data)
+        self.h = root.value
+        return res
+
+    def insert(self, xyz):
+        return self.edit(True, xyz)
+
+    def delete(self, xyz):
+        return self.edit(False, xyz)
+
+    def rebuild(self):
+        """vox_rebuild_tree: a new, independent tree."""
+        h = libs.trees.vox_rebuild_tree(self.h)
+        if not h and self.h:
+            raise VoxError(last_error())
+        return Tree(h)
 
     # ---- queries (GPU) ----
     def ray(self, origin, direction, start=None):

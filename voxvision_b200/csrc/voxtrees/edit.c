@@ -1,0 +1,668 @@
+/*
+ * edit.c -- online tree edits and what they mean for the device copy
+ * (SURVEY.md 8 f-3).
+ *
+ *   vox_insert_voxel[_coord]   reference: src/voxtrees/tree.c:437-633
+ *   vox_delete_voxel[_coord]   reference: src/voxtrees/tree.c:635-866
+ *   vox_rebuild_tree           reference: src/voxtrees/tree.c:366-435
+ *
+ * The searchable form of a tree here is a flat, breadth-first array set that is
+ * mirrored in GPU memory; it has no room for a node to grow.  So the first edit
+ * of a tree makes a linked, mutable mirror of it (`struct enode`), edits are
+ * applied to the mirror with the reference's rules -- the SHAPE of the edited
+ * tree decides later search results (which leaf a ray ends in, tie order
+ * inside leaves, never-shrunk bounding boxes), so the rules are followed to the
+ * letter, quirks included -- and the store is only marked dirty.  The next
+ * query / render / inspection call re-numbers the mirror breadth-first into the
+ * flat arrays (vox_store_sync), drops the device copies, and the usual lazy
+ * upload brings the new arrays to the GPU: a burst of edits between two frames
+ * costs one re-flatten (O(nodes), ~ms for the bundled volumes) and one upload.
+ *
+ * The root handle (`&store->root`) keeps its address across edits, so a context
+ * whose scene is the root keeps rendering the edited tree, as it would with the
+ * reference whenever the reference's root node survives the edit.  Handles of
+ * other nodes die with the first edit after they were obtained (the reference
+ * frees / reallocates nodes on edits as well).
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "build.h"
+
+struct enode
+{
+    float bb_min[3], bb_max[3];
+    uint32_t flags, dots_num;
+    float center[3];                 /* inner */
+    struct enode *child[VOX_NS];     /* inner */
+    float (*dots)[3];                /* leaf; room for max (VOX_MAX_DOTS, dots_num) */
+};
+
+struct vox_edit
+{
+    struct enode *root;
+    float voxel[3];
+};
+
+/* ------------------------------------------------------------ small parts */
+
+static struct enode* enode_new (uint32_t flags)
+{
+    struct enode *n = calloc (1, sizeof *n);
+    if (n) n->flags = flags;
+    return n;
+}
+
+static void enode_free_tree (struct enode *n)
+{
+    if (!n) return;
+    if (!(n->flags & VOX_LEAF_MASK)) for (int i=0; i<VOX_NS; i++) enode_free_tree (n->child[i]);
+    free (n->dots);
+    free (n);
+}
+
+void vox_edit_free (struct vox_edit *e)
+{
+    if (!e) return;
+    enode_free_tree (e->root);
+    free (e);
+}
+
+static inline int same_dot (const float a[3], const float b[3])
+{
+    return memcmp (a, b, 3*sizeof (float)) == 0;     /* vox_dot_equalp, voxvision.h.in */
+}
+
+/* geom.c:44-51 */
+static inline int subspace (const float center[3], const float dot[3])
+{
+    return (center[0] > dot[0]) | ((center[1] > dot[1]) << 1) | ((center[2] > dot[2]) << 2);
+}
+
+/* geom.c:5-11: min <= dot < max */
+static inline int in_box (const struct enode *n, const float dot[3])
+{
+    for (int i=0; i<3; i++) if (dot[i] < n->bb_min[i] || dot[i] >= n->bb_max[i]) return 0;
+    return 1;
+}
+
+/* tree.c:197-208 update_bounding_box: grow the box so that it holds the voxel at `dot` */
+static void grow_box (float mn[3], float mx[3], const float dot[3], const float voxel[3])
+{
+    for (int i=0; i<3; i++)
+    {
+        float top = dot[i] + voxel[i];
+        mn[i] = (dot[i] < mn[i]) ? dot[i] : mn[i];
+        mx[i] = (top > mx[i]) ? top : mx[i];
+    }
+}
+
+/* geom.c:157-167 */
+static int dense_box (const float mn[3], const float mx[3], size_t n, const float voxel[3])
+{
+    float bbvol = (mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]);
+    float vvol = voxel[0] * voxel[1] * voxel[2];
+    return fabsf (n*vvol - bbvol) < vvol;
+}
+
+/* geom.c:192-196 */
+static void box_dims (const float mn[3], const float mx[3], const float voxel[3], size_t dim[3])
+{
+    for (int i=0; i<3; i++) dim[i] = (size_t) ((mx[i] - mn[i]) / voxel[i]);
+}
+
+/* tree.c:229-240 */
+static struct enode* dense_leaf (const float mn[3], const float mx[3], const float voxel[3])
+{
+    struct enode *n = enode_new (VOX_DENSE_LEAF);
+    size_t dim[3];
+    memcpy (n->bb_min, mn, sizeof n->bb_min);
+    memcpy (n->bb_max, mx, sizeof n->bb_max);
+    box_dims (mn, mx, voxel, dim);
+    n->dots_num = (uint32_t) (dim[0]*dim[1]*dim[2]);
+    return n;
+}
+
+/* geom.c:169-182: the octant `idx` of the box around `center`; 0 if it is flat.
+   The result box is only meaningful when 1 is returned. */
+static int octant (const struct enode *box, const float center[3], int idx, float mn[3], float mx[3])
+{
+    memcpy (mn, box->bb_min, 3*sizeof (float));
+    memcpy (mx, box->bb_max, 3*sizeof (float));
+    for (int i=0; i<3; i++)
+    {
+        if (idx & (1<<i)) mx[i] = center[i];
+        else mn[i] = center[i];
+        if (mn[i] == mx[i]) return 0;
+    }
+    return 1;
+}
+
+/* geom.c:199-210: exactly two unit dimensions; *axis = the long one */
+static int is_stripe (const struct enode *n, const float voxel[3], int *axis)
+{
+    size_t dim[3];
+    int count = 0;
+    box_dims (n->bb_min, n->bb_max, voxel, dim);
+    for (int i=0; i<3; i++)
+    {
+        if (dim[i] == 1) count++;
+        else *axis = i;
+    }
+    return count == 2;
+}
+
+/* Voxels of a subtree in the reference's order (flatten_tree, tree.c:366-422): children 0..7 depth-first,
+   leaf dots as stored, a dense box x-outer / z-inner by repeated addition. */
+static size_t collect (const struct enode *n, const float voxel[3], vox_dot *out)
+{
+    if (!n) return 0;
+    if (n->flags & VOX_LEAF)
+    {
+        for (uint32_t i=0; i<n->dots_num; i++) vox_dot_set (out[i], n->dots[i][0], n->dots[i][1], n->dots[i][2]);
+        return n->dots_num;
+    }
+    if (n->flags & VOX_DENSE_LEAF)
+    {
+        size_t dim[3], count = 0;
+        box_dims (n->bb_min, n->bb_max, voxel, dim);
+        float cur[3];
+        cur[0] = n->bb_min[0];
+        for (size_t i=0; i<dim[0]; i++)
+        {
+            cur[1] = n->bb_min[1];
+            for (size_t j=0; j<dim[1]; j++)
+            {
+                cur[2] = n->bb_min[2];
+                for (size_t k=0; k<dim[2]; k++)
+                {
+                    vox_dot_set (out[count], cur[0], cur[1], cur[2]);
+                    cur[2] += voxel[2];
+                    count++;
+                }
+                cur[1] += voxel[1];
+            }
+            cur[0] += voxel[0];
+        }
+        return count;
+    }
+    size_t count = 0;
+    for (int i=0; i<VOX_NS; i++) count += collect (n->child[i], voxel, out + count);
+    return count;
+}
+
+/* ------------------------------------------- builder output -> linked form */
+
+static struct enode* from_pool (struct pool *pool, uint32_t idx, const vox_dot *set)
+{
+    const struct bnode *b = pool_at (pool, idx);
+    struct enode *n = enode_new (b->flags);
+    memcpy (n->bb_min, b->bb_min, sizeof n->bb_min);
+    memcpy (n->bb_max, b->bb_max, sizeof n->bb_max);
+    n->dots_num = b->dots_num;
+    if (b->flags & VOX_DENSE_LEAF) return n;
+    if (b->flags & VOX_LEAF)
+    {
+        uint32_t cap = b->dots_num > VOX_MAX_DOTS ? b->dots_num : VOX_MAX_DOTS;
+        n->dots = malloc (cap * sizeof *n->dots);
+        for (uint32_t k=0; k<b->dots_num; k++) memcpy (n->dots[k], set[b->set_off + k], 3*sizeof (float));
+        return n;
+    }
+    memcpy (n->center, b->center, sizeof n->center);
+    for (int s=0; s<VOX_NS; s++)
+        if (b->child[s] != NO_NODE) n->child[s] = from_pool (pool, b->child[s], set);
+    return n;
+}
+
+/* vox_make_tree (tree.c:249-338) of a handful of voxels, as a linked subtree. */
+static struct enode* subtree_of (vox_dot *set, size_t n, const float voxel[3])
+{
+    if (!n) return NULL;
+    struct pool *pool = calloc (1, sizeof *pool);
+    uint32_t root = vox_build (pool, set, 0, n, voxel);
+    struct enode *res = (root != NO_NODE && !pool->failed) ? from_pool (pool, root, (const vox_dot*) set) : NULL;
+    vox_pool_free (pool);
+    return res;
+}
+
+/* flat arrays -> linked form (first edit of a tree) */
+static struct vox_edit* edit_from_store (const struct vox_tree_store *st)
+{
+    struct vox_edit *e = calloc (1, sizeof *e);
+    struct enode **byid = malloc (st->n_nodes * sizeof *byid);
+    memcpy (e->voxel, st->voxel, sizeof e->voxel);
+    for (uint64_t id=0; id<st->n_nodes; id++)
+    {
+        struct enode *n = byid[id] = enode_new (st->flags[id]);
+        memcpy (n->bb_min, st->bb_min + 3*id, sizeof n->bb_min);
+        memcpy (n->bb_max, st->bb_max + 3*id, sizeof n->bb_max);
+        n->dots_num = st->dots_num[id];
+        if (n->flags & VOX_DENSE_LEAF) continue;
+        if (n->flags & VOX_LEAF)
+        {
+            uint32_t cap = n->dots_num > VOX_MAX_DOTS ? n->dots_num : VOX_MAX_DOTS;
+            n->dots = malloc (cap * sizeof *n->dots);
+            memcpy (n->dots, st->dots + 3*st->dots_off[id], (size_t) n->dots_num * 3 * sizeof (float));
+        }
+        else memcpy (n->center, st->center + 3*id, sizeof n->center);
+    }
+    for (uint64_t id=0; id<st->n_nodes; id++)
+    {
+        if (st->flags[id] & VOX_LEAF_MASK) continue;
+        uint32_t mask = st->child_mask[id], next = st->first_child[id];
+        for (int s=0; s<VOX_NS; s++) if (mask & (1u << s)) byid[id]->child[s] = byid[next++];
+    }
+    e->root = byid[0];
+    free (byid);
+    return e;
+}
+
+/* ------------------------------------------------ linked form -> flat arrays */
+
+static void count_tree (const struct enode *n, uint64_t *nodes, uint64_t *dots)
+{
+    if (!n) return;
+    (*nodes)++;
+    if (n->flags & VOX_DENSE_LEAF) return;
+    if (n->flags & VOX_LEAF) { *dots += n->dots_num; return; }
+    for (int i=0; i<VOX_NS; i++) count_tree (n->child[i], nodes, dots);
+}
+
+static int grow (void **p, size_t bytes)
+{
+    void *q = realloc (*p, bytes);
+    if (!q) return 0;
+    *p = q;
+    return 1;
+}
+
+int vox_store_sync (struct vox_tree_store *st)
+{
+    if (!st->dirty) return 1;
+    pthread_mutex_lock (&st->lock);
+    if (!st->dirty) { pthread_mutex_unlock (&st->lock); return 1; }
+
+    uint64_t n_nodes = 0, n_dots = 0;
+    count_tree (st->edit->root, &n_nodes, &n_dots);
+    if (st->handles) for (uint64_t i=1; i<st->n_nodes; i++) st->handles[i].magic = 0;   /* old handles die */
+    if (n_nodes > st->cap_nodes)
+    {
+        uint64_t cap = n_nodes + n_nodes/8 + 64;
+        if (!grow ((void**) &st->bb_min, cap*3*sizeof (float)) || !grow ((void**) &st->bb_max, cap*3*sizeof (float)) ||
+            !grow ((void**) &st->center, cap*3*sizeof (float)) || !grow ((void**) &st->flags, cap*sizeof (uint32_t)) ||
+            !grow ((void**) &st->dots_num, cap*sizeof (uint32_t)) || !grow ((void**) &st->first_child, cap*sizeof (uint32_t)) ||
+            !grow ((void**) &st->child_mask, cap*sizeof (uint32_t)) || !grow ((void**) &st->dots_off, cap*sizeof (uint64_t)) ||
+            !grow ((void**) &st->handles, cap*sizeof (struct vox_node)))
+        { pthread_mutex_unlock (&st->lock); vox_set_error ("out of memory refreshing an edited tree"); return 0; }
+        st->cap_nodes = cap;
+    }
+    if (n_dots > st->cap_dots)
+    {
+        uint64_t cap = n_dots + n_dots/8 + 64;
+        if (!grow ((void**) &st->dots, cap*3*sizeof (float)))
+        { pthread_mutex_unlock (&st->lock); vox_set_error ("out of memory refreshing an edited tree"); return 0; }
+        st->cap_dots = cap;
+    }
+
+    /* breadth-first numbering, children consecutive in subspace order (as flatten_pool, tree.c) */
+    const struct enode **order = malloc (n_nodes * sizeof *order);
+    uint64_t head = 0, tail = 0, dots = 0;
+    order[tail++] = st->edit->root;
+    while (head < tail)
+    {
+        const struct enode *n = order[head];
+        uint64_t id = head++;
+        memcpy (st->bb_min + 3*id, n->bb_min, 3*sizeof (float));
+        memcpy (st->bb_max + 3*id, n->bb_max, 3*sizeof (float));
+        memset (st->center + 3*id, 0, 3*sizeof (float));
+        st->flags[id] = n->flags;
+        st->dots_num[id] = n->dots_num;
+        st->dots_off[id] = dots;
+        st->first_child[id] = 0;
+        st->child_mask[id] = 0;
+        if (n->flags & VOX_DENSE_LEAF) {}
+        else if (n->flags & VOX_LEAF)
+        {
+            memcpy (st->dots + 3*dots, n->dots, (size_t) n->dots_num * 3 * sizeof (float));
+            dots += n->dots_num;
+        }
+        else
+        {
+            uint32_t mask = 0;
+            memcpy (st->center + 3*id, n->center, 3*sizeof (float));
+            st->first_child[id] = (uint32_t) tail;
+            for (int s=0; s<VOX_NS; s++) if (n->child[s]) { mask |= 1u << s; order[tail++] = n->child[s]; }
+            st->child_mask[id] = mask;
+        }
+    }
+    free (order);
+    st->n_nodes = n_nodes; st->n_dots = n_dots;
+    vox_store_finish (st);
+
+    /* the device copies describe the tree before the edits */
+    for (int d=0; d<VOX_MAX_DEVICES; d++)
+        if (st->dev[d]) { voxgpu_tree_free (st->dev[d]); st->dev[d] = NULL; }
+    st->dirty = 0;
+    pthread_mutex_unlock (&st->lock);
+    return 1;
+}
+
+/* ------------------------------------------------------------- membership */
+
+/* voxel_in_tree, tree.c:437-458 */
+static int contains (const struct enode *n, const float v[3])
+{
+    while (n && in_box (n, v))
+    {
+        if (n->flags & VOX_DENSE_LEAF) return 1;
+        if (n->flags & VOX_LEAF)
+        {
+            for (uint32_t i=0; i<n->dots_num; i++) if (same_dot (v, n->dots[i])) return 1;
+            return 0;
+        }
+        n = n->child[subspace (n->center, v)];
+    }
+    return 0;
+}
+
+/* -------------------------------------------------------------- insertion */
+
+static struct enode* insert (struct enode *t, const float v[3], const float voxel[3]);
+
+/* insert_in_big_dense, tree.c:461-503: a solid box and one voxel outside it become the two children of a new node
+   split at the box vertex nearest to the voxel */
+static struct enode* wrap_dense (struct enode *t, const float v[3], const float voxel[3])
+{
+    struct enode *node = enode_new (0);
+    memcpy (node->bb_min, t->bb_min, sizeof node->bb_min);
+    memcpy (node->bb_max, t->bb_max, sizeof node->bb_max);
+    grow_box (node->bb_min, node->bb_max, v, voxel);
+    node->dots_num = t->dots_num + 1;
+    float mid[3];
+    for (int i=0; i<3; i++)
+    {
+        /* geom.c:33-42 closest_vertex */
+        float d1 = fabsf (t->bb_min[i] - v[i]);
+        float d2 = fabsf (t->bb_max[i] - v[i]);
+        node->center[i] = (d1 < d2) ? t->bb_min[i] : t->bb_max[i];
+        mid[i] = (t->bb_min[i] + t->bb_max[i]) / 2;
+    }
+    int at_box = subspace (node->center, mid), at_voxel = subspace (node->center, v);
+    node->child[at_box] = t;
+    node->child[at_voxel] = insert (node->child[at_voxel], v, voxel);
+    return node;
+}
+
+/* vox_insert_voxel_, tree.c:506-611; the voxel is known to be absent.  Returns what takes t's place. */
+static struct enode* insert (struct enode *t, const float v[3], const float voxel[3])
+{
+    if (!t)
+    {
+        vox_dot one;
+        vox_dot_set (one, v[0], v[1], v[2]);
+        return subtree_of (&one, 1, voxel);
+    }
+
+    /* does the voxel complete a solid box? (tree.c:522-538) */
+    float old_min[3], old_max[3];
+    memcpy (old_min, t->bb_min, sizeof old_min);
+    memcpy (old_max, t->bb_max, sizeof old_max);
+    grow_box (t->bb_min, t->bb_max, v, voxel);
+    if (dense_box (t->bb_min, t->bb_max, (size_t) t->dots_num + 1, voxel))
+    {
+        if (t->flags & VOX_DENSE_LEAF) { t->dots_num++; return t; }
+        struct enode *solid = dense_leaf (t->bb_min, t->bb_max, voxel);
+        enode_free_tree (t);
+        return solid;
+    }
+    if (t->flags & VOX_DENSE_LEAF)
+    {
+        /* a solid box keeps its exact extent */
+        memcpy (t->bb_min, old_min, sizeof old_min);
+        memcpy (t->bb_max, old_max, sizeof old_max);
+        if (t->dots_num >= VOX_MAX_DOTS) return wrap_dense (t, v, voxel);
+        /* small: turn it into an ordinary leaf (tree.c:556-568) */
+        vox_dot set[VOX_MAX_DOTS + 1];
+        size_t n = collect (t, voxel, set);
+        vox_dot_set (set[n], v[0], v[1], v[2]);
+        struct enode *node = subtree_of (set, n + 1, voxel);
+        enode_free_tree (t);
+        return node;
+    }
+    if (t->flags & VOX_LEAF)
+    {
+        if (t->dots_num < VOX_MAX_DOTS)
+        {
+            memcpy (t->dots[t->dots_num], v, 3*sizeof (float));
+            t->dots_num++;
+            return t;
+        }
+        /* full (tree.c:581-590; an overflowed leaf, which the reference only asserts against,
+           is re-split together with the new voxel) */
+        size_t n = t->dots_num;
+        vox_dot *set = malloc ((n + 1) * sizeof (vox_dot));
+        collect (t, voxel, set);
+        vox_dot_set (set[n], v[0], v[1], v[2]);
+        struct enode *node = subtree_of (set, n + 1, voxel);
+        free (set);
+        enode_free_tree (t);
+        return node;
+    }
+    /* inner node: count and descend (tree.c:593-607) */
+    int idx = subspace (t->center, v);
+    t->dots_num++;
+    t->child[idx] = insert (t->child[idx], v, voxel);
+    return t;
+}
+
+/* --------------------------------------------------------------- deletion */
+
+/* delete_from_dense_stripe, tree.c:641-693: a stripe loses an end voxel by shrinking, an inner voxel by splitting in two.
+   NULL if t is not a stripe. */
+static struct enode* cut_stripe (struct enode *t, const float v[3], const float voxel[3])
+{
+    int axis = 0;
+    if (!is_stripe (t, voxel, &axis)) return NULL;
+    if (same_dot (t->bb_min, v))
+    {
+        t->dots_num--;
+        t->bb_min[axis] += voxel[axis];
+        return t;
+    }
+    float far_corner[3] = { v[0] + voxel[0], v[1] + voxel[1], v[2] + voxel[2] };
+    if (same_dot (t->bb_max, far_corner))
+    {
+        t->dots_num--;
+        t->bb_max[axis] -= voxel[axis];
+        return t;
+    }
+    struct enode *node = enode_new (0);
+    memcpy (node->bb_min, t->bb_min, sizeof node->bb_min);
+    memcpy (node->bb_max, t->bb_max, sizeof node->bb_max);
+    node->dots_num = t->dots_num - 1;
+    memcpy (node->center, v, sizeof node->center);
+    float mn[3], mx[3];
+    octant (t, v, 1 << axis, mn, mx);
+    node->child[1 << axis] = dense_leaf (mn, mx, voxel);
+    octant (t, v, 0, mn, mx);
+    struct enode *upper = node->child[0] = dense_leaf (mn, mx, voxel);
+    upper->dots_num--;
+    upper->bb_min[axis] += voxel[axis];
+    enode_free_tree (t);
+    return node;
+}
+
+/* delete_from_big_dense, tree.c:695-756: split a solid box around the voxel into up to 8 solid boxes; the octant that
+   starts AT the voxel then loses its min-corner voxel by the same routine. */
+static struct enode* cut_dense (struct enode *t, const float v[3], const float voxel[3])
+{
+    struct enode *node = cut_stripe (t, v, voxel);
+    if (node) return node;
+
+    float mn[3], mx[3];
+    node = enode_new (0);
+    memcpy (node->bb_min, t->bb_min, sizeof node->bb_min);
+    memcpy (node->bb_max, t->bb_max, sizeof node->bb_max);
+    node->dots_num = t->dots_num - 1;
+    if (same_dot (t->bb_min, v))
+    {
+        /* min-corner voxel: split at its far corner, octant 7 (the voxel itself) stays empty */
+        for (int i=0; i<3; i++) node->center[i] = v[i] + voxel[i];
+        for (int i=0; i<VOX_NS-1; i++)
+            if (octant (t, node->center, i, mn, mx)) node->child[i] = dense_leaf (mn, mx, voxel);
+        enode_free_tree (t);
+        return node;
+    }
+    memcpy (node->center, v, sizeof node->center);
+    for (int i=0; i<VOX_NS; i++)
+        if (octant (t, v, i, mn, mx)) node->child[i] = dense_leaf (mn, mx, voxel);
+    node->child[0] = cut_dense (node->child[0], v, voxel);
+    enode_free_tree (t);
+    return node;
+}
+
+/* vox_delete_voxel_, tree.c:759-845; the voxel is known to be present.  Returns what takes t's place. */
+static struct enode* delete (struct enode *t, const float v[3], const float voxel[3])
+{
+    if (t->dots_num == 1) { enode_free_tree (t); return NULL; }
+    if (t->flags & VOX_LEAF)
+    {
+        /* the bounding box is left as it is (tree.c:772) */
+        uint32_t i = 0;
+        while (i < t->dots_num && !same_dot (t->dots[i], v)) i++;
+        if (i == t->dots_num) return t;
+        t->dots_num--;
+        memmove (t->dots + i, t->dots + i + 1, (size_t) (t->dots_num - i) * sizeof *t->dots);
+        return t;
+    }
+    if (t->flags & VOX_DENSE_LEAF)
+    {
+        if (t->dots_num > VOX_MAX_DOTS) return cut_dense (t, v, voxel);
+        struct enode *node = cut_stripe (t, v, voxel);
+        if (node) return node;
+        vox_dot set[VOX_MAX_DOTS];
+        size_t n = collect (t, voxel, set), i = 0;
+        while (i < n && !same_dot (set[i], v)) i++;
+        if (i < n) { memmove (set + i, set + i + 1, (n - i - 1) * sizeof (vox_dot)); n--; }
+        node = subtree_of (set, n, voxel);
+        enode_free_tree (t);
+        return node;
+    }
+    int idx = subspace (t->center, v);
+    struct enode *child = t->child[idx];
+    if (!child) return t;    /* unreachable for a voxel `contains` found */
+    if (child->dots_num == t->dots_num)
+    {
+        /* an only child takes its parent's place (tree.c:828-839) */
+        free (t);
+        return delete (child, v, voxel);
+    }
+    t->dots_num--;
+    t->child[idx] = delete (child, v, voxel);
+    return t;
+}
+
+/* ------------------------------------------------------------------- API */
+
+/* vox_align, tree.c:185-195 */
+static void align_voxel (vox_dot dot)
+{
+    for (int i=0; i<3; i++) dot[i] = vox_voxel[i] * floorf (dot[i] / vox_voxel[i]);
+}
+
+static struct vox_tree_store* editable (struct vox_node **tree_ptr, const char *who)
+{
+    struct vox_node *tree = *tree_ptr;
+    if (!vox_node_valid (tree) || tree->id != 0)
+    { vox_set_error ("%s: not the root of a live tree", who); return NULL; }
+    struct vox_tree_store *st = tree->store;
+    if (!st->edit) st->edit = edit_from_store (st);
+    return st;
+}
+
+int vox_insert_voxel (struct vox_node **tree_ptr, vox_dot voxel)
+{
+    align_voxel (voxel);
+    if (!*tree_ptr)
+    {
+        /* an empty tree: the new voxel is the whole tree (tree.c:540-551) */
+        vox_dot one;
+        vox_dot_copy (one, voxel);
+        *tree_ptr = vox_make_tree (&one, 1);
+        return *tree_ptr != NULL;
+    }
+    struct vox_tree_store *st = editable (tree_ptr, "vox_insert_voxel");
+    if (!st) return 0;
+    pthread_mutex_lock (&st->lock);
+    int absent = !contains (st->edit->root, voxel);
+    if (absent)
+    {
+        st->edit->root = insert (st->edit->root, voxel, st->edit->voxel);
+        st->dirty = 1;
+    }
+    pthread_mutex_unlock (&st->lock);
+    return absent;
+}
+
+int vox_insert_voxel_coord (struct vox_node **tree_ptr, float x, float y, float z)
+{
+    vox_dot dot;
+    vox_dot_set (dot, x, y, z);
+    return vox_insert_voxel (tree_ptr, dot);
+}
+
+int vox_delete_voxel (struct vox_node **tree_ptr, vox_dot voxel)
+{
+    align_voxel (voxel);
+    if (!*tree_ptr) return 0;
+    struct vox_tree_store *st = editable (tree_ptr, "vox_delete_voxel");
+    if (!st) return 0;
+    pthread_mutex_lock (&st->lock);
+    int present = contains (st->edit->root, voxel);
+    if (present)
+    {
+        st->edit->root = delete (st->edit->root, voxel, st->edit->voxel);
+        st->dirty = 1;
+    }
+    int emptied = present && !st->edit->root;
+    pthread_mutex_unlock (&st->lock);
+    if (emptied)
+    {
+        /* the last voxel went: the tree is the NULL tree again (tree.c:765-770) */
+        st->dirty = 0;
+        vox_store_free (st);
+        *tree_ptr = NULL;
+    }
+    return present;
+}
+
+int vox_delete_voxel_coord (struct vox_node **tree_ptr, float x, float y, float z)
+{
+    vox_dot dot;
+    vox_dot_set (dot, x, y, z);
+    return vox_delete_voxel (tree_ptr, dot);
+}
+
+struct vox_node* vox_rebuild_tree (const struct vox_node *tree)
+{
+    /* tree.c:424-435: list the voxels in tree order, build anew; the old tree stays valid */
+    if (!tree) return NULL;
+    if (!vox_node_valid (tree)) { vox_set_error ("vox_rebuild_tree: not a live tree"); return NULL; }
+    if (tree->id != 0) { vox_set_error ("vox_rebuild_tree: pass the root"); return NULL; }
+    struct vox_tree_store *st = tree->store;
+    struct vox_edit *e = st->edit, *tmp = NULL;
+    if (!e) e = tmp = edit_from_store (st);
+    size_t n = e->root ? e->root->dots_num : 0;
+    vox_dot *set = vox_alloc (sizeof (vox_dot) * (n ? n : 1));
+    struct vox_node *res = NULL;
+    if (set)
+    {
+        size_t got = collect (e->root, e->voxel, set);
+        res = vox_make_tree (set, got);
+        free (set);
+    }
+    vox_edit_free (tmp);
+    return res;
+}

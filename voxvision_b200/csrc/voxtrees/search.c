@@ -67,7 +67,7 @@ vox_ray_tree_intersection (const struct vox_node *tree, const vox_dot origin,
     }
     if (leaf < 0) return NULL;
     res[0] = p[0]; res[1] = p[1]; res[2] = p[2];
-    return &tree->store->handles[leaf];
+    return vox_store_handle (tree->store, (uint64_t) leaf);
 }
 
 int vox_tree_ball_collidep (const struct vox_node *tree, const vox_dot center, float radius)

@@ -44,7 +44,14 @@ struct vox_tree_store
     uint32_t *flags, *dots_num, *first_child, *child_mask;
     uint64_t *dots_off;
 
-    struct vox_node *handles;
+    struct vox_node root;                        /* handle of node 0: its address never changes */
+    struct vox_node *handles;                    /* handles of nodes 1.. (entry 0 unused); replaced by edits */
+    uint64_t cap_nodes, cap_dots;                /* allocated entries of the arrays above */
+
+    /* online edits (edit.c): a linked, mutable mirror of the tree; the flat arrays and the
+       device copies are refreshed from it on the next use when `dirty` is set */
+    struct vox_edit *edit;
+    int dirty;
 
     pthread_mutex_t lock;
     voxgpu_tree *dev[VOX_MAX_DEVICES];           /* device copies, by CUDA ordinal */
@@ -57,6 +64,13 @@ struct vox_tree_store* vox_store_alloc (uint64_t n_nodes, uint64_t n_dots);
 void vox_store_finish (struct vox_tree_store *st);   /* handles + statistics */
 void vox_store_free (struct vox_tree_store *st);
 int vox_node_valid (const struct vox_node *node);
+static inline struct vox_node* vox_store_handle (struct vox_tree_store *st, uint64_t id)
+{
+    return id ? &st->handles[id] : &st->root;
+}
+/* edit.c */
+void vox_edit_free (struct vox_edit *e);
+int vox_store_sync (struct vox_tree_store *st);      /* flat arrays <- edited tree, if dirty; 0 on failure */
 voxgpu_tree* vox_store_device (struct vox_tree_store *st);
 
 #endif

@@ -42,6 +42,7 @@ struct vox_tree_store* vox_store_alloc (uint64_t n_nodes, uint64_t n_dots)
     if (!st) return NULL;
     size_t nn = n_nodes ? n_nodes : 1, nd = n_dots ? n_dots : 1;
     st->n_nodes = n_nodes; st->n_dots = n_dots;
+    st->cap_nodes = nn; st->cap_dots = nd;
     st->bb_min = malloc (nn * 3 * sizeof (float));
     st->bb_max = malloc (nn * 3 * sizeof (float));
     st->center = calloc (nn * 3, sizeof (float));
@@ -73,9 +74,10 @@ void vox_store_finish (struct vox_tree_store *st)
     if (st->n_nodes) level[0] = 1;
     for (uint64_t id=0; id<st->n_nodes; id++)
     {
-        st->handles[id].store = st;
-        st->handles[id].id = (uint32_t) id;
-        st->handles[id].magic = VOX_NODE_MAGIC;
+        struct vox_node *hd = vox_store_handle (st, id);
+        hd->store = st;
+        hd->id = (uint32_t) id;
+        hd->magic = VOX_NODE_MAGIC;
         if (level[id] > st->depth) st->depth = level[id];
         uint32_t fl = st->flags[id];
         if (fl & VOX_DENSE_LEAF) st->n_dense++;
@@ -97,41 +99,28 @@ void vox_store_free (struct vox_tree_store *st)
     free (st->bb_min); free (st->bb_max); free (st->center); free (st->dots);
     free (st->flags); free (st->dots_num); free (st->first_child); free (st->child_mask);
     free (st->dots_off);
-    if (st->handles) for (uint64_t i=0; i<st->n_nodes; i++) st->handles[i].magic = 0;
+    if (st->handles) for (uint64_t i=1; i<st->n_nodes; i++) st->handles[i].magic = 0;
+    st->root.magic = 0;
     free (st->handles);
+    vox_edit_free (st->edit);
     pthread_mutex_destroy (&st->lock);
     free (st);
 }
 
 int vox_node_valid (const struct vox_node *node)
 {
-    return node && node->magic == VOX_NODE_MAGIC && node->store && node->id < node->store->n_nodes;
+    if (!node || node->magic != VOX_NODE_MAGIC || !node->store) return 0;
+    /* every public entry point passes through here: bring the flat arrays (and, by dropping
+       them, the device copies) up to date with pending edits first (edit.c) */
+    if (node->store->dirty && !vox_store_sync (node->store)) return 0;
+    return node->id < node->store->n_nodes;
 }
 
 /* ---------------------------------------------------------------- builder */
 
-/* A node as the recursion produces it, before breadth-first numbering. */
-struct bnode
-{
-    float bb_min[3], bb_max[3], center[3];
-    uint32_t flags, dots_num;
-    uint32_t child[VOX_NS];     /* pool index or NO_NODE */
-    size_t set_off;             /* leaves: where the dots sit in the reordered set */
-};
-#define NO_NODE 0xffffffffu
+#include "build.h"
 
-/* Chunked, append-only pool shared by the builder tasks. */
-#define POOL_SHIFT 16
-#define POOL_CHUNK (1u << POOL_SHIFT)
-#define POOL_MAX_CHUNKS (1u << (31 - POOL_SHIFT))
-struct pool
-{
-    struct bnode *chunk[POOL_MAX_CHUNKS];
-    uint32_t used;
-    int failed;
-};
-
-static uint32_t pool_new (struct pool *p)
+uint32_t vox_pool_new (struct pool *p)
 {
     uint32_t idx;
 #pragma omp atomic capture
@@ -158,10 +147,6 @@ static uint32_t pool_new (struct pool *p)
     return idx;
 }
 
-static inline struct bnode* pool_at (struct pool *p, uint32_t idx)
-{
-    return &p->chunk[idx >> POOL_SHIFT][idx & (POOL_CHUNK - 1)];
-}
 
 static inline void swap_dots (vox_dot a, vox_dot b)
 {
@@ -173,10 +158,10 @@ static inline void swap_dots (vox_dot a, vox_dot b)
 
 #define TASK_MIN_DOTS 32768
 
-static uint32_t build (struct pool *pool, vox_dot *base, size_t off, size_t n, const float voxel[3])
+uint32_t vox_build (struct pool *pool, vox_dot *base, size_t off, size_t n, const float voxel[3])
 {
     vox_dot *set = base + off;
-    uint32_t self = pool_new (pool);
+    uint32_t self = vox_pool_new (pool);
     if (self == NO_NODE) return NO_NODE;
     struct bnode *node = pool_at (pool, self);
     memset (node, 0, sizeof *node);
@@ -276,20 +261,27 @@ static uint32_t build (struct pool *pool, vox_dot *base, size_t off, size_t n, c
         {
 #pragma omp task default(none) firstprivate(pool, base, off, c_off, c_n, voxel, self, idx)
             {
-                uint32_t ch = build (pool, base, off + c_off, c_n, voxel);
+                uint32_t ch = vox_build (pool, base, off + c_off, c_n, voxel);
                 pool_at (pool, self)->child[idx] = ch;
                 if (ch == NO_NODE) pool->failed = 1;
             }
         }
         else
         {
-            uint32_t ch = build (pool, base, off + c_off, c_n, voxel);
+            uint32_t ch = vox_build (pool, base, off + c_off, c_n, voxel);
             pool_at (pool, self)->child[idx] = ch;
             if (ch == NO_NODE) pool->failed = 1;
         }
     }
 #pragma omp taskwait
     return self;
+}
+
+void vox_pool_free (struct pool *pool)
+{
+    if (!pool) return;
+    for (uint32_t c=0; c<POOL_MAX_CHUNKS; c++) free (pool->chunk[c]);
+    free (pool);
 }
 
 /* Breadth-first numbering of the pool into a store. */
@@ -349,14 +341,13 @@ struct vox_node* vox_make_tree (vox_dot set[], size_t n)
     uint32_t root = NO_NODE;
 #pragma omp parallel default(none) shared(pool, set, n, voxel, root)
 #pragma omp single nowait
-    root = build (pool, set, 0, n, voxel);
+    root = vox_build (pool, set, 0, n, voxel);
 
     struct vox_tree_store *st = NULL;
     if (root != NO_NODE && !pool->failed) st = flatten_pool (pool, root, (const vox_dot*) set);
     else vox_set_error ("vox_make_tree: out of memory while building");
-    for (uint32_t c=0; c<POOL_MAX_CHUNKS; c++) free (pool->chunk[c]);
-    free (pool);
-    return st ? &st->handles[0] : NULL;
+    vox_pool_free (pool);
+    return st ? &st->root : NULL;
 }
 
 struct vox_node* vox_make_dense_leaf (const struct vox_box *box)
@@ -374,7 +365,7 @@ struct vox_node* vox_make_dense_leaf (const struct vox_box *box)
     st->flags[0] = VOX_DENSE_LEAF;
     st->dots_num[0] = (uint32_t) (dim[0]*dim[1]*dim[2]);
     vox_store_finish (st);
-    return &st->handles[0];
+    return &st->root;
 }
 
 void vox_destroy_tree (struct vox_node *tree)
@@ -398,6 +389,47 @@ void vox_bounding_box (const struct vox_node *tree, struct vox_box *box)
     const struct vox_tree_store *st = tree->store;
     vox_dot_set (box->min, st->bb_min[3*tree->id], st->bb_min[3*tree->id+1], st->bb_min[3*tree->id+2]);
     vox_dot_set (box->max, st->bb_max[3*tree->id], st->bb_max[3*tree->id+1], st->bb_max[3*tree->id+2]);
+}
+
+void vox_dump_tree (const struct vox_node *tree)
+{
+    /* tree.c:868-918: debugging aid; ids are breadth-first positions instead of addresses */
+    if (!vox_node_valid (tree)) return;
+    const struct vox_tree_store *st = tree->store;
+    uint64_t id = tree->id;
+    uint32_t fl = st->flags[id];
+    const char *kind = (fl & VOX_LEAF) ? "LEAF" : (fl & VOX_DENSE_LEAF) ? "DENSE LEAF" : "INNER";
+    printf ("Node %llu %s\n", (unsigned long long) id, kind);
+    printf ("Bounding box min <%f, %f, %f>\n", st->bb_min[3*id], st->bb_min[3*id+1], st->bb_min[3*id+2]);
+    printf ("Bounding box max <%f, %f, %f>\n", st->bb_max[3*id], st->bb_max[3*id+1], st->bb_max[3*id+2]);
+    printf ("Number of voxels %u\n", st->dots_num[id]);
+    if (fl & VOX_LEAF)
+    {
+        printf ("Dots:\n");
+        for (uint32_t i=0; i<st->dots_num[id]; i++)
+        {
+            const float *d = st->dots + 3*(st->dots_off[id] + i);
+            printf ("<%f, %f, %f>\n", d[0], d[1], d[2]);
+        }
+    }
+    else if (!(fl & VOX_LEAF_MASK))
+    {
+        printf ("Center <%f, %f, %f>\n", st->center[3*id], st->center[3*id+1], st->center[3*id+2]);
+        printf ("Children:\n");
+        uint32_t next = st->first_child[id];
+        for (int s=0; s<VOX_NS; s++)
+        {
+            if (st->child_mask[id] & (1u << s)) printf ("%u\n", next++);
+            else printf ("(nil)\n");
+        }
+    }
+    printf ("------Node ends here------\n");
+    if (!(fl & VOX_LEAF_MASK))
+    {
+        int nc = __builtin_popcount (st->child_mask[id]);
+        for (int j=0; j<nc; j++) vox_dump_tree (vox_store_handle ((struct vox_tree_store*) st, st->first_child[id] + j));
+        printf ("=======Node and children end here=======\n");
+    }
 }
 
 /* ------------------------------------------------- inspection and import */
@@ -462,11 +494,11 @@ struct vox_node* vox_tree_import (const struct vox_tree_arrays *in, uint64_t n_n
     memcpy (st->dots_off, in->dots_off, n_nodes*sizeof (uint64_t));
     memcpy (st->dots, in->dots, n_dots*3*sizeof (float));
     vox_store_finish (st);
-    return &st->handles[0];
+    return &st->root;
 }
 
 const struct vox_node* vox_tree_node (const struct vox_node *tree, uint32_t id)
 {
     if (!vox_node_valid (tree) || id >= tree->store->n_nodes) return NULL;
-    return &tree->store->handles[id];
+    return vox_store_handle (tree->store, id);
 }
