@@ -80,6 +80,23 @@ typedef struct
     uint8_t rshift, gshift, bshift, pad1;
 } voxgpu_pixfmt;
 
+/** Shadowless lights (reference: src/voxrnd/lights.c:91-116 over the M-tree of
+    src/voxtrees/mtree.c), flattened by the host: M-tree nodes in PRE-ORDER, so that walking the
+    array front to back, jumping to `skip` when a node's bounding sphere does not contain the
+    point, visits the spheres in exactly the order of the reference's recursion
+    (mtree.c:463-493) -- the order the fp32 light sum is taken in. */
+typedef struct
+{
+    float ambient[3];
+    uint32_t n_nodes, n_spheres;
+    const float    *node_bounds;   /* 4*n_nodes: bounding sphere centre xyz, squared radius */
+    const uint32_t *node_link;     /* 4*n_nodes: skip (index of the next node outside this subtree),
+                                      leaf flag, first sphere (leaf), number of spheres (leaf) */
+    const float    *sphere_geom;   /* 4*n_spheres: centre xyz, squared radius */
+    const float    *sphere_light;  /* 4*n_spheres: colour rgb, radius */
+} voxgpu_lights_flat;
+typedef struct voxgpu_lights voxgpu_lights;
+
 /** One render request: rows [y0, y1) of a w x h frame. */
 typedef struct
 {
@@ -88,6 +105,7 @@ typedef struct
     int pitch_pixels;            /* distance between rows of `pixels`, in pixels */
     unsigned quality;            /* VOX_QUALITY_* bits, renderer.h:81-127 */
     voxgpu_pixfmt fmt;
+    const voxgpu_lights *lights; /* NULL: unlit grey (renderer.c:38-39); else renderer.c:41-49 */
 } voxgpu_frame;
 
 /** Counters of the instrumented ("stats") variant of the ray kernel. */
@@ -139,6 +157,11 @@ VOXGPU_EXPORT voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *flat);
 VOXGPU_EXPORT void voxgpu_tree_free (voxgpu_tree *tree);
 VOXGPU_EXPORT size_t voxgpu_tree_device_bytes (const voxgpu_tree *tree);
 VOXGPU_EXPORT int voxgpu_tree_device (const voxgpu_tree *tree);
+
+/* ---- lights ---- */
+/** Copy a flattened light set to the current device (one small synchronous upload). */
+VOXGPU_EXPORT voxgpu_lights* voxgpu_lights_upload (const voxgpu_lights_flat *flat);
+VOXGPU_EXPORT void voxgpu_lights_free (voxgpu_lights *lights);
 
 /* ---- batched ray queries (K2) ----
  * origins/dirs: float4 per ray (xyz + unused lane = vox_dot).

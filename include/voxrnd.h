@@ -1,7 +1,7 @@
 /**
    @file voxrnd.h
    @brief Umbrella header of libvoxrnd (reference: src/voxrnd.h:7-14; the
-   fps-control, lights and screenshot parts are out of scope).
+   fps-control and screenshot parts are out of scope).
 **/
 #ifndef VOXRND_H
 #define VOXRND_H
@@ -14,6 +14,7 @@ extern "C" {
 #include "voxrnd/surface.h"
 #include "voxrnd/renderer.h"
 #include "voxrnd/cd.h"
+#include "voxrnd/lights.h"
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@
 #include "../voxtrees/tree.h"
 #include "camera.h"
 
-struct vox_light_manager;   /* lights are out of scope; the field is kept for layout */
+struct vox_light_manager;   /* lights.h */
 
 /**
    \brief A renderer context.  The five leading members are public, exactly as
@@ -21,7 +21,7 @@ struct vox_rnd_ctx
     SDL_Surface *surface;     /**< surface the context draws to */
     struct vox_node *scene;   /**< set with vox_context_set_scene() */
     struct vox_camera *camera;/**< set with vox_context_set_camera() */
-    struct vox_light_manager *light_manager; /**< must stay NULL */
+    struct vox_light_manager *light_manager; /**< set with vox_context_set_light_manager(), may be NULL */
 };
 
 /* Quality bits, renderer.h:81-127 */

@@ -13,6 +13,7 @@ extern "C" {
 #include "voxtrees/geom.h"
 #include "voxtrees/datareader.h"
 #include "voxtrees/batch.h"
+#include "voxtrees/mtree.h"
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,19 @@ typedef struct
     uint8_t rshift, gshift, bshift, pad1;
 } orc_pixfmt;
 
+/* A light manager's lights as flat arrays (the layout the product uploads to the GPU,
+ * include/voxgpu.h voxgpu_lights_flat): M-tree nodes in pre-order. */
+typedef struct
+{
+    float ambient[3];
+    uint32_t n_nodes, n_spheres;
+    float    *node_bounds;   /* 4*n_nodes: bounding centre xyz, squared radius */
+    uint32_t *node_link;     /* 4*n_nodes: skip, leaf flag, first sphere, count */
+    float    *sphere_geom;   /* 4*n_spheres: centre xyz, squared radius */
+    float    *sphere_light;  /* 4*n_spheres: colour rgb, radius */
+} orc_lights_flat;
+typedef struct orc_lights orc_lights;
+
 ORC_EXPORT const char* orc_impl_name (void);  /* "port" or "reference-scalar" ... */
 
 /* Global voxel size (params.h:38, tree.c:11). */
@@ -160,6 +173,27 @@ ORC_EXPORT int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned qu
                            const uint8_t *texture, const orc_pixfmt *fmt,
                            uint32_t *pixels, int32_t *leaf_id, float *hit,
                            int threads);
+
+/* ---- lights (voxrnd/lights.c over voxtrees/mtree.c) ----
+ * orc_lights_new: a light manager driven through the reference's own API -- reference glue only
+ * (mtree.c / lights.c object code), the port returns NULL.  orc_lights_from_flat: a light set
+ * given as flat arrays, evaluated by the restated traversal (both implementations). */
+ORC_EXPORT orc_lights* orc_lights_new (void);
+ORC_EXPORT orc_lights* orc_lights_from_flat (const orc_lights_flat *flat);
+ORC_EXPORT void orc_lights_free (orc_lights *l);
+ORC_EXPORT int orc_lights_insert (orc_lights *l, const float center[3], float radius, const float color[3]);
+ORC_EXPORT int orc_lights_delete (orc_lights *l, const float center[3], float radius);
+ORC_EXPORT void orc_lights_clear (orc_lights *l);
+ORC_EXPORT int orc_lights_count (orc_lights *l);
+ORC_EXPORT int orc_lights_set_ambient (orc_lights *l, const float color[3]);
+/* sizes, then contents (arrays caller-allocated; NULL arrays = sizes + ambient only) */
+ORC_EXPORT void orc_lights_flatten (orc_lights *l, orc_lights_flat *out);
+/* vox_get_light (lights.c:104-116) for n points -> rgb[3n] */
+ORC_EXPORT void orc_lights_get (orc_lights *l, const float *points, size_t n, float *rgb);
+/* orc_render with a light manager attached (renderer.c:41-49) */
+ORC_EXPORT int orc_render_lit (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
+                               const uint8_t *texture, const orc_pixfmt *fmt, orc_lights *lights,
+                               uint32_t *pixels, int threads);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,12 @@ class PixFmt(C.Structure):
                 ("rshift", C.c_uint8), ("gshift", C.c_uint8), ("bshift", C.c_uint8), ("pad1", C.c_uint8)]
 
 
+class LightsFlat(C.Structure):
+    _fields_ = [("ambient", C.c_float * 3), ("n_nodes", C.c_uint32), ("n_spheres", C.c_uint32),
+                ("node_bounds", C.c_void_p), ("node_link", C.c_void_p), ("sphere_geom", C.c_void_p),
+                ("sphere_light", C.c_void_p)]
+
+
 def pixfmt_xrgb8888():
     """SDL_PIXELFORMAT_RGB888 (the usual window-surface format): R<<16 | G<<8 | B."""
     return PixFmt(0, 0, 0, 0, 0, 16, 8, 0, 0)
@@ -114,6 +120,19 @@ class Oracle:
         L.orc_camera_get_state.argtypes = [vp, vp]
         L.orc_camera_rays.argtypes = [vp, i, i, vp, vp]
         L.orc_render.restype = i
+        L.orc_lights_new.restype = vp
+        L.orc_lights_from_flat.restype = vp
+        L.orc_lights_from_flat.argtypes = [C.POINTER(LightsFlat)]
+        L.orc_lights_free.argtypes = [vp]
+        L.orc_lights_insert.restype = i; L.orc_lights_insert.argtypes = [vp, vp, f, vp]
+        L.orc_lights_delete.restype = i; L.orc_lights_delete.argtypes = [vp, vp, f]
+        L.orc_lights_clear.argtypes = [vp]
+        L.orc_lights_count.restype = i; L.orc_lights_count.argtypes = [vp]
+        L.orc_lights_set_ambient.restype = i; L.orc_lights_set_ambient.argtypes = [vp, vp]
+        L.orc_lights_flatten.argtypes = [vp, C.POINTER(LightsFlat)]
+        L.orc_lights_get.argtypes = [vp, vp, sz, vp]
+        L.orc_render_lit.restype = i
+        L.orc_render_lit.argtypes = [vp, vp, i, i, u, vp, C.POINTER(PixFmt), vp, vp, i]
         L.orc_render.argtypes = [vp, vp, i, i, u, vp, C.POINTER(PixFmt), vp, vp, vp, i]
 
     @property
@@ -134,6 +153,11 @@ class Oracle:
 
     def camera(self, kind=CAMERA_SIMPLE):
         return OracleCamera(self, kind)
+
+    def lights(self, flat=None):
+        """A light manager driven through the reference's API (reference glue only), or -- with
+        `flat` (dict as vv.LightManager.flatten()) -- a given flat light set."""
+        return OracleLights(self, flat)
 
 
 class OracleTree:
@@ -217,6 +241,15 @@ class OracleTree:
                                     out.ctypes.data, threads)
         return out
 
+    def render_lit(self, cam, w, h, lights, quality=QUALITY_BEST, texture=None, fmt=None, threads=1):
+        """vox_render with a light manager attached (renderer.c:41-49) -> pixels."""
+        texture = np.ascontiguousarray(texture, np.uint8)
+        fmt = fmt or pixfmt_xrgb8888()
+        pixels = np.zeros((h, w), np.uint32)
+        ok = self.orc.lib.orc_render_lit(self.h, cam.h, w, h, quality, texture.ctypes.data, C.byref(fmt),
+                                         lights.h if lights is not None else None, pixels.ctypes.data, threads)
+        return pixels if ok else None
+
     def render(self, cam, w, h, quality=QUALITY_BEST, texture=None, fmt=None, threads=1,
                want_hits=True):
         if texture is None:
@@ -233,6 +266,58 @@ class OracleTree:
         if not ok:
             return None
         return (pixels, leaf, hit) if want_hits else pixels
+
+
+class OracleLights:
+    def __init__(self, orc, flat=None):
+        self.orc = orc
+        if flat is None:
+            self.h = orc.lib.orc_lights_new()
+            if not self.h:
+                raise RuntimeError("this oracle cannot build light managers (reference glue only)")
+        else:
+            keep = {k: np.ascontiguousarray(flat[k]) for k in ("node_bounds", "node_link", "sphere_geom", "sphere_light")}
+            f = LightsFlat((C.c_float * 3)(*[float(x) for x in flat["ambient"]]), keep["node_bounds"].shape[0],
+                           keep["sphere_geom"].shape[0], keep["node_bounds"].ctypes.data, keep["node_link"].ctypes.data,
+                           keep["sphere_geom"].ctypes.data, keep["sphere_light"].ctypes.data)
+            self.h = orc.lib.orc_lights_from_flat(C.byref(f))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.orc.lib.orc_lights_free(self.h)
+            self.h = None
+
+    def insert(self, center, radius, color):
+        c, col = _f32(center), _f32(color)
+        return int(self.orc.lib.orc_lights_insert(self.h, c.ctypes.data, radius, col.ctypes.data))
+
+    def delete(self, center, radius):
+        c = _f32(center)
+        return int(self.orc.lib.orc_lights_delete(self.h, c.ctypes.data, radius))
+
+    def clear(self): self.orc.lib.orc_lights_clear(self.h)
+    def count(self): return int(self.orc.lib.orc_lights_count(self.h))
+    def set_ambient(self, color):
+        c = _f32(color)
+        return int(self.orc.lib.orc_lights_set_ambient(self.h, c.ctypes.data))
+
+    def flatten(self):
+        f = LightsFlat()
+        self.orc.lib.orc_lights_flatten(self.h, C.byref(f))
+        nn, ns = f.n_nodes, f.n_spheres
+        a = {"node_bounds": np.zeros((nn, 4), np.float32), "node_link": np.zeros((nn, 4), np.uint32),
+             "sphere_geom": np.zeros((ns, 4), np.float32), "sphere_light": np.zeros((ns, 4), np.float32)}
+        f = LightsFlat((C.c_float * 3)(), 0, 0, a["node_bounds"].ctypes.data, a["node_link"].ctypes.data,
+                       a["sphere_geom"].ctypes.data, a["sphere_light"].ctypes.data)
+        self.orc.lib.orc_lights_flatten(self.h, C.byref(f))
+        a["ambient"] = np.array(list(f.ambient), np.float32)
+        return a
+
+    def get_light(self, points):
+        p = _f32(points).reshape(-1, 3)
+        out = np.zeros((p.shape[0], 3), np.float32)
+        self.orc.lib.orc_lights_get(self.h, p.ctypes.data, p.shape[0], out.ctypes.data)
+        return out
 
 
 class OracleCamera:

@@ -25,6 +25,9 @@
 #include "voxtrees/geom.h"
 #include "voxrnd/camera.h"
 #include "voxrnd/modules.h"
+/* lights.h pulls in mtree.h, whose Block-typed declaration (mtree.h:124-126) gcc cannot parse: the
+   Makefile puts copies of both headers with those three lines deleted first on the include path */
+#include "voxrnd/lights.h"
 
 #include "oracle_api.h"
 #include "render_loop.h"
@@ -435,6 +438,168 @@ static void hook_pos (void *cam, float *pos)
 static float hook_sqr_metric (const float *a, const float *b)
 { vox_dot a_, b_; DOT_IN (a_, a); DOT_IN (b_, b); return vox_sqr_metric (a_, b_); }
 static float hook_sqr_norm (const float *a) { vox_dot a_; DOT_IN (a_, a); return vox_sqr_norm (a_); }
+
+/* ---- lights: the reference's light manager and M-tree (lights.c, mtree.c object code) ---- */
+
+/* layout mirror of the private struct (lights.c:11-14), to reach the M-tree root */
+struct light_manager_mirror
+{
+    vox_dot ambient_light;
+    struct vox_mtree_node *bound_lights;
+};
+
+struct orc_lights
+{
+    struct vox_light_manager *lm;   /* reference-driven, or */
+    orc_lights_flat *flat;          /* given as flat arrays */
+};
+
+orc_lights* orc_lights_new (void)
+{
+    orc_lights *l = calloc (1, sizeof *l);
+    l->lm = vox_make_light_manager ();
+    return l;
+}
+
+static void* dup_bytes (const void *p, size_t n)
+{
+    void *q = malloc (n ? n : 1);
+    if (n) memcpy (q, p, n);
+    return q;
+}
+
+orc_lights* orc_lights_from_flat (const orc_lights_flat *f)
+{
+    orc_lights *l = calloc (1, sizeof *l);
+    l->flat = malloc (sizeof *l->flat);
+    *l->flat = *f;
+    l->flat->node_bounds = dup_bytes (f->node_bounds, (size_t) f->n_nodes * 4 * sizeof (float));
+    l->flat->node_link = dup_bytes (f->node_link, (size_t) f->n_nodes * 4 * sizeof (uint32_t));
+    l->flat->sphere_geom = dup_bytes (f->sphere_geom, (size_t) f->n_spheres * 4 * sizeof (float));
+    l->flat->sphere_light = dup_bytes (f->sphere_light, (size_t) f->n_spheres * 4 * sizeof (float));
+    return l;
+}
+
+void orc_lights_free (orc_lights *l)
+{
+    if (!l) return;
+    if (l->lm) vox_destroy_light_manager (l->lm);
+    if (l->flat)
+    {
+        free (l->flat->node_bounds); free (l->flat->node_link); free (l->flat->sphere_geom); free (l->flat->sphere_light);
+        free (l->flat);
+    }
+    free (l);
+}
+
+int orc_lights_insert (orc_lights *l, const float center[3], float radius, const float color[3])
+{
+    if (!l->lm) return -1;
+    vox_dot c_, col_;
+    DOT_IN (c_, center); DOT_IN (col_, color);
+    return vox_insert_shadowless_light (l->lm, c_, radius, col_);
+}
+
+int orc_lights_delete (orc_lights *l, const float center[3], float radius)
+{
+    if (!l->lm) return -1;
+    vox_dot c_;
+    DOT_IN (c_, center);
+    return vox_delete_shadowless_light (l->lm, c_, radius);
+}
+
+void orc_lights_clear (orc_lights *l) { if (l->lm) vox_delete_shadowless_lights (l->lm); }
+int orc_lights_count (orc_lights *l) { return l->lm ? vox_shadowless_lights_number (l->lm) : (int) l->flat->n_spheres; }
+
+int orc_lights_set_ambient (orc_lights *l, const float color[3])
+{
+    if (l->lm) { vox_dot c_; DOT_IN (c_, color); return vox_set_ambient_light (l->lm, c_); }
+    for (int i=0; i<3; i++) if (color[i] < 0 || color[i] > 1) return 0;
+    memcpy (l->flat->ambient, color, sizeof l->flat->ambient);
+    return 1;
+}
+
+/* pre-order walk of the reference's M-tree into the flat layout */
+static void flatten_mtree (const struct vox_mtree_node *n, orc_lights_flat *o)
+{
+    uint32_t me = o->n_nodes++, first = o->n_spheres;
+    if (o->node_bounds)
+    {
+        DOT_OUT (o->node_bounds + 4*me, n->bounding_sphere.center);
+        o->node_bounds[4*me + 3] = n->bounding_sphere.sqr_radius;
+    }
+    if (n->leaf)
+        for (unsigned i=0; i<n->num; i++)
+        {
+            uint32_t k = o->n_spheres++;
+            if (!o->sphere_geom) continue;
+            DOT_OUT (o->sphere_geom + 4*k, n->data.spheres[i].center);
+            o->sphere_geom[4*k + 3] = n->data.spheres[i].sqr_radius;
+            DOT_OUT (o->sphere_light + 4*k, n->data.spheres[i].color);
+            o->sphere_light[4*k + 3] = n->data.spheres[i].radius;
+        }
+    else for (unsigned i=0; i<n->num; i++) flatten_mtree (n->data.children[i], o);
+    if (o->node_link)
+    {
+        o->node_link[4*me] = o->n_nodes;
+        o->node_link[4*me + 1] = n->leaf ? 1u : 0u;
+        o->node_link[4*me + 2] = first;
+        o->node_link[4*me + 3] = n->leaf ? n->num : 0u;
+    }
+}
+
+void orc_lights_flatten (orc_lights *l, orc_lights_flat *out)
+{
+    if (l->flat)
+    {
+        const orc_lights_flat *f = l->flat;
+        memcpy (out->ambient, f->ambient, sizeof out->ambient);
+        out->n_nodes = f->n_nodes; out->n_spheres = f->n_spheres;
+        if (!out->node_bounds) return;
+        memcpy (out->node_bounds, f->node_bounds, (size_t) f->n_nodes * 4 * sizeof (float));
+        memcpy (out->node_link, f->node_link, (size_t) f->n_nodes * 4 * sizeof (uint32_t));
+        memcpy (out->sphere_geom, f->sphere_geom, (size_t) f->n_spheres * 4 * sizeof (float));
+        memcpy (out->sphere_light, f->sphere_light, (size_t) f->n_spheres * 4 * sizeof (float));
+        return;
+    }
+    const struct light_manager_mirror *m = (const void*) l->lm;
+    DOT_OUT (out->ambient, m->ambient_light);
+    out->n_nodes = out->n_spheres = 0;
+    if (m->bound_lights) flatten_mtree (m->bound_lights, out);
+}
+
+static void hook_light (void *lights, const float *inter, float *light)
+{
+    orc_lights *l = lights;
+    if (l->lm)
+    {
+        vox_dot p_, out_;
+        DOT_IN (p_, inter);
+        vox_get_light (l->lm, p_, out_);       /* lights.c:104-116 */
+        DOT_OUT (light, out_);
+    }
+    else orc_flat_light (l->flat, hook_sqr_metric, inter, light);
+}
+
+void orc_lights_get (orc_lights *l, const float *points, size_t n, float *rgb)
+{
+    for (size_t i=0; i<n; i++) hook_light (l, points + 3*i, rgb + 3*i);
+}
+
+int orc_render_lit (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
+                    const uint8_t *texture, const orc_pixfmt *fmt, orc_lights *lights,
+                    uint32_t *pixels, int threads)
+{
+    build_index (t);
+    orc_render_hooks hk = {
+        .scene = t->root, .camera = c->cam,
+        .ray = hook_ray, .screen2world = hook_s2w, .get_position = hook_pos,
+        .sqr_metric = hook_sqr_metric, .sqr_norm = hook_sqr_norm,
+        .get_light = lights ? hook_light : NULL, .lights = lights,
+    };
+    DOT_OUT (hk.voxel, vox_voxel);
+    return orc_render_loop (&hk, w, h, quality, texture, fmt, pixels, NULL, NULL, threads);
+}
 
 int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
                 const uint8_t *texture, const orc_pixfmt *fmt,

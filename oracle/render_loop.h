@@ -33,6 +33,9 @@ typedef struct
     int32_t (*node_id) (void *idctx, const void *node); /* for the optional leaf_id output */
     void *idctx;
     float voxel[3];
+    /* vox_get_light (lights.c:104-116) when a light manager is attached, else NULL */
+    void (*get_light) (void *lights, const float *inter, float *light);
+    void *lights;
 } orc_render_hooks;
 
 /* renderer.c:23-25 */
@@ -50,15 +53,52 @@ static inline uint32_t orc_map_rgb (const orc_pixfmt *f, uint8_t r, uint8_t g, u
            ((uint32_t)(b >> f->bloss) << f->bshift) | f->amask;
 }
 
-/* renderer.c:27-41 (light_manager == NULL branch) */
-static inline uint32_t orc_get_color (const uint8_t *texture, const orc_pixfmt *fmt,
-                                      const float voxel[3], const float inter[3])
+/* renderer.c:27-52 */
+static inline uint32_t orc_get_color_lit (const orc_render_hooks *hk, const uint8_t *texture, const orc_pixfmt *fmt,
+                                          const float voxel[3], const float inter[3])
 {
     int x = abs ((int)(inter[0] / voxel[0])) & 31;
     int y = abs ((int)(inter[1] / voxel[1])) & 31;
     int z = abs ((int)(inter[2] / voxel[2])) & 31;
     uint8_t c = texture[x*32*32 + y*32 + z];
-    return orc_map_rgb (fmt, c, c, c);
+    if (!hk->get_light) return orc_map_rgb (fmt, c, c, c);
+    float light[4];
+    uint8_t r, g, b;
+    hk->get_light (hk->lights, inter, light);
+    r = fminf (light[0], 1.0) * c;
+    g = fminf (light[1], 1.0) * c;
+    b = fminf (light[2], 1.0) * c;
+    return orc_map_rgb (fmt, r, g, b);
+}
+#define orc_get_color(texture, fmt, voxel, inter) orc_get_color_lit (hk, texture, fmt, voxel, inter)
+
+/* ---- lights over a FLAT M-tree (the layout the product uploads, voxgpu_lights_flat): the
+ * traversal of mtree.c:463-493 and the sum of lights.c:91-116, restated.  `sqr` is the
+ * implementation's vox_sqr_metric. */
+static inline void orc_flat_light (const orc_lights_flat *f, float (*sqr) (const float*, const float*),
+                                   const float *p, float *light)
+{
+    light[0] = f->ambient[0]; light[1] = f->ambient[1]; light[2] = f->ambient[2];
+    uint32_t i = 0;
+    while (i < f->n_nodes)
+    {
+        const float *b = f->node_bounds + 4*i;
+        const uint32_t *l = f->node_link + 4*i;
+        if (!(sqr (b, p) < b[3])) { i = l[0]; continue; }
+        if (l[1])
+            for (uint32_t k=l[2]; k<l[2]+l[3]; k++)
+            {
+                const float *g = f->sphere_geom + 4*k, *c = f->sphere_light + 4*k;
+                if (l[3] != 1 && !(sqr (g, p) < g[3])) continue;       /* mtree.c:475-482 */
+                float dist = fminf (c[3], sqrtf (sqr (g, p)));           /* lights.c:95-101 */
+                float add = 1 - dist / c[3];
+                float r = light[0] + add * c[0];
+                float gg = light[1] + add * c[1];
+                float bb = light[2] + add * c[2];
+                light[0] = r; light[1] = gg; light[2] = bb;
+            }
+        i++;
+    }
 }
 
 #define ORC_LENGTH_THRESHOLD 1.69   /* renderer.c:197 */

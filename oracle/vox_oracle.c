@@ -809,6 +809,90 @@ static const void* hook_ray (const void *node, const float *o, const float *d, f
 static void hook_s2w (void *cam, float *dir, int sx, int sy) { orc_camera_screen2world (cam, dir, sx, sy); }
 static void hook_pos (void *cam, float *pos) { orc_camera_get_position (cam, pos); }
 
+/* ------------------------------------------------------------------- lights */
+
+struct orc_lights
+{
+    orc_lights_flat flat;    /* owns copies of the arrays */
+};
+
+static void* dup_bytes (const void *p, size_t n)
+{
+    void *q = malloc (n ? n : 1);
+    if (n) memcpy (q, p, n);
+    return q;
+}
+
+orc_lights* orc_lights_new (void) { return NULL; /* the M-tree's construction is reference-only */ }
+
+orc_lights* orc_lights_from_flat (const orc_lights_flat *f)
+{
+    orc_lights *l = calloc (1, sizeof *l);
+    l->flat = *f;
+    l->flat.node_bounds = dup_bytes (f->node_bounds, (size_t) f->n_nodes * 4 * sizeof (float));
+    l->flat.node_link = dup_bytes (f->node_link, (size_t) f->n_nodes * 4 * sizeof (uint32_t));
+    l->flat.sphere_geom = dup_bytes (f->sphere_geom, (size_t) f->n_spheres * 4 * sizeof (float));
+    l->flat.sphere_light = dup_bytes (f->sphere_light, (size_t) f->n_spheres * 4 * sizeof (float));
+    return l;
+}
+
+void orc_lights_free (orc_lights *l)
+{
+    if (!l) return;
+    free (l->flat.node_bounds); free (l->flat.node_link); free (l->flat.sphere_geom); free (l->flat.sphere_light);
+    free (l);
+}
+
+int orc_lights_insert (orc_lights *l, const float center[3], float radius, const float color[3])
+{ (void) l; (void) center; (void) radius; (void) color; return -1; }
+int orc_lights_delete (orc_lights *l, const float center[3], float radius)
+{ (void) l; (void) center; (void) radius; return -1; }
+void orc_lights_clear (orc_lights *l) { (void) l; }
+int orc_lights_count (orc_lights *l) { return (int) l->flat.n_spheres; }
+int orc_lights_set_ambient (orc_lights *l, const float color[3])
+{
+    for (int i=0; i<3; i++) if (color[i] < 0 || color[i] > 1) return 0;   /* lights.c:81-89 */
+    memcpy (l->flat.ambient, color, sizeof l->flat.ambient);
+    return 1;
+}
+
+void orc_lights_flatten (orc_lights *l, orc_lights_flat *out)
+{
+    const orc_lights_flat *f = &l->flat;
+    memcpy (out->ambient, f->ambient, sizeof out->ambient);
+    out->n_nodes = f->n_nodes; out->n_spheres = f->n_spheres;
+    if (!out->node_bounds) return;
+    memcpy (out->node_bounds, f->node_bounds, (size_t) f->n_nodes * 4 * sizeof (float));
+    memcpy (out->node_link, f->node_link, (size_t) f->n_nodes * 4 * sizeof (uint32_t));
+    memcpy (out->sphere_geom, f->sphere_geom, (size_t) f->n_spheres * 4 * sizeof (float));
+    memcpy (out->sphere_light, f->sphere_light, (size_t) f->n_spheres * 4 * sizeof (float));
+}
+
+static void hook_light (void *lights, const float *inter, float *light)
+{
+    orc_flat_light (&((orc_lights*) lights)->flat, sqr_metric, inter, light);
+}
+
+void orc_lights_get (orc_lights *l, const float *points, size_t n, float *rgb)
+{
+    for (size_t i=0; i<n; i++) hook_light (l, points + 3*i, rgb + 3*i);
+}
+
+int orc_render_lit (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
+                    const uint8_t *texture, const orc_pixfmt *fmt, orc_lights *lights,
+                    uint32_t *pixels, int threads)
+{
+    build_index (t);
+    orc_render_hooks hk = {
+        .scene = t->root, .camera = c,
+        .ray = hook_ray, .screen2world = hook_s2w, .get_position = hook_pos,
+        .sqr_metric = sqr_metric, .sqr_norm = sqr_norm,
+        .get_light = lights ? hook_light : NULL, .lights = lights,
+    };
+    memcpy (hk.voxel, g_voxel, sizeof hk.voxel);
+    return orc_render_loop (&hk, w, h, quality, texture, fmt, pixels, NULL, NULL, threads);
+}
+
 int orc_render (orc_tree *t, orc_camera *c, int w, int h, unsigned quality,
                 const uint8_t *texture, const orc_pixfmt *fmt,
                 uint32_t *pixels, int32_t *leaf_id, float *hit, int threads)

@@ -148,6 +148,22 @@ def main():
     arrays["edit_rays_leaf"], arrays["edit_rays_hit"] = l, h
     meta["edits"]["ray_hits"] = int((l >= 0).sum())
 
+    # ---- lights (lights.c over mtree.c): the M-tree after a scripted set of insertions / deletions,
+    #      the light at sample points, and lit frames (renderer.c:41-49)
+    script = ds.light_script()
+    L = R.lights()
+    arrays["light_results"] = np.array(ds.apply_lights(L, script), np.int32)
+    lf = L.flatten()
+    meta["lights"] = {"flat": {k: sha(v) for k, v in lf.items()}, "count": L.count(),
+                      "nodes": int(lf["node_bounds"].shape[0])}
+    pts = ds.uniform01(0, 3 * 4096, ds.SEED + 5).reshape(4096, 3).astype(np.float32) * np.float32(300) - np.float32(20)
+    arrays["light_at_points"] = L.get_light(pts)
+    cam = ds.setup_camera(R.camera(orc.CAMERA_SIMPLE), (128, 128, 400), (128, 128, 128), 1.2, 800, 600)
+    meta["lights"]["c1_frames"] = {}
+    for qname, q in (("best", 0), ("adaptive", 2), ("adaptive+merge", 2 | 4)):
+        pix = T["bonsai"].render_lit(cam, 800, 600, L, q, tex, threads=threads)
+        meta["lights"]["c1_frames"][qname] = {"pix_sha": sha(pix), "lit": int((pix != 0).sum())}
+
     # reference benchmark known answers (benchmarks/voxtrees/hit-box.c:16-27, ball-intersection.c:14-23)
     one = R.tree(np.array([[0, 10, 0]], np.float32), by_insertion=True)
     j = np.arange(10, dtype=np.float32)

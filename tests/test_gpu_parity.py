@@ -471,6 +471,87 @@ def test_render_follows_edits(gpu, checker, ds):
     assert rb.voxels() == t.voxels()                   # same voxels, differently shaped tree
 
 
+# ------------------------------------------------- lights (f-4): shading through the flattened M-tree
+
+@pytest.mark.parametrize("qname,q", [("best", 0), ("adaptive", 2), ("adaptive+merge", 2 | 4)])
+def test_lit_frames(gpu, checker, golden, bonsai, ds, qname, q):
+    """vox_render with a light manager attached (renderer.c:41-49, lights.c:91-116): per-channel
+    min(1, ambient + lights) * texture, the lights summed in M-tree order.  Pixels equal the reference's
+    (golden, made with its lights.c / mtree.c object code) and the live oracle's evaluation of the same
+    flat light set; through vox_render/vox_redraw and through voxgpu_render with row bands."""
+    meta, _ = golden
+    t = gpu.Tree.build(bonsai)
+    w, h = 800, 600
+    lm = gpu.LightManager()
+    ds.apply_lights(lm, ds.light_script())
+    cam = ds.setup_camera(gpu.Camera(), (128, 128, 400), (128, 128, 128), 1.2, w, h)
+    ctx = gpu.Context(w, h)
+    ctx.set_scene(t); ctx.set_camera(cam); ctx.set_light_manager(lm)
+    assert ctx.set_quality(q)
+    ctx.render(); ctx.redraw()
+    assert gpu.last_error() == ""
+    pix = ctx.pixels().copy()
+    want = meta["lights"]["c1_frames"][qname]
+    assert int((pix != 0).sum()) == want["lit"]
+    assert sha(pix) == want["pix_sha"]
+    ocam = ds.setup_camera(checker.camera(0), (128, 128, 400), (128, 128, 128), 1.2, w, h)
+    olights = checker.lights(lm.flatten())
+    opix = checker.tree(bonsai).render_lit(ocam, w, h, olights, q, ctx.texture(), threads=THREADS)
+    assert np.array_equal(pix, opix)
+    # coloured, not grey: the three channels differ somewhere
+    assert ((pix & 0xff) != ((pix >> 8) & 0xff)).any()
+    # the device entry point with an explicit light handle, one row band
+    api = gpu.api
+    dl = gpu.upload_lights(lm.flatten())
+    d_tex = gpu.DeviceBuffer.from_array(ctx.texture())
+    d_pix = gpu.DeviceBuffer(w * 120 * 4)
+    fr = api.GpuFrame(w, h, 240, 360, w, q, ctx.pixfmt(), dl)
+    gc = cam.gpu_camera()
+    assert api.libs.gpu.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None) == 0
+    assert np.array_equal(d_pix.download(np.uint32, (120, w)), pix[240:360])
+    api.libs.gpu.voxgpu_synchronize(None)
+    api.libs.gpu.voxgpu_lights_free(dl)
+
+
+def test_lights_follow_changes(gpu, checker, skull, ds):
+    """The device copy of the lights is refreshed after every change of the manager; detaching the
+    manager gives the unlit frame again; a manager without lights applies the ambient colour only."""
+    t = gpu.Tree.build(skull)
+    w, h = 320, 160
+    pos, look = ds.orbit_pose(30)
+    cam = ds.setup_camera(gpu.Camera(), pos, look, 1.2, w, h)
+    ocam = ds.setup_camera(checker.camera(0), pos, look, 1.2, w, h)
+    otree = checker.tree(skull)
+    ctx = gpu.Context(w, h)
+    ctx.set_scene(t); ctx.set_camera(cam); ctx.set_quality(0)
+
+    def frame():
+        ctx.render(); ctx.redraw()
+        assert gpu.last_error() == ""
+        return ctx.pixels().copy()
+
+    def oracle(lm):
+        return otree.render_lit(ocam, w, h, checker.lights(lm.flatten()) if lm else None, 0, ctx.texture(), threads=THREADS)
+
+    unlit = frame()
+    assert np.array_equal(unlit, oracle(None))
+    lm = gpu.LightManager()
+    ctx.set_light_manager(lm)
+    assert np.array_equal(frame(), unlit)                       # ambient (1,1,1), no lights: same as unlit
+    lm.set_ambient([0.2, 0.1, 0.05])
+    dim = frame()
+    assert np.array_equal(dim, oracle(lm)) and not np.array_equal(dim, unlit)
+    lm.insert([128, 60, 128], 120.0, [1.0, 0.6, 0.2])
+    lm.insert([60, 128, 200], 90.0, [0.1, 0.9, 1.0])
+    two = frame()
+    assert np.array_equal(two, oracle(lm)) and not np.array_equal(two, dim)
+    lm.delete([128, 60, 128], 120.0)
+    one = frame()
+    assert np.array_equal(one, oracle(lm)) and not np.array_equal(one, two)
+    ctx.set_light_manager(None)
+    assert np.array_equal(frame(), unlit)
+
+
 # ------------------------------------------------- full-size configs, by properties
 
 def test_c3_full_size_properties(gpu, port, ds):

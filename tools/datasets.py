@@ -158,6 +158,37 @@ def edit_script(n_edits=3000, seed=SEED + 3):
     return vox, ins, pts
 
 
+def light_script(n=120, lo=-30.0, hi=290.0, seed=SEED + 4):
+    """A deterministic light workload (f-4) for the 256^3 bundled volumes: n shadowless lights
+    (centre uniform in [lo,hi)^3, radius in [12,90), colour in [0,1]^3), every fourth one deleted
+    again after 8 more insertions (exercises M-tree splits, leaf drops and re-parenting,
+    mtree.c:113-188, 274-330), and a dim ambient colour.
+    Returns (ambient, ops) with ops = list of ('+', centre, radius, colour) / ('-', centre, radius)."""
+    u = uniform01(0, 7 * n + 3, seed)
+    amb = (u[:3] * 0.35).astype(np.float32)
+    e = u[3:].reshape(n, 7).astype(np.float32)
+    ops, pending = [], []
+    for i in range(n):
+        c = (e[i, :3] * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+        r = np.float32(e[i, 3] * np.float32(78.0) + np.float32(12.0))
+        ops.append(("+", c, float(r), e[i, 4:7].copy()))
+        if i % 4 == 1:
+            pending.append((i + 8, c, float(r)))
+        while pending and pending[0][0] <= i:
+            _, pc, pr = pending.pop(0)
+            ops.append(("-", pc, pr))
+    return amb, ops
+
+
+def apply_lights(lm, script):
+    """Run a light_script() on anything with set_ambient / insert / delete (product or oracle)."""
+    amb, ops = script
+    res = [lm.set_ambient(amb)]
+    for op in ops:
+        res.append(lm.insert(op[1], op[2], op[3]) if op[0] == "+" else lm.delete(op[1], op[2]))
+    return res
+
+
 def orbit_pose(frame, frames=360, centre=(128.0, 128.0, 128.0), radius=328.0):
     """C2 camera path: position on the xz orbit, looking at the centre.
     Frame 0 is exactly examples/scene1.cfg's camera (128,128,-200)."""

@@ -15,6 +15,7 @@ tests and by bench.py; it contains no compute of its own and never touches
 device those calls fail loudly (VoxError) -- there is no CPU fallback.
 """
 from .api import (  # noqa: F401
+    LightManager, upload_lights,
     VoxError, libs, gpu_available, device_count, set_device, last_error, launch_count,
     set_voxel_size, get_voxel_size, Tree, Camera, Context, DeviceBuffer, Timer,
     QUALITY_BEST, QUALITY_FAST, QUALITY_ADAPTIVE, QUALITY_RAY_MERGE, QUALITY_RAY_MERGE_ACCURATE,

@@ -100,7 +100,14 @@ class GpuPixFmt(C.Structure):
 
 class GpuFrame(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("pitch_pixels", C.c_int),
-                ("quality", C.c_uint), ("fmt", GpuPixFmt)]
+                ("quality", C.c_uint), ("fmt", GpuPixFmt), ("lights", C.c_void_p)]
+
+
+class GpuLightsFlat(C.Structure):
+    """voxgpu_lights_flat (include/voxgpu.h)."""
+    _fields_ = [("ambient", C.c_float * 3), ("n_nodes", C.c_uint32), ("n_spheres", C.c_uint32),
+                ("node_bounds", C.c_void_p), ("node_link", C.c_void_p), ("sphere_geom", C.c_void_p),
+                ("sphere_light", C.c_void_p)]
 
 
 class GpuStats(C.Structure):
@@ -161,6 +168,8 @@ class _Libs:
         g.voxgpu_ipc_open.restype = _vp; g.voxgpu_ipc_open.argtypes = [_vp]
         g.voxgpu_ipc_close.argtypes = [_vp]
         g.voxgpu_tree_device_bytes.restype = sz; g.voxgpu_tree_device_bytes.argtypes = [_vp]
+        g.voxgpu_lights_upload.restype = _vp; g.voxgpu_lights_upload.argtypes = [C.POINTER(GpuLightsFlat)]
+        g.voxgpu_lights_free.argtypes = [_vp]
         g.voxgpu_rays_device.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, _vp]
         g.voxgpu_rays_stats.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, C.POINTER(GpuStats)]
         g.voxgpu_balls_device.argtypes = [_vp, _vp, _vp, sz, _vp, _vp]
@@ -223,6 +232,16 @@ class _Libs:
         r.vox_context_set_texture.argtypes = [C.POINTER(_Ctx), _vp]
         r.vox_context_get_texture.restype = _vp; r.vox_context_get_texture.argtypes = [C.POINTER(_Ctx)]
         r.vox_context_last_kernel_ms.restype = _f; r.vox_context_last_kernel_ms.argtypes = [C.POINTER(_Ctx)]
+        r.vox_context_set_light_manager.argtypes = [C.POINTER(_Ctx), _vp]
+        r.vox_make_light_manager.restype = _vp
+        r.vox_destroy_light_manager.argtypes = [_vp]
+        r.vox_insert_shadowless_light.restype = _i; r.vox_insert_shadowless_light.argtypes = [_vp, _vp, _f, _vp]
+        r.vox_delete_shadowless_light.restype = _i; r.vox_delete_shadowless_light.argtypes = [_vp, _vp, _f]
+        r.vox_delete_shadowless_lights.argtypes = [_vp]
+        r.vox_shadowless_lights_number.restype = _i; r.vox_shadowless_lights_number.argtypes = [_vp]
+        r.vox_set_ambient_light.restype = _i; r.vox_set_ambient_light.argtypes = [_vp, _vp]
+        r.vox_get_light.argtypes = [_vp, _vp, _vp]
+        r.vox_light_manager_flatten.argtypes = [_vp, C.POINTER(u32), C.POINTER(u32), _vp, _vp, _vp, _vp]
         r.vox_render.argtypes = [C.POINTER(_Ctx)]
         r.vox_redraw.argtypes = [C.POINTER(_Ctx)]
         r.vox_make_cd.restype = _vp
@@ -513,12 +532,16 @@ class Camera:
         except Exception:
             pass
 
-    def set_position(self, p): self.iface.set_property_dot(self.h, b"position", dots4([p]).ctypes.data)
-    def set_rotation(self, a): self.iface.set_property_dot(self.h, b"rotation", dots4([a]).ctypes.data)
+    def _dot(self, fn, v, *pre):
+        d = dots4([v])                       # named: the buffer must outlive the call
+        fn(self.h, *pre, d.ctypes.data)
+
+    def set_position(self, p): self._dot(self.iface.set_property_dot, p, b"position")
+    def set_rotation(self, a): self._dot(self.iface.set_property_dot, a, b"rotation")
     def set_fov(self, fov): self.iface.set_property_number(self.h, b"fov", fov)
-    def look_at(self, p): self.iface.look_at(self.h, dots4([p]).ctypes.data)
-    def rotate(self, d): self.iface.rotate_camera(self.h, dots4([d]).ctypes.data)
-    def move(self, d): self.iface.move_camera(self.h, dots4([d]).ctypes.data)
+    def look_at(self, p): self._dot(self.iface.look_at, p)
+    def rotate(self, d): self._dot(self.iface.rotate_camera, d)
+    def move(self, d): self._dot(self.iface.move_camera, d)
     def set_window_size(self, w, h): self.iface.set_window_size(self.h, w, h)
 
     def get_position(self):
@@ -562,6 +585,70 @@ class Camera:
         return s
 
 
+class LightManager:
+    """struct vox_light_manager* (include/voxrnd/lights.h)."""
+
+    def __init__(self):
+        self.h = libs.rnd.vox_make_light_manager()
+
+    def __del__(self):
+        try:
+            if self.h:
+                libs.rnd.vox_destroy_light_manager(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def insert(self, center, radius, color):
+        c, col = dots4([center]), dots4([color])      # named: the buffers must outlive the call
+        return int(libs.rnd.vox_insert_shadowless_light(self.h, c.ctypes.data, radius, col.ctypes.data))
+
+    def delete(self, center, radius):
+        c = dots4([center])
+        return int(libs.rnd.vox_delete_shadowless_light(self.h, c.ctypes.data, radius))
+
+    def clear(self):
+        libs.rnd.vox_delete_shadowless_lights(self.h)
+
+    def count(self):
+        return int(libs.rnd.vox_shadowless_lights_number(self.h))
+
+    def set_ambient(self, color):
+        c = dots4([color])
+        return int(libs.rnd.vox_set_ambient_light(self.h, c.ctypes.data))
+
+    def get_light(self, points):
+        """vox_get_light on the HOST for every row of points -> (n, 3)."""
+        p = dots4(points)
+        out = dots4(np.zeros((p.shape[0], 3), np.float32))
+        for i in range(p.shape[0]):
+            libs.rnd.vox_get_light(self.h, p[i].ctypes.data, out[i].ctypes.data)
+        return out[:, :3].copy()
+
+    def flatten(self):
+        """The flat light set vox_render uploads (dict of arrays + 'ambient')."""
+        nn, ns = C.c_uint32(0), C.c_uint32(0)
+        libs.rnd.vox_light_manager_flatten(self.h, C.byref(nn), C.byref(ns), None, None, None, None)
+        a = {"node_bounds": np.zeros((nn.value, 4), np.float32), "node_link": np.zeros((nn.value, 4), np.uint32),
+             "sphere_geom": np.zeros((ns.value, 4), np.float32), "sphere_light": np.zeros((ns.value, 4), np.float32)}
+        libs.rnd.vox_light_manager_flatten(self.h, None, None, a["node_bounds"].ctypes.data, a["node_link"].ctypes.data,
+                                           a["sphere_geom"].ctypes.data, a["sphere_light"].ctypes.data)
+        a["ambient"] = self.get_light([[1e30, 1e30, 1e30]])[0]     # far from every light: the ambient colour
+        return a
+
+
+def upload_lights(flat):
+    """voxgpu_lights_upload of a flat light set (dict as LightManager.flatten()) -> device handle."""
+    keep = {k: np.ascontiguousarray(flat[k]) for k in ("node_bounds", "node_link", "sphere_geom", "sphere_light")}
+    f = GpuLightsFlat((C.c_float * 3)(*[float(x) for x in flat["ambient"]]), keep["node_bounds"].shape[0],
+                      keep["sphere_geom"].shape[0], keep["node_bounds"].ctypes.data, keep["node_link"].ctypes.data,
+                      keep["sphere_geom"].ctypes.data, keep["sphere_light"].ctypes.data)
+    h = libs.gpu.voxgpu_lights_upload(C.byref(f))
+    if not h:
+        raise VoxError(libs.gpu.voxgpu_last_error().decode())
+    return h
+
+
 class Context:
     """struct vox_rnd_ctx* with a headless surface."""
 
@@ -587,6 +674,10 @@ class Context:
     def set_camera(self, cam):
         self._camera = cam
         libs.rnd.vox_context_set_camera(self.h, cam.h)
+
+    def set_light_manager(self, lm):
+        self._lights = lm
+        libs.rnd.vox_context_set_light_manager(self.h, lm.h if lm is not None else None)
 
     def set_quality(self, q):
         return bool(libs.rnd.vox_context_set_quality(self.h, q))

@@ -477,11 +477,22 @@ struct DevCamera
     const float4 *table;
 };
 
+/* Flattened M-tree of lights (voxgpu_lights_flat): 2 x float4 per node {bounding centre, squared
+   radius}{skip, leaf, first sphere, count} and per sphere {centre, squared radius}{colour, radius}. */
+struct DevLights
+{
+    const float4 *nodes;
+    const float4 *spheres;
+    unsigned n_nodes;
+    float ar, ag, ab;
+};
+
 struct DevFrame
 {
     int w, y0, rows, pitch;
     unsigned amask;
     unsigned char rloss, gloss, bloss, rshift, gshift, bshift;
+    DevLights lt;
 };
 
 /* vect-ops.c:8-16 vox_cross_product */
@@ -526,14 +537,66 @@ __device__ __forceinline__ V3 screen2world (const DevCamera &cam, int sx, int sy
     return dir;
 }
 
-/* renderer.c:27-41 get_color (no light manager) + SDL_MapRGB */
+/* geom.c:133-139 vox_sqr_metric: ((dx^2 + dy^2) + dz^2) */
+__device__ __forceinline__ float sqr_metric4 (const float4 c, const V3 p)
+{
+    const float dx = __fsub_rn (c.x, p.x), dy = __fsub_rn (c.y, p.y), dz = __fsub_rn (c.z, p.z);
+    return __fadd_rn (__fadd_rn (__fmul_rn (dx, dx), __fmul_rn (dy, dy)), __fmul_rn (dz, dz));
+}
+
+/* lights.c:91-102 get_color_callback: a sphere's contribution fades linearly from its centre */
+__device__ __forceinline__ void add_light (const DevLights &lt, unsigned sphere, const V3 p, float &lr, float &lg, float &lb)
+{
+    const float4 g = __ldg (lt.spheres + 2*sphere), c = __ldg (lt.spheres + 2*sphere + 1);
+    const float dist = fminf (c.w, __fsqrt_rn (sqr_metric4 (g, p)));
+    const float add = __fsub_rn (1.0f, __fdiv_rn (dist, c.w));
+    lr = __fadd_rn (lr, __fmul_rn (add, c.x));
+    lg = __fadd_rn (lg, __fmul_rn (add, c.y));
+    lb = __fadd_rn (lb, __fmul_rn (add, c.z));
+}
+
+/* lights.c:104-116 vox_get_light over mtree.c:463-493, on the pre-order node array: same nodes
+   entered, same spheres in the same order as the reference's recursion, so the same fp32 sums. */
+__device__ __noinline__ void get_light (const DevLights &lt, const V3 p, float &lr, float &lg, float &lb)
+{
+    lr = lt.ar; lg = lt.ag; lb = lt.ab;
+    unsigned i = 0;
+    while (i < lt.n_nodes)
+    {
+        const float4 b = __ldg (lt.nodes + 2*i);
+        const float4 l = __ldg (lt.nodes + 2*i + 1);
+        if (!(sqr_metric4 (b, p) < b.w)) { i = __float_as_uint (l.x); continue; }
+        if (__float_as_uint (l.y))
+        {
+            const unsigned first = __float_as_uint (l.z), num = __float_as_uint (l.w);
+            if (num == 1) add_light (lt, first, p, lr, lg, lb);      /* mtree.c:475-482: no second test */
+            else for (unsigned k=0; k<num; k++)
+            {
+                const float4 g = __ldg (lt.spheres + 2*(first + k));
+                if (sqr_metric4 (g, p) < g.w) add_light (lt, first + k, p, lr, lg, lb);
+            }
+        }
+        i++;
+    }
+}
+
+/* renderer.c:27-52 get_color + SDL_MapRGB; LIT = a light manager is attached (renderer.c:41-49) */
+template <bool LIT>
 __device__ __forceinline__ unsigned shade (const TreeRef &tr, const DevFrame &fr, const unsigned char *tex, const V3 p)
 {
     const int x = abs (__float2int_rz (__fdiv_rn (p.x, tr.vx))) & 31;
     const int y = abs (__float2int_rz (__fdiv_rn (p.y, tr.vy))) & 31;
     const int z = abs (__float2int_rz (__fdiv_rn (p.z, tr.vz))) & 31;
     const unsigned c = __ldg (tex + (x*1024 + y*32 + z));
-    return ((c >> fr.rloss) << fr.rshift) | ((c >> fr.gloss) << fr.gshift) | ((c >> fr.bloss) << fr.bshift) | fr.amask;
+    if (!LIT)
+        return ((c >> fr.rloss) << fr.rshift) | ((c >> fr.gloss) << fr.gshift) | ((c >> fr.bloss) << fr.bshift) | fr.amask;
+    float lr, lg, lb;
+    get_light (fr.lt, p, lr, lg, lb);
+    const float fc = (float) c;
+    const unsigned r = __float2uint_rz (__fmul_rn (fminf (lr, 1.0f), fc)) & 0xffu;
+    const unsigned g = __float2uint_rz (__fmul_rn (fminf (lg, 1.0f), fc)) & 0xffu;
+    const unsigned b = __float2uint_rz (__fmul_rn (fminf (lb, 1.0f), fc)) & 0xffu;
+    return ((r >> fr.rloss) << fr.rshift) | ((g >> fr.gloss) << fr.gshift) | ((b >> fr.bloss) << fr.bshift) | fr.amask;
 }
 
 /*
@@ -563,7 +626,7 @@ k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restri
     ray_tree<false> (tr, 0, origin, dir, stack, r, NULL);
 
     unsigned color = 0;
-    if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+    if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
     pixels[(size_t) ry * fr.pitch + sx] = color;
     if (OUT_HITS)
     {
@@ -651,7 +714,7 @@ __global__ void k_sched_build (const unsigned char * __restrict__ cost_prev, int
     }
 }
 
-template <bool OUT_HITS, unsigned STRIPS>
+template <bool OUT_HITS, unsigned STRIPS, bool LIT>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
@@ -701,7 +764,7 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         if (sch.cost_next && lane == 0) sch.cost_next[tile] = (unsigned char) min (iterations, 255);
 
         unsigned color = 0;
-        if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+        if (r.leaf >= 0) color = shade<LIT> (tr, fr, tex, r.point);
         pixels[(size_t) ry * fr.pitch + sx] = color;
         if (OUT_HITS)
         {
@@ -779,7 +842,7 @@ k_render_stream (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * _
                 RayResult r;
                 lane_search_result (s, stack, r);
                 unsigned color = 0;
-                if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+                if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
                 pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
                 if (OUT_HITS)
                 {
@@ -828,7 +891,7 @@ k_render_stream (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * _
         RayResult r;
         lane_search_result (s, stack, r);
         unsigned color = 0;
-        if (r.leaf >= 0) color = shade (tr, fr, tex, r.point);
+        if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
         pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
         if (OUT_HITS)
         {
@@ -867,7 +930,7 @@ __device__ __forceinline__ float sqr_norm3 (const V3 a)
     return __fadd_rn (__fadd_rn (__fmul_rn (a.x, a.x), __fmul_rn (a.y, a.y)), __fmul_rn (a.z, a.z));
 }
 
-template <bool OUT_HITS>
+template <bool OUT_HITS, bool LIT>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const unsigned char * __restrict__ tex,
                  unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
@@ -950,7 +1013,7 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
                     if (r.leaf >= 0)
                     {
                         c1 = true; iend = 15; inter = r.point; inter_c1 = r.point;
-                        sq[0] = shade (tr, fr, tex, r.point);
+                        sq[0] = shade<LIT> (tr, fr, tex, r.point);
                         if (OUT_HITS)
                         {
                             const size_t pos = (size_t) ystart * fr.w + xstart;
@@ -964,7 +1027,7 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
             {
                 if (want && r.leaf >= 0)
                 {
-                    sq[15] = shade (tr, fr, tex, r.point);
+                    sq[15] = shade<LIT> (tr, fr, tex, r.point);
                     if (OUT_HITS)
                     {
                         const size_t pos = (size_t) (ystart + 3) * fr.w + xstart + 3;
@@ -995,7 +1058,7 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
                     {
                         if (leaf >= 0)
                         {
-                            sq[p] = merge ? sq[prev_p] : shade (tr, fr, tex, inter);
+                            sq[p] = merge ? sq[prev_p] : shade<LIT> (tr, fr, tex, inter);
                             if (OUT_HITS)
                             {
                                 const size_t pos = (size_t) py * fr.w + px;
@@ -1029,13 +1092,63 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
    slots so that renders in flight on different streams never share one. */
 #define COUNTER_SLOTS 64
 static unsigned *g_counters[64] = {0};
-static int g_render_blocks[64][5] = {{0}};
+static int g_render_blocks[64][7] = {{0}};
 static std::atomic<unsigned> g_counter_seq{0};
 static int g_variant = 1;
 static int g_refill_min = 8;
 static unsigned long long *g_trace = NULL;
 
 extern "C" void voxgpu_set_trace (void *d_trace) { g_trace = (unsigned long long*) d_trace; }
+
+/* ------------------------------------------------------------------ lights */
+
+struct voxgpu_lights
+{
+    int device;
+    float4 *buf;
+    DevLights ref;
+};
+
+extern "C" voxgpu_lights* voxgpu_lights_upload (const voxgpu_lights_flat *f)
+{
+    if (!f) { fail ("voxgpu_lights_upload: NULL argument"); return NULL; }
+    voxgpu_lights *l = (voxgpu_lights*) calloc (1, sizeof *l);
+    const size_t n4 = 2 * ((size_t) f->n_nodes + f->n_spheres);
+    float4 *host = (float4*) malloc ((n4 ? n4 : 1) * sizeof (float4));
+    for (uint32_t i=0; i<f->n_nodes; i++)
+    {
+        host[2*i] = make_float4 (f->node_bounds[4*i], f->node_bounds[4*i+1], f->node_bounds[4*i+2], f->node_bounds[4*i+3]);
+        memcpy (&host[2*i+1], f->node_link + 4*i, sizeof (float4));
+    }
+    float4 *sph = host + 2 * (size_t) f->n_nodes;
+    for (uint32_t i=0; i<f->n_spheres; i++)
+    {
+        memcpy (&sph[2*i], f->sphere_geom + 4*i, sizeof (float4));
+        memcpy (&sph[2*i+1], f->sphere_light + 4*i, sizeof (float4));
+    }
+    cudaError_t e;
+    if ((e = cudaGetDevice (&l->device)) != cudaSuccess ||
+        (e = cudaMalloc (&l->buf, (n4 ? n4 : 1) * sizeof (float4))) != cudaSuccess ||
+        (e = cudaMemcpy (l->buf, host, n4 * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess)
+    {
+        fail ("voxgpu_lights_upload: %s", cudaGetErrorString (e));
+        free (host); cudaFree (l->buf); free (l);
+        return NULL;
+    }
+    free (host);
+    l->ref.nodes = l->buf;
+    l->ref.spheres = l->buf + 2 * (size_t) f->n_nodes;
+    l->ref.n_nodes = f->n_nodes;
+    l->ref.ar = f->ambient[0]; l->ref.ag = f->ambient[1]; l->ref.ab = f->ambient[2];
+    return l;
+}
+
+extern "C" void voxgpu_lights_free (voxgpu_lights *l)
+{
+    if (!l) return;
+    cudaFree (l->buf);
+    free (l);
+}
 
 extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
 extern "C" void voxgpu_set_refill_min (int n) { g_refill_min = n < 1 ? 1 : (n > 32 ? 32 : n); }
@@ -1049,13 +1162,18 @@ static unsigned* counter_slot (int device)
         if (cudaMemset (p, 0, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
         int sms = 0, b0 = 0, b1 = 0;
         cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false, RENDER_STRIPS>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false, RENDER_STRIPS, false>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true, RENDER_STRIPS, false>, RENDER_BLOCK, 0);
         g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
         g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
         int b2 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true, false>, RENDER_BLOCK, 0);
         g_render_blocks[device][2] = sms * (b2 > 0 ? b2 : 1);
+        int b5 = 0, b6 = 0;     /* with a light manager attached */
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b5, k_render_persistent<true, RENDER_STRIPS, true>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b6, k_render_blocks<true, true>, RENDER_BLOCK, 0);
+        g_render_blocks[device][5] = sms * (b5 > 0 ? b5 : 1);
+        g_render_blocks[device][6] = sms * (b6 > 0 ? b6 : 1);
         int b3 = 0, b4 = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b3, k_render_stream<false, RENDER_STRIPS>, RENDER_BLOCK, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b4, k_render_stream<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
@@ -1170,6 +1288,13 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
     df.amask = f->fmt.amask;
     df.rloss = f->fmt.rloss; df.gloss = f->fmt.gloss; df.bloss = f->fmt.bloss;
     df.rshift = f->fmt.rshift; df.gshift = f->fmt.gshift; df.bshift = f->fmt.bshift;
+    memset (&df.lt, 0, sizeof df.lt);
+    const bool lit = f->lights != NULL;
+    if (lit)
+    {
+        if (f->lights->device != t->device) return fail ("voxgpu_render: lights live on device %d, tree on %d", f->lights->device, t->device);
+        df.lt = f->lights->ref;
+    }
 
     const int ntiles = (df.w >> 3) * (df.rows >> 2);
     const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
@@ -1184,14 +1309,16 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
         const int warps = (((df.w >> 2) + 7) >> 3) * (((df.rows >> 2) + 3) >> 2);
         int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
-        const int cap = g_render_blocks[t->device][2];
+        const int cap = g_render_blocks[t->device][lit ? 6 : 2];
         if (grid > cap) grid = cap;
-        if (d_leaf || d_pts)
-            k_render_blocks<true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        if (lit)
+            k_render_blocks<true, true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        else if (d_leaf || d_pts)
+            k_render_blocks<true, false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
         else
-            k_render_blocks<false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters);
+            k_render_blocks<false, false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters);
     }
-    else if (g_variant == 0)
+    else if (g_variant == 0 && !lit)
     {
         if (d_leaf || d_pts)
             k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
@@ -1211,7 +1338,13 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         memset (&sch, 0, sizeof sch);
         if (sched && g_variant == 1 && sched->t_heavy &&
             sched_prepare (sched, t->device, df.w, df.y0, df.rows, st, &sch)) return -1;
-        if (g_variant >= 3)
+        if (lit)
+        {   /* light manager attached: the default kernel, shading through the flattened M-tree */
+            grid = g_render_blocks[t->device][5];
+            if (grid > blocks) grid = blocks;
+            k_render_persistent<true, RENDER_STRIPS, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
+        }
+        else if (g_variant >= 3)
         {   /* per-lane refill; g_variant - 2 = refill threshold when >= 3 ... */
             const int rmin = g_refill_min;
             grid = g_render_blocks[t->device][hits ? 4 : 3];
@@ -1221,13 +1354,13 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         }
         else if (g_variant == 2)
         {   /* raster tile order, kept for A/B measurements */
-            if (hits) k_render_persistent<true, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
-            else      k_render_persistent<false, 1u><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
+            if (hits) k_render_persistent<true, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
+            else      k_render_persistent<false, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
         }
         else
         {
-            if (hits) k_render_persistent<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
-            else      k_render_persistent<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
+            if (hits) k_render_persistent<true, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
+            else      k_render_persistent<false, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
         }
     }
     g_launches++;

@@ -40,4 +40,7 @@ struct vox_rnd_ctx_full
 
 void vox_default_texture (Uint8 *texture);
 
+/* lights.c: the light set as the render kernel reads it, on the current device */
+const voxgpu_lights* vox_light_manager_device (struct vox_light_manager *lm);
+
 #endif

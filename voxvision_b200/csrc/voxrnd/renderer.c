@@ -113,9 +113,8 @@ void vox_context_set_scene (struct vox_rnd_ctx *ctx, struct vox_node *scene)
 
 void vox_context_set_light_manager (struct vox_rnd_ctx *ctx, struct vox_light_manager *light_manager)
 {
-    /* lights (renderer.c:42-50, lights.c) are out of scope: only NULL is honoured */
-    if (light_manager) vox_set_error ("light managers are not supported; rendering without lights");
-    ctx->light_manager = NULL;
+    /* renderer.c:173-177; NULL detaches */
+    ctx->light_manager = light_manager;
 }
 
 int vox_context_set_quality (struct vox_rnd_ctx *pub, unsigned int quality)
@@ -227,6 +226,13 @@ void vox_render (struct vox_rnd_ctx *pub)
     fr.fmt.amask = s->format->Amask;
     fr.fmt.rloss = s->format->Rloss; fr.fmt.gloss = s->format->Gloss; fr.fmt.bloss = s->format->Bloss;
     fr.fmt.rshift = s->format->Rshift; fr.fmt.gshift = s->format->Gshift; fr.fmt.bshift = s->format->Bshift;
+
+    if (pub->light_manager)
+    {
+        /* renderer.c:41-49: the kernel shades through a flattened copy of the manager's M-tree */
+        fr.lights = vox_light_manager_device (pub->light_manager);
+        if (!fr.lights) return;
+    }
 
     if (voxgpu_present_render (ctx->present, tree, &cam, &fr, ctx->d_texture, s->pixels, (size_t) s->pitch))
     { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
