@@ -49,8 +49,8 @@ BYTES_INNER, BYTES_LEAF, BYTES_DENSE, BYTES_DOT, BYTES_PIXEL = 48, 32, 32, 16, 4
 METRIC = "Mrays/s primary-ray render (skull 1080p)"
 GATHER_BATCH = 8          # frames per NCCL gather
 RING = 2 * GATHER_BATCH   # device framebuffers per rank
-FRAME_STREAMS = 4         # frames in flight per GPU (independent frames of the scripted path)
-E2E_CONTEXTS = int(os.environ.get("VOX_E2E_CONTEXTS", "4"))          # render contexts (host surfaces) taking the frames round-robin in the e2e leg
+FRAME_STREAMS = int(os.environ.get("VOX_FRAME_STREAMS", "4"))         # frames in flight per GPU (independent frames of the scripted path)
+E2E_CONTEXTS = int(os.environ.get("VOX_E2E_CONTEXTS", "6"))          # render contexts (host surfaces) taking the frames round-robin in the e2e leg
 
 
 def rank_env():

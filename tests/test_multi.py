@@ -74,6 +74,17 @@ def worker(rank, world, port, out_dir):
         if rank == 0:
             assert torch.equal(res, torch.arange(n, dtype=torch.int64) * 3)
 
+        # tree replication: built on rank 0, broadcast as flat arrays, imported everywhere
+        import voxvision_b200 as vv
+        from tools import datasets as ds
+        vox = ds.random_voxels(side=24, p=0.2)[0]
+        flat = vv.Tree.build(vox).export() if rank == 0 else None
+        got = multi.broadcast_flat_tree(flat, src=0)
+        mine = vv.Tree.build(vox).export()
+        for k, _, _ in multi.FLAT_KEYS:
+            assert np.array_equal(np.asarray(got[k]).view(np.uint8), np.asarray(mine[k]).view(np.uint8)), k
+        assert vv.Tree.from_arrays(got).voxels() == len(vox)
+
         slowest = multi.max_over_ranks(1.0 + rank)
         assert slowest == float(world)
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()

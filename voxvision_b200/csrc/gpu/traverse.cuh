@@ -542,7 +542,10 @@ __device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool 
 
 #define VOXGPU_FULL 0xffffffffu
 #define VOXGPU_DEAD 0xffffffffu
-#define VOXGPU_COOP_MAX_LANES 12     /* more lanes than this at a leaf: everyone loops over its own voxels */
+#ifndef VOXGPU_COOP_MAX_LANES
+#define VOXGPU_COOP_MAX_LANES 8      /* more lanes than this at a leaf: everyone loops over its own voxels
+                                        (C2, tools/ab_variants.sh: 8 -> 12.54, 12 -> 12.48, 16 -> 12.40 Grays/s) */
+#endif
 
 /*
  * One lane's search state between node visits.  `cur` is the node of the pending call

@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "voxgpu.h"
 #include "traverse.cuh"
@@ -303,8 +304,14 @@ static int check_tree (const voxgpu_tree *t, uint32_t start_node, const char *wh
 
 #define RAYS_BLOCK 128
 
+/* Resident CTAs per SM for K2.  C3 (tools/ab_rays.sh): 7 (66 registers) 1446 Mrays/s, 8 (64 registers,
+   40 bytes spilled) 1558, 9 1493, 10 1503, 12 1414: the random rays of C3 wait on HBM, one more CTA of
+   latency hiding pays for the spill. */
+#ifndef VOXGPU_RAYS_MIN_BLOCKS
+#define VOXGPU_RAYS_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(RAYS_BLOCK)
+__global__ void __launch_bounds__(RAYS_BLOCK, VOXGPU_RAYS_MIN_BLOCKS)
 k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const float4 * __restrict__ dirs,
         size_t n, int * __restrict__ leaf_ids, float4 * __restrict__ points, int * __restrict__ voxels,
         unsigned long long *stats)
@@ -372,40 +379,126 @@ extern "C" int voxgpu_rays_stats (const voxgpu_tree *t, uint32_t start, const fl
     return 0;
 }
 
+/* ------------------------------------------------- queries with HOST buffers
+ *
+ * What vox_ray_tree_intersection[_batch] / vox_tree_ball_collidep[_batch] call.  The caller's
+ * arrays are ordinary pageable memory, so a batch moves through a per-device pipeline of
+ * HP_SLOTS chunks: the host threads copy chunk c into page-locked staging (OpenMP, one memcpy per
+ * thread), the stream of its slot runs H2D copy -> kernel -> D2H copy, and while the device works
+ * on chunk c the host drains chunk c-1 from staging into the caller's arrays (hit points only
+ * where there is a hit: "res is written only on a hit", search.h:24-26).  Staging and device
+ * scratch live as long as the process: a single query (n = 1) costs two small copies and a
+ * launch, no allocation.
+ */
+#define HP_SLOTS 3
+#define HP_CHUNK (1u << 20)        /* queries per chunk */
+
+struct HostSlot
+{
+    cudaStream_t st;
+    cudaEvent_t done;
+    char *h_in, *h_out;            /* page-locked: 32 B in, 24 B out per query */
+    char *d_in, *d_out;
+};
+
+struct HostPipe
+{
+    int ready;
+    std::mutex lock;
+    HostSlot slot[HP_SLOTS];
+};
+static HostPipe g_pipe[64];
+
+static int pipe_get (int device, HostPipe **out)
+{
+    HostPipe *p = &g_pipe[device];
+    if (!p->ready)
+    {
+        for (int i=0; i<HP_SLOTS; i++)
+        {
+            HostSlot &s = p->slot[i];
+            CU (cudaStreamCreateWithFlags (&s.st, cudaStreamNonBlocking));
+            CU (cudaEventCreateWithFlags (&s.done, cudaEventDisableTiming));
+            CU (cudaHostAlloc (&s.h_in, (size_t) HP_CHUNK * 32, cudaHostAllocDefault));
+            CU (cudaHostAlloc (&s.h_out, (size_t) HP_CHUNK * 24, cudaHostAllocDefault));
+            CU (cudaMalloc (&s.d_in, (size_t) HP_CHUNK * 32));
+            CU (cudaMalloc (&s.d_out, (size_t) HP_CHUNK * 24));
+        }
+        p->ready = 1;
+    }
+    *out = p;
+    return 0;
+}
+
+/* memcpy spread over the host threads (a single thread moves ~10 GB/s, PCIe 5 x16 carries 55) */
+static void par_copy (void *dst, const void *src, size_t bytes)
+{
+    const size_t piece = 1u << 20;
+    const long pieces = (long) ((bytes + piece - 1) / piece);
+    if (pieces <= 2) { memcpy (dst, src, bytes); return; }
+    #pragma omp parallel for schedule(static)
+    for (long i=0; i<pieces; i++)
+    {
+        const size_t off = (size_t) i * piece;
+        memcpy ((char*) dst + off, (const char*) src + off, bytes - off < piece ? bytes - off : piece);
+    }
+}
+
 extern "C" int voxgpu_rays_host (const voxgpu_tree *t, uint32_t start, const float *o, const float *d, size_t n,
                                  int32_t *leaf, float *pts, int32_t *vox, long *n_hits)
 {
     if (check_tree (t, start, "voxgpu_rays_host")) return -1;
     if (n_hits) *n_hits = 0;
     if (n == 0) return 0;
-    float4 *d_o = NULL, *d_d = NULL, *d_p = NULL;
-    int *d_l = NULL, *d_v = NULL;
-    int rc = -1;
-    cudaError_t e = cudaSuccess;
-    int32_t *tmp_leaf = NULL;
-    if ((e = cudaMalloc (&d_o, n * sizeof (float4))) != cudaSuccess) goto done;
-    if ((e = cudaMalloc (&d_d, n * sizeof (float4))) != cudaSuccess) goto done;
-    if ((e = cudaMalloc (&d_l, n * sizeof (int))) != cudaSuccess) goto done;
-    if (pts && (e = cudaMalloc (&d_p, n * sizeof (float4))) != cudaSuccess) goto done;
-    if (vox && (e = cudaMalloc (&d_v, n * sizeof (int))) != cudaSuccess) goto done;
-    if ((e = cudaMemcpy (d_o, o, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
-    if ((e = cudaMemcpy (d_d, d, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
-    /* points are only written on a hit: start from the caller's contents */
-    if (pts && (e = cudaMemcpy (d_p, pts, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
-    if (voxgpu_rays_device (t, start, (float*) d_o, (float*) d_d, n, d_l, (float*) d_p, d_v, NULL)) goto cleanup;
-    if (!leaf && n_hits) leaf = tmp_leaf = (int32_t*) malloc (n * sizeof (int32_t));
-    if (leaf && (e = cudaMemcpy (leaf, d_l, n * sizeof (int), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
-    if (pts && (e = cudaMemcpy (pts, d_p, n * sizeof (float4), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
-    if (vox && (e = cudaMemcpy (vox, d_v, n * sizeof (int), cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
-    if ((e = cudaDeviceSynchronize ()) != cudaSuccess) goto done;
-    if (n_hits && leaf) { long h = 0; for (size_t i=0; i<n; i++) h += leaf[i] >= 0; *n_hits = h; }
-    rc = 0;
-done:
-    if (e != cudaSuccess) fail ("voxgpu_rays_host: %s", cudaGetErrorString (e));
-cleanup:
-    free (tmp_leaf);
-    cudaFree (d_o); cudaFree (d_d); cudaFree (d_p); cudaFree (d_l); cudaFree (d_v);
-    return rc;
+    HostPipe *p;
+    if (pipe_get (t->device, &p)) return -1;
+    std::lock_guard<std::mutex> guard (p->lock);
+
+    const size_t chunks = (n + HP_CHUNK - 1) / HP_CHUNK;
+    long hits = 0;
+    for (size_t c = 0; c <= chunks; c++)
+    {
+        if (c < chunks)
+        {
+            /* stage A: chunk c goes to the device (its slot was drained two iterations ago) */
+            HostSlot &s = p->slot[c % HP_SLOTS];
+            const size_t lo = c * HP_CHUNK, m = (n - lo < HP_CHUNK) ? n - lo : HP_CHUNK;
+            par_copy (s.h_in, o + 4*lo, m * 16);
+            par_copy (s.h_in + (size_t) HP_CHUNK * 16, d + 4*lo, m * 16);
+            float4 *d_o = (float4*) s.d_in, *d_d = (float4*) (s.d_in + (size_t) HP_CHUNK * 16);
+            float4 *d_p = (float4*) s.d_out;
+            int *d_l = (int*) (s.d_out + (size_t) HP_CHUNK * 16), *d_v = (int*) (s.d_out + (size_t) HP_CHUNK * 20);
+            CU (cudaMemcpyAsync (d_o, s.h_in, m * 16, cudaMemcpyHostToDevice, s.st));
+            CU (cudaMemcpyAsync (d_d, s.h_in + (size_t) HP_CHUNK * 16, m * 16, cudaMemcpyHostToDevice, s.st));
+            if (voxgpu_rays_device (t, start, (float*) d_o, (float*) d_d, m, d_l, pts ? (float*) d_p : NULL, vox ? d_v : NULL, s.st)) return -1;
+            if (pts) CU (cudaMemcpyAsync (s.h_out, d_p, m * 16, cudaMemcpyDeviceToHost, s.st));
+            CU (cudaMemcpyAsync (s.h_out + (size_t) HP_CHUNK * 16, d_l, m * 4, cudaMemcpyDeviceToHost, s.st));
+            if (vox) CU (cudaMemcpyAsync (s.h_out + (size_t) HP_CHUNK * 20, d_v, m * 4, cudaMemcpyDeviceToHost, s.st));
+            CU (cudaEventRecord (s.done, s.st));
+        }
+        if (c > 0)
+        {
+            /* stage B: chunk c-1 comes back while the device works on chunk c */
+            HostSlot &s = p->slot[(c - 1) % HP_SLOTS];
+            const size_t lo = (c - 1) * HP_CHUNK, m = (n - lo < HP_CHUNK) ? n - lo : HP_CHUNK;
+            CU (cudaEventSynchronize (s.done));
+            const int32_t *h_l = (const int32_t*) (s.h_out + (size_t) HP_CHUNK * 16);
+            const float4 *h_p = (const float4*) s.h_out;
+            if (leaf) par_copy (leaf + lo, h_l, m * 4);
+            if (vox) par_copy (vox + lo, s.h_out + (size_t) HP_CHUNK * 20, m * 4);
+            long h = 0;
+            if (pts || n_hits)
+            {
+                float4 *out_p = (float4*) pts + lo;
+                #pragma omp parallel for schedule(static) reduction(+:h) if (m > 65536)
+                for (long i=0; i<(long) m; i++)
+                    if (h_l[i] >= 0) { h++; if (pts) out_p[i] = h_p[i]; }
+            }
+            hits += h;
+        }
+    }
+    if (n_hits) *n_hits = hits;
+    return 0;
 }
 
 /* --------------------------------------------------------------- K3: balls */
@@ -442,24 +535,40 @@ extern "C" int voxgpu_balls_host (const voxgpu_tree *t, const float *c, const fl
     if (check_tree (t, 0, "voxgpu_balls_host")) return -1;
     if (n_hits) *n_hits = 0;
     if (n == 0) return 0;
-    float4 *d_c = NULL; float *d_r = NULL; unsigned char *d_o = NULL;
-    int rc = -1;
-    cudaError_t e;
-    if ((e = cudaMalloc (&d_c, n * sizeof (float4))) != cudaSuccess) goto done;
-    if ((e = cudaMalloc (&d_r, n * sizeof (float))) != cudaSuccess) goto done;
-    if ((e = cudaMalloc (&d_o, n)) != cudaSuccess) goto done;
-    if ((e = cudaMemcpy (d_c, c, n * sizeof (float4), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
-    if ((e = cudaMemcpy (d_r, r, n * sizeof (float), cudaMemcpyHostToDevice)) != cudaSuccess) goto done;
-    if (voxgpu_balls_device (t, (float*) d_c, d_r, n, d_o, NULL)) { e = cudaSuccess; goto cleanup; }
-    if ((e = cudaMemcpy (out, d_o, n, cudaMemcpyDeviceToHost)) != cudaSuccess) goto done;
-    if ((e = cudaDeviceSynchronize ()) != cudaSuccess) goto done;
-    if (n_hits) { long h = 0; for (size_t i=0; i<n; i++) h += out[i] != 0; *n_hits = h; }
-    rc = 0;
-done:
-    if (e != cudaSuccess) fail ("voxgpu_balls_host: %s", cudaGetErrorString (e));
-cleanup:
-    cudaFree (d_c); cudaFree (d_r); cudaFree (d_o);
-    return rc;
+    HostPipe *p;
+    if (pipe_get (t->device, &p)) return -1;
+    std::lock_guard<std::mutex> guard (p->lock);
+
+    /* the same pipeline as voxgpu_rays_host: 20 B in, 1 B out per ball */
+    const size_t chunks = (n + HP_CHUNK - 1) / HP_CHUNK;
+    long hits = 0;
+    for (size_t k = 0; k <= chunks; k++)
+    {
+        if (k < chunks)
+        {
+            HostSlot &s = p->slot[k % HP_SLOTS];
+            const size_t lo = k * HP_CHUNK, m = (n - lo < HP_CHUNK) ? n - lo : HP_CHUNK;
+            par_copy (s.h_in, c + 4*lo, m * 16);
+            par_copy (s.h_in + (size_t) HP_CHUNK * 16, r + lo, m * 4);
+            float4 *d_c = (float4*) s.d_in;
+            float *d_r = (float*) (s.d_in + (size_t) HP_CHUNK * 16);
+            CU (cudaMemcpyAsync (d_c, s.h_in, m * 16, cudaMemcpyHostToDevice, s.st));
+            CU (cudaMemcpyAsync (d_r, s.h_in + (size_t) HP_CHUNK * 16, m * 4, cudaMemcpyHostToDevice, s.st));
+            if (voxgpu_balls_device (t, (float*) d_c, d_r, m, (uint8_t*) s.d_out, s.st)) return -1;
+            CU (cudaMemcpyAsync (s.h_out, s.d_out, m, cudaMemcpyDeviceToHost, s.st));
+            CU (cudaEventRecord (s.done, s.st));
+        }
+        if (k > 0)
+        {
+            HostSlot &s = p->slot[(k - 1) % HP_SLOTS];
+            const size_t lo = (k - 1) * HP_CHUNK, m = (n - lo < HP_CHUNK) ? n - lo : HP_CHUNK;
+            CU (cudaEventSynchronize (s.done));
+            memcpy (out + lo, s.h_out, m);
+            if (n_hits) for (size_t i=0; i<m; i++) hits += s.h_out[i] != 0;
+        }
+    }
+    if (n_hits) *n_hits = hits;
+    return 0;
 }
 
 /* -------------------------------------------------------------- K1: render */
@@ -714,8 +823,14 @@ __global__ void k_sched_build (const unsigned char * __restrict__ cost_prev, int
     }
 }
 
+/* Resident CTAs per SM the compiler must allow for K1.  Measured on C2 (tools/ab_variants.sh):
+   7 (72 registers, what ptxas picks on its own) 12.31 Grays/s, 8 (61 registers, no spills) 12.48,
+   9 (56 registers, 12 bytes spilled) 12.01. */
+#ifndef VOXGPU_RENDER_MIN_BLOCKS
+#define VOXGPU_RENDER_MIN_BLOCKS 8
+#endif
 template <bool OUT_HITS, unsigned STRIPS, bool LIT>
-__global__ void __launch_bounds__(RENDER_BLOCK)
+__global__ void __launch_bounds__(RENDER_BLOCK, VOXGPU_RENDER_MIN_BLOCKS)
 k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
                      unsigned *counters, unsigned long long *trace, DevSched sch)

@@ -13,8 +13,46 @@ tree (built and uploaded locally) and works on
 
 Nothing here touches CUDA directly; tensors live wherever the caller put them.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
+
+FLAT_KEYS = (("bb_min", np.float32, 3), ("bb_max", np.float32, 3), ("flags", np.uint32, 1),
+             ("dots_num", np.uint32, 1), ("center", np.float32, 3), ("first_child", np.uint32, 1),
+             ("child_mask", np.uint32, 1), ("dots_off", np.uint64, 1), ("dots", np.float32, 3))
+
+
+def broadcast_flat_tree(flat, src=0, device="cpu"):
+    """Replicate a tree: `flat` (dict of arrays as Tree.export(), only needed on `src`) is broadcast to
+    every rank -- over NCCL when `device` is a CUDA device, the arrays staged through it -- and returned
+    as a dict of numpy arrays ready for Tree.from_arrays().  The tree is built ONCE (on src) instead of
+    once per rank; for C5 that is ~3 GB of arrays against ~30 s of building."""
+    rank = dist.get_rank()
+    sizes = torch.zeros(3, dtype=torch.int64, device=device)
+    if rank == src:
+        sizes = torch.tensor([flat["flags"].shape[0], flat["dots"].shape[0], int(flat.get("depth", 0))],
+                             dtype=torch.int64, device=device)
+    dist.broadcast(sizes, src)
+    n_nodes, n_dots, depth = (int(x) for x in sizes.tolist())
+    out = {"depth": depth}
+    for key, dtype, width in FLAT_KEYS:
+        rows = n_dots if key == "dots" else n_nodes
+        if rank == src:
+            host = np.ascontiguousarray(flat[key], dtype).reshape(-1)
+        else:
+            host = np.empty(rows * width, dtype)
+        # torch has no uint32/uint64 arithmetic needs here: ship the raw bytes
+        t = torch.from_numpy(host.view(np.uint8))
+        if str(device) != "cpu":
+            d = t.to(device)
+            dist.broadcast(d, src)
+            if rank != src:
+                t.copy_(d)
+            del d
+        else:
+            dist.broadcast(t, src)
+        out[key] = host.reshape(rows, width) if width > 1 else host
+    return out
 
 
 def split_range(n, rank, world):
