@@ -61,7 +61,19 @@ struct TreeRef
     const float4 *ctr;
     const float4 *dots;
     float vx, vy, vz;       /* vox_voxel captured at upload */
+    /* the first `ntop` nodes (breadth-first order = the top levels of the tree) staged in shared
+       memory by the kernel: 2 x float4 record + float4 centre per node; ntop = 0: nothing staged */
+    const float4 *top_rec, *top_ctr;
+    unsigned ntop;
 };
+
+/* Build-time knobs for A/B runs (tools/ab_variants.sh). */
+#ifndef VOXGPU_SMEM_TOP
+#define VOXGPU_SMEM_TOP 0          /* nodes staged per CTA by the render kernel: 73 = levels 0-2, 585 = levels 0-3 */
+#endif
+#ifndef VOXGPU_PREFETCH
+#define VOXGPU_PREFETCH 0          /* prefetch.global.L1 of the child a lane descends into */
+#endif
 
 /* one 32-byte node record with a single 256-bit read-only load */
 __device__ __forceinline__ void load_rec (const NodeRec *p, float4 &lo, float4 &hi)
@@ -589,7 +601,13 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
     {
         /* ---- one call: vox_ray_tree_intersection (cur, org, d) ---- */
         float4 q0, q1;
+#if VOXGPU_SMEM_TOP
+        const bool top = s.cur < tr.ntop;
+        if (top) { q0 = tr.top_rec[2*s.cur]; q1 = tr.top_rec[2*s.cur + 1]; }
+        else load_rec (tr.rec + s.cur, q0, q1);
+#else
         load_rec (tr.rec + s.cur, q0, q1);
+#endif
         const unsigned meta = __float_as_uint (q0.w);
         const unsigned link = __float_as_uint (q1.w);
         const unsigned kind = meta & 3u;
@@ -601,9 +619,22 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
         {
             if (kind == VOXGPU_KIND_INNER)
             {
+#if VOXGPU_SMEM_TOP
+                const V3 c = v3 (top ? tr.top_ctr[s.cur] : __ldg (tr.ctr + s.cur));
+#else
                 const V3 c = v3 (__ldg (tr.ctr + s.cur));
+#endif
                 const unsigned mask = (meta >> 8) & 0xffu;
                 const unsigned sub = subspace_fast (c, entry, k.nx, k.ny, k.nz);
+#if VOXGPU_PREFETCH
+                /* the child this lane descends into is known now; its record is needed at the top of
+                   the next iteration, after the pushes below and the leaf phase of the other lanes */
+                if ((mask >> sub) & 1u)
+                {
+                    const unsigned nxt = child_id (link, mask, sub);
+                    asm volatile ("prefetch.global.L1 [%0];" :: "l"(tr.rec + nxt));
+                }
+#endif
 
                 /* search.c:105-113: the three dividing planes, from the entry point */
                 V3 p0, p1, p2;

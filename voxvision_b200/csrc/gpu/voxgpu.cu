@@ -287,6 +287,8 @@ static TreeRef tree_ref (const voxgpu_tree *t)
     TreeRef r;
     r.rec = t->rec; r.ctr = t->ctr; r.dots = t->dots;
     r.vx = t->voxel[0]; r.vy = t->voxel[1]; r.vz = t->voxel[2];
+    r.top_rec = r.top_ctr = NULL;
+    r.ntop = t->n_nodes < VOXGPU_SMEM_TOP ? (unsigned) t->n_nodes : VOXGPU_SMEM_TOP;
     return r;
 }
 
@@ -841,6 +843,21 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
     const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
     float4 stack[VOXGPU_RAY_STACK];
     V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
+#if VOXGPU_SMEM_TOP
+    /* the top levels of the tree (breadth-first order: simply the first nodes), once per persistent CTA */
+    __shared__ float4 s_top[3 * VOXGPU_SMEM_TOP];
+    for (unsigned i = threadIdx.x; i < tr.ntop; i += RENDER_BLOCK)
+    {
+        float4 a, b;
+        load_rec (tr.rec + i, a, b);
+        s_top[2*i] = a; s_top[2*i + 1] = b;
+        s_top[2*VOXGPU_SMEM_TOP + i] = __ldg (tr.ctr + i);
+    }
+    __syncthreads ();
+    tr.top_rec = s_top; tr.top_ctr = s_top + 2*VOXGPU_SMEM_TOP;
+#else
+    tr.ntop = 0;
+#endif
 
     /* Tiles are handed out strip-interleaved: consecutive tickets land in
        RENDER_STRIPS different horizontal strips of the frame.  In raster order
