@@ -430,6 +430,11 @@ def run_own(args):
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": round(bytes_per_launch), "bytes_per_ray": round(bytes_per_launch / RAYS_PER_FRAME, 2),
                 "kernel_ms_mean": round(mean_kernel_ms, 5), "kernel_ms_min": round(float(np.min(kernel_ms)), 5),
+                "how": "achieved/frac: one launch at a time (CUDA events around each of 90 lone launches after the timed region); "
+                       "in_flight: the timed region itself, ms_per_step / launches with FRAME_STREAMS launches overlapping",
+                "in_flight": {"ms_per_launch": round(ms_total / args.steps / FRAMES, 5),
+                              "achieved": round(bytes_per_launch / (ms_total / args.steps / FRAMES * 1e-3) / 1e9, 2),
+                              "frac": round(bytes_per_launch / (ms_total / args.steps / FRAMES * 1e-3) / 1e9 / peak, 5)},
                 "note": "the 18 MB tree is L2-resident, so DRAM traffic is far below the algorithmic bytes; "
                         "the kernel is latency/issue bound (see profiles/)"}
     cpu_baseline = None

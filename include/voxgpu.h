@@ -106,6 +106,11 @@ typedef struct
     unsigned quality;            /* VOX_QUALITY_* bits, renderer.h:81-127 */
     voxgpu_pixfmt fmt;
     const voxgpu_lights *lights; /* NULL: unlit grey (renderer.c:38-39); else renderer.c:41-49 */
+    /* Multi-GPU screen split at the finest grain: with interleave_world = N > 1 the launch draws
+       only the 4-row tile rows r (counted from y0) with r % N == interleave_rank and leaves every
+       other pixel of the band untouched, so N GPUs writing into ONE frame buffer get statistically
+       identical shares of the image in one launch each.  0 / 1: the whole band.  Quality BEST only. */
+    int interleave_world, interleave_rank;
 } voxgpu_frame;
 
 /** Counters of the instrumented ("stats") variant of the ray kernel. */

@@ -346,6 +346,41 @@ def test_row_bands_tile_the_frame(gpu, skull, ds):
     assert b"row band" in api.libs.gpu.voxgpu_last_error()
 
 
+def test_interleaved_tile_rows_tile_the_frame(gpu, skull, ds):
+    """voxgpu_frame.interleave_*: N launches (one per GPU in the multi-GPU drivers), each drawing every
+    N-th 4-row tile row into the SAME buffer, give the frame one launch gives -- and a launch touches
+    nothing but its own rows."""
+    t = gpu.Tree.build(skull)
+    w, h = 640, 360
+    ctx = gpu.Context(w, h)
+    cam = ds.setup_camera(gpu.Camera(), *ds.orbit_pose(200), 1.2, w, h)
+    gc = cam.gpu_camera()
+    api = gpu.api
+    g = api.libs.gpu
+    d_tex = gpu.DeviceBuffer.from_array(ctx.texture())
+    full = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt(), want_hits=False)[0]
+    for world in (2, 3, 8):
+        d_pix = gpu.DeviceBuffer(w * h * 4)
+        g.voxgpu_memset(d_pix.ptr, 0x5a, w * h * 4, None)
+        for rank in range(world):
+            fr = api.GpuFrame(w, h, 0, h, w, 0, ctx.pixfmt(), None, world, rank)
+            assert g.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None) == 0
+            if rank == 0:
+                part = d_pix.download(np.uint32, (h, w))
+                rows = (np.arange(h) // 4) % world
+                assert np.array_equal(part[rows == 0], full[rows == 0])
+                assert (part[rows != 0] == 0x5a5a5a5a).all()
+        assert np.array_equal(d_pix.download(np.uint32, (h, w)), full)
+    # a band [y0, y1) interleaved: rows are counted from y0
+    d_pix = gpu.DeviceBuffer(w * 120 * 4)
+    for rank in range(2):
+        fr = api.GpuFrame(w, h, 120, 240, w, 0, ctx.pixfmt(), None, 2, rank)
+        assert g.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None) == 0
+    assert np.array_equal(d_pix.download(np.uint32, (120, w)), full[120:240])
+    fr = api.GpuFrame(w, h, 0, h, w, 2, ctx.pixfmt(), None, 2, 0)       # not with the block-sequential modes
+    assert g.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None) != 0
+
+
 def test_foreign_camera_without_describe(gpu, checker, skull, ds):
     """A camera written against the reference's 10-slot vtable (no `describe`) still renders:
     its host screen2world is tabulated."""

@@ -45,6 +45,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--partition", default="interleave", choices=["interleave", "bands"],
+                    help="interleave: rank r draws the 4-row tile rows r, r+N, ... in ONE launch per frame "
+                         "(voxgpu_frame.interleave_*); bands: world*BANDS_PER_RANK row bands dealt round-robin")
+    ap.add_argument("--simulate", type=int, default=0,
+                    help="one GPU: time the share of each of N virtual ranks separately and report the balance")
     args = ap.parse_args()
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 
@@ -134,8 +139,15 @@ def main():
         else:
             g.voxgpu_synchronize(None)
 
-    def render_frame(k):
-        for i, (y0, y1) in enumerate(bands):
+    def render_frame(k, vrank=rank, vworld=world):
+        if args.partition == "interleave":
+            fr = api.GpuFrame(W, H, 0, H, W, vv.QUALITY_BEST, fmt, None, vworld, vrank)
+            rc = g.voxgpu_render(dev_tree, C.byref(gcams[k]), C.byref(fr), d_tex.ptr, base, None, None, streams[k % STREAMS])
+            if rc:
+                raise vv.VoxError(g.voxgpu_last_error().decode())
+            return
+        my = bands if vworld == world else multi.interleaved_bands(H, vworld, BANDS_PER_RANK)[vrank]
+        for i, (y0, y1) in enumerate(my):
             fr = api.GpuFrame(W, H, y0, y1, W, vv.QUALITY_BEST, fmt, None)
             rc = g.voxgpu_render(dev_tree, C.byref(gcams[k]), C.byref(fr), d_tex.ptr, base + y0 * W * 4, None, None,
                                  streams[i % STREAMS])
@@ -151,6 +163,27 @@ def main():
             g.voxgpu_stream_join(s0, st)
 
     timer = vv.Timer()
+    if args.simulate > 1 and world == 1:
+        # balance of an N-way split, measured on one GPU: each virtual rank's share of every frame, alone
+        for part in ("interleave", "bands"):
+            args.partition = part
+            per_rank = []
+            for vr in range(args.simulate):
+                for k in range(args.frames):
+                    render_frame(k, vr, args.simulate)
+                g.voxgpu_synchronize(None)
+                timer.start(s0)
+                for st in streams[1:]:
+                    g.voxgpu_stream_join(st, s0)
+                for k in range(args.frames):
+                    render_frame(k, vr, args.simulate)
+                for st in streams[1:]:
+                    g.voxgpu_stream_join(s0, st)
+                timer.stop(s0)
+                per_rank.append(timer.elapsed_ms())
+            print(json.dumps({"simulate": args.simulate, "partition": part, "ms_per_rank": [round(x, 3) for x in per_rank],
+                              "balance_mean_over_max": round(float(np.mean(per_rank) / np.max(per_rank)), 4)}), flush=True)
+        return
     for _ in range(max(args.warmup, 1)):
         step()
     sync_all()
@@ -222,8 +255,10 @@ def main():
         "ms_per_frame": round(ms / args.steps / args.frames, 4), "higher_is_better": True, "scaling": "strong", "dtype": "f32",
         "data": f"synthetic: union of {args.balls} balls with 1-in-8 hash holes in a {args.side}^3 grid, {n_vox} voxels",
         "config": {"workload": f"C5: {W}x{H}, {args.frames} poses of the scaled orbit, quality BEST, simple-camera",
-                   "partition": f"{world * BANDS_PER_RANK} row bands dealt round-robin over {world} GPU(s), tree replicated "
-                                f"(built on rank 0, broadcast over NCCL), frame buffer on GPU 0 ({mode})",
+                   "partition": (f"tile rows interleaved over {world} GPU(s) (rank r draws rows r, r+{world}, ...; one launch per frame)"
+                                 if args.partition == "interleave" else
+                                 f"{world * BANDS_PER_RANK} row bands dealt round-robin over {world} GPU(s)") +
+                                f", tree replicated (built on rank 0, broadcast over NCCL), frame buffer on GPU 0 ({mode})",
                    "tree": {"nodes": int(ti.n_nodes), "inner": int(ti.n_inner), "leaf": int(ti.n_leaf), "dense": int(ti.n_dense),
                             "dots": int(ti.n_dots), "depth": int(ti.depth), "device_bytes": tree_bytes},
                    "host_seconds": {"generate": round(t_gen, 1), "vox_make_tree": round(t_build, 1), "replicate": round(t_repl, 1)},

@@ -6,7 +6,7 @@ rate through the host-buffer C API (copies inside the timed region), algorithmic
 from the instrumented traversal, and the reference's CPU code on a bounded sample on all host
 threads.  Prints one JSON line per config.
 
-    python tools/configs_bench.py [c1] [c3] [c4]
+    python tools/configs_bench.py [c1] [c3] [c4] [modes]
 """
 import ctypes as C
 import json
@@ -84,6 +84,36 @@ def c1():
             "device": round(W * H / mean / 1e3, 1), "kernel_ms": round(mean, 4), "kernel_ms_min": round(best, 4),
             "e2e_vox_render_redraw": round(W * H / e2e / 1e6, 1),
             "cpu": {"value": round(W * H / cpu / 1e6, 1), "threads": THREADS, "oracle": O.name, "sample": "the same frame, best of 5"}}
+
+
+def modes():
+    """C2 frames in the reference's other quality modes (ADAPTIVE is its default, renderer.c:78)."""
+    W, H = 1920, 1080
+    vox = ds.volume_voxels("skull")
+    tree = vv.Tree.build(vox)
+    dev = tree.device_handle()
+    ctx = vv.Context(W, H)
+    d_tex, d_pix = vv.DeviceBuffer.from_array(ctx.texture()), vv.DeviceBuffer(W * H * 4)
+    cam = vv.Camera()
+    O = cpu_oracle()
+    ot = O.tree(vox)
+    frames = [0, 90, 180, 270]
+    out = {"config": "C2 frames 0/90/180/270 per quality mode (device-resident kernel; CPU = same mode, all threads)", "unit": "Mrays/s"}
+    for name, q in (("best", 0), ("fast", 1), ("adaptive", 2), ("adaptive+merge", 6)):
+        ms, cpu = [], []
+        for f in frames:
+            ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
+            gc = cam.gpu_camera()
+            fr = api.GpuFrame(W, H, 0, H, W, q, ctx.pixfmt(), None)
+            run = lambda: g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None)
+            run(); run()
+            ms.append(timed(run, 9)[0])
+            ocam = ds.setup_camera(O.camera(0), *ds.orbit_pose(f), 1.2, W, H)
+            ot.render(ocam, W, H, q, threads=THREADS, want_hits=False)
+            cpu.append(min(_t(lambda: ot.render(ocam, W, H, q, threads=THREADS, want_hits=False)) for _ in range(3)))
+        out[name] = {"device": round(W * H / np.mean(ms) / 1e3, 1), "kernel_ms": round(float(np.mean(ms)), 4),
+                     "cpu": round(W * H / np.mean(cpu) / 1e6, 1)}
+    return out
 
 
 def _t(fn):
@@ -164,4 +194,4 @@ if __name__ == "__main__":
     vv.set_device(0)
     which = [a.lower() for a in sys.argv[1:]] or ["c1", "c3", "c4"]
     for name in which:
-        print(json.dumps({"c1": c1, "c3": c3, "c4": c4}[name]()), flush=True)
+        print(json.dumps({"c1": c1, "c3": c3, "c4": c4, "modes": modes}[name]()), flush=True)

@@ -100,7 +100,8 @@ class GpuPixFmt(C.Structure):
 
 class GpuFrame(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("pitch_pixels", C.c_int),
-                ("quality", C.c_uint), ("fmt", GpuPixFmt), ("lights", C.c_void_p)]
+                ("quality", C.c_uint), ("fmt", GpuPixFmt), ("lights", C.c_void_p),
+                ("interleave_world", C.c_int), ("interleave_rank", C.c_int)]
 
 
 class GpuLightsFlat(C.Structure):

@@ -65,6 +65,7 @@ struct TreeRef
        memory by the kernel: 2 x float4 record + float4 centre per node; ntop = 0: nothing staged */
     const float4 *top_rec, *top_ctr;
     unsigned ntop;
+    unsigned ntop_avail;    /* min (nodes in the tree, VOXGPU_SMEM_TOP): what a kernel may stage */
 };
 
 /* Build-time knobs for A/B runs (tools/ab_variants.sh). */

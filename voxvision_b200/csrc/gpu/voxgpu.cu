@@ -288,7 +288,11 @@ static TreeRef tree_ref (const voxgpu_tree *t)
     r.rec = t->rec; r.ctr = t->ctr; r.dots = t->dots;
     r.vx = t->voxel[0]; r.vy = t->voxel[1]; r.vz = t->voxel[2];
     r.top_rec = r.top_ctr = NULL;
-    r.ntop = t->n_nodes < VOXGPU_SMEM_TOP ? (unsigned) t->n_nodes : VOXGPU_SMEM_TOP;
+    r.ntop = 0;
+    r.ntop_avail = 0;
+#if VOXGPU_SMEM_TOP
+    r.ntop_avail = t->n_nodes < VOXGPU_SMEM_TOP ? (unsigned) t->n_nodes : VOXGPU_SMEM_TOP;
+#endif
     return r;
 }
 
@@ -604,6 +608,7 @@ struct DevFrame
     unsigned amask;
     unsigned char rloss, gloss, bloss, rshift, gshift, bshift;
     DevLights lt;
+    int il_world, il_rank;          /* this launch draws the 4-row tile rows r with r % il_world == il_rank */
 };
 
 /* vect-ops.c:8-16 vox_cross_product */
@@ -838,7 +843,10 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
                      unsigned *counters, unsigned long long *trace, DevSched sch)
 {
     const int tiles_x = fr.w >> 3;
-    const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
+    /* tile rows of the band this launch owns (all of them unless the frame is interleaved over GPUs) */
+    const int band_rows = fr.rows >> 2;
+    const int own_rows = fr.il_rank < band_rows ? (band_rows - fr.il_rank + fr.il_world - 1) / fr.il_world : 0;
+    const unsigned ntiles = (unsigned) (tiles_x * own_rows);
     const int lane = threadIdx.x & 31;
     const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
     float4 stack[VOXGPU_RAY_STACK];
@@ -846,7 +854,7 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
 #if VOXGPU_SMEM_TOP
     /* the top levels of the tree (breadth-first order: simply the first nodes), once per persistent CTA */
     __shared__ float4 s_top[3 * VOXGPU_SMEM_TOP];
-    for (unsigned i = threadIdx.x; i < tr.ntop; i += RENDER_BLOCK)
+    for (unsigned i = threadIdx.x; i < tr.ntop_avail; i += RENDER_BLOCK)
     {
         float4 a, b;
         load_rec (tr.rec + i, a, b);
@@ -854,9 +862,7 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         s_top[2*VOXGPU_SMEM_TOP + i] = __ldg (tr.ctr + i);
     }
     __syncthreads ();
-    tr.top_rec = s_top; tr.top_ctr = s_top + 2*VOXGPU_SMEM_TOP;
-#else
-    tr.ntop = 0;
+    tr.top_rec = s_top; tr.top_ctr = s_top + 2*VOXGPU_SMEM_TOP; tr.ntop = tr.ntop_avail;
 #endif
 
     /* Tiles are handed out strip-interleaved: consecutive tickets land in
@@ -888,7 +894,7 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         unsigned long long t0 = 0;
         if (trace) t0 = globaltimer_ns ();
         const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
-        const int ry = (int) (tile / tiles_x) * 4 + (lane >> 3);
+        const int ry = ((int) (tile / tiles_x) * fr.il_world + fr.il_rank) * 4 + (lane >> 3);
         const int sy = fr.y0 + ry;
         const V3 dir = screen2world (cam, sx, sy, fr.w);
         RayResult r;
@@ -1421,6 +1427,11 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
     df.rloss = f->fmt.rloss; df.gloss = f->fmt.gloss; df.bloss = f->fmt.bloss;
     df.rshift = f->fmt.rshift; df.gshift = f->fmt.gshift; df.bshift = f->fmt.bshift;
     memset (&df.lt, 0, sizeof df.lt);
+    df.il_world = f->interleave_world > 1 ? f->interleave_world : 1;
+    df.il_rank = f->interleave_world > 1 ? f->interleave_rank : 0;
+    if (df.il_rank < 0 || df.il_rank >= df.il_world) return fail ("voxgpu_render: interleave rank %d of %d", df.il_rank, df.il_world);
+    if (df.il_world > 1 && ((f->quality & 3u) != 0u || g_variant == 0 || g_variant >= 3))
+        return fail ("voxgpu_render: interleaved tile rows need quality BEST and the default kernel variant");
     const bool lit = f->lights != NULL;
     if (lit)
     {
@@ -1468,7 +1479,7 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         float4 *pts = (float4*) d_pts;
         DevSched sch;
         memset (&sch, 0, sizeof sch);
-        if (sched && g_variant == 1 && sched->t_heavy &&
+        if (sched && g_variant == 1 && sched->t_heavy && df.il_world == 1 &&
             sched_prepare (sched, t->device, df.w, df.y0, df.rows, st, &sch)) return -1;
         if (lit)
         {   /* light manager attached: the default kernel, shading through the flattened M-tree */
