@@ -1068,11 +1068,20 @@ __device__ __forceinline__ float sqr_norm3 (const V3 a)
     return __fadd_rn (__fadd_rn (__fmul_rn (a.x, a.x), __fmul_rn (a.y, a.y)), __fmul_rn (a.z, a.z));
 }
 
-template <bool OUT_HITS, bool LIT>
+/*
+ * FAST / ADAPTIVE (+ ray merge), renderer.c:240-316: one lane owns one 4x4 block and walks its 16 pixels in
+ * the reference's Z-order, because pixel i+1 is first searched inside the leaf pixel i ended in.  Only that
+ * in-leaf search depends on the previous pixel; the search from the ROOT it falls back to (and the two corner
+ * rays of ADAPTIVE) is a pure function of the pixel.  PRE = true: those root searches were done for every
+ * pixel of the band by the pixel-parallel BEST kernel in a launch before this one (pre_leaf / pre_pts, dense
+ * w-pitch), and the walk only looks them up; what is left to do sequentially is one node visit per pixel.
+ * PRE = false is the single-launch form (every search inside the walk, 1/16 of the parallelism).
+ */
+template <bool OUT_HITS, bool LIT, bool PRE>
 __global__ void __launch_bounds__(RENDER_BLOCK)
 k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const unsigned char * __restrict__ tex,
                  unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
-                 unsigned *counters)
+                 unsigned *counters, const int * __restrict__ pre_leaf, const float4 * __restrict__ pre_pts)
 {
     const int bw = fr.w >> 2, bh = fr.rows >> 2;               /* 4x4 blocks */
     const int tiles_x = (bw + 7) >> 3, tiles_y = (bh + 3) >> 2;
@@ -1137,7 +1146,18 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
             RayResult r;
             r.leaf = -1;
             V3 dir = origin;
-            if (__any_sync (0xffffffffu, want))
+            if (PRE && !phase_leaf)
+            {
+                /* a search from the root: done already, for this very ray */
+                if (want)
+                {
+                    if (step < 2) dir = screen2world (cam, px, fr.y0 + py, fr.w);     /* the corner criterion needs it */
+                    const size_t pos = (size_t) py * fr.w + px;
+                    r.leaf = pre_leaf[pos];
+                    if (r.leaf >= 0) { const float4 q = pre_pts[pos]; r.point.x = q.x; r.point.y = q.y; r.point.z = q.z; }
+                }
+            }
+            else if (__any_sync (0xffffffffu, want))
             {
                 dir = screen2world (cam, valid ? px : 0, fr.y0 + (valid ? py : 0), fr.w);
                 ray_tree_warp (tr, start, origin, dir, want, stack, r);
@@ -1305,11 +1325,11 @@ static unsigned* counter_slot (int device)
         g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
         g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
         int b2 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true, false>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true, false, false>, RENDER_BLOCK, 0);
         g_render_blocks[device][2] = sms * (b2 > 0 ? b2 : 1);
         int b5 = 0, b6 = 0;     /* with a light manager attached */
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b5, k_render_persistent<true, RENDER_STRIPS, true>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b6, k_render_blocks<true, true>, RENDER_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b6, k_render_blocks<true, true, false>, RENDER_BLOCK, 0);
         g_render_blocks[device][5] = sms * (b5 > 0 ? b5 : 1);
         g_render_blocks[device][6] = sms * (b6 > 0 ? b6 : 1);
         int b3 = 0, b4 = 0;
@@ -1317,6 +1337,13 @@ static unsigned* counter_slot (int device)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b4, k_render_stream<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
         g_render_blocks[device][3] = sms * (b3 > 0 ? b3 : 1);
         g_render_blocks[device][4] = sms * (b4 > 0 ? b4 : 1);
+        /* stream-ordered scratch (cudaMallocAsync in voxgpu_render): keep freed blocks in the pool */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool (&pool, device) == cudaSuccess)
+        {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         g_counters[device] = p;
     }
     return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
@@ -1454,12 +1481,44 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
         int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
         const int cap = g_render_blocks[t->device][lit ? 6 : 2];
         if (grid > cap) grid = cap;
-        if (lit)
-            k_render_blocks<true, true><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
-        else if (d_leaf || d_pts)
-            k_render_blocks<true, false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters);
+        cudaStream_t st = (cudaStream_t) s;
+        const bool hits = d_leaf || d_pts;
+        static const bool onepass = getenv ("VOXGPU_BLOCKS_ONEPASS") && atoi (getenv ("VOXGPU_BLOCKS_ONEPASS"));
+        int *pre_leaf = NULL;
+        float4 *pre_pts = NULL;
+        if (!onepass)
+        {
+            /* launch 1: every root search of the band, pixel-parallel (K1 as for BEST), into stream-ordered scratch */
+            const size_t npix = (size_t) df.w * df.rows;
+            CU (cudaMallocAsync (&pre_leaf, npix * sizeof (int), st));
+            CU (cudaMallocAsync (&pre_pts, npix * sizeof (float4), st));
+            unsigned *c1 = counter_slot (t->device);
+            if (!c1) return fail ("voxgpu_render: cannot allocate tile counters");
+            int g1 = g_render_blocks[t->device][1];
+            if (g1 > blocks) g1 = blocks;
+            DevSched none;
+            memset (&none, 0, sizeof none);
+            DevFrame plain = df;
+            memset (&plain.lt, 0, sizeof plain.lt);
+            k_render_persistent<true, RENDER_STRIPS, false><<<g1, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, plain, d_tex, d_pixels, pre_leaf, pre_pts, c1, NULL, none);
+            g_launches++;
+            /* launch 2: the walk, looking those results up */
+            if (lit)
+                k_render_blocks<true, true, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, pre_leaf, pre_pts);
+            else if (hits)
+                k_render_blocks<true, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, pre_leaf, pre_pts);
+            else
+                k_render_blocks<false, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters, pre_leaf, pre_pts);
+            CU (cudaGetLastError ());
+            CU (cudaFreeAsync (pre_leaf, st));
+            CU (cudaFreeAsync (pre_pts, st));
+        }
+        else if (lit)
+            k_render_blocks<true, true, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, NULL, NULL);
+        else if (hits)
+            k_render_blocks<true, false, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, NULL, NULL);
         else
-            k_render_blocks<false, false><<<grid, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters);
+            k_render_blocks<false, false, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters, NULL, NULL);
     }
     else if (g_variant == 0 && !lit)
     {
