@@ -196,6 +196,11 @@ def main():
     if world > 1:
         ms = multi.max_over_ranks(ms, device="cuda")
 
+    # Frames of the timed region overlap on different streams and share the one frame buffer; for the
+    # check every rank draws its share of the LAST pose once more, alone.
+    render_frame(args.frames - 1)
+    sync_all()
+
     # ---- checks and roofline bookkeeping (rank 0) ----------------------------------------------
     check = None
     bytes_per_ray = None

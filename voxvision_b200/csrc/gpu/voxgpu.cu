@@ -415,9 +415,12 @@ struct HostPipe
 };
 static HostPipe g_pipe[64];
 
+static std::mutex g_pipe_init;
+
 static int pipe_get (int device, HostPipe **out)
 {
     HostPipe *p = &g_pipe[device];
+    std::lock_guard<std::mutex> guard (g_pipe_init);
     if (!p->ready)
     {
         for (int i=0; i<HP_SLOTS; i++)
