@@ -251,6 +251,15 @@ VOXGPU_EXPORT void voxgpu_set_variant (int variant);
 /** Variant 3: refill a warp as soon as this many of its 32 lanes are idle (1..32). */
 VOXGPU_EXPORT void voxgpu_set_refill_min (int lanes);
 
+/** Screen-space culling of tiles that cannot see the tree's root box (on by default; also
+    $VOXGPU_NO_CULL=1).  Results do not depend on it: it only skips rays the search would reject at
+    the root.  Kept switchable for A/B runs and for the test that proves the independence. */
+VOXGPU_EXPORT void voxgpu_set_cull (int on);
+/** The bounds that culling uses (host arithmetic, no device needed): out = {x0, x1, y0, y1}, pixels outside
+    [x0,x1) x [y0,y1) of a w x h frame cannot see the box; the whole frame if the camera gives no bounds. */
+VOXGPU_EXPORT void voxgpu_screen_bounds (const float root_min[3], const float root_max[3], const voxgpu_camera *camera,
+                                         int w, int h, int out[4]);
+
 /** Development trace: when non-NULL, every following voxgpu_render launch (persistent
     variants) records per 8x4 tile {start ns, end ns, smid<<32 | warp} (3 x uint64 per
     tile of the launch's band, device memory supplied by the caller).  NULL switches it off. */

@@ -381,6 +381,48 @@ def test_interleaved_tile_rows_tile_the_frame(gpu, skull, ds):
     assert g.voxgpu_render(t.device_handle(), C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None) != 0
 
 
+@pytest.mark.parametrize("camera", ["simple-camera", "doom-camera"])
+def test_root_box_culling_changes_nothing(gpu, checker, skull, ds, camera):
+    """Tiles outside the screen bounds of the root box are cleared without casting their rays
+    (screen_bounds in voxgpu.cu).  Random poses -- far, near, inside the volume, rolled, looking away,
+    narrow and wide fov: the frame, the leaf ids and the hit points must not depend on the switch, and
+    must equal the oracle's."""
+    t = gpu.Tree.build(skull)
+    otree = checker.tree(skull)
+    w, h = 320, 160
+    ctx = gpu.Context(w, h)
+    g = gpu.api.libs.gpu
+    g.voxgpu_set_cull.argtypes = [C.c_int]
+    rng = np.random.default_rng(11)
+    kind = 0 if camera == "simple-camera" else 1
+    culled_something = 0
+    try:
+        for trial in range(24):
+            dist = [600.0, 330.0, 200.0, 140.0, 60.0, 0.0][trial % 6]
+            v = rng.normal(size=3)
+            pos = 128 + dist * v / np.linalg.norm(v) + rng.normal(size=3) * 3
+            look = 128 + rng.normal(size=3) * (40 if trial % 4 else 400)
+            fov = [0.3, 1.2, 2.5][trial % 3]
+            cam, ocam = gpu.Camera(camera), checker.camera(kind)
+            rot = [float(x) for x in rng.normal(size=3) * (0.5 if trial % 2 else 0.0)]
+            for c_ in (cam, ocam):
+                ds.setup_camera(c_, pos, look, fov, w, h)
+                c_.rotate(rot)
+            g.voxgpu_set_cull(1)
+            on = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+            g.voxgpu_set_cull(0)
+            off = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+            assert np.array_equal(on[0], off[0]) and np.array_equal(on[1], off[1]), trial
+            m = off[1] >= 0
+            assert np.array_equal(bits(on[2][m]), bits(off[2][m])), trial
+            opix, oleaf, _ = otree.render(ocam, w, h, 0, ctx.texture(), threads=THREADS)
+            assert np.array_equal(on[0], opix) and np.array_equal(on[1], oleaf), trial
+            culled_something += int((~m).any())
+    finally:
+        g.voxgpu_set_cull(1)
+    assert culled_something > 5
+
+
 def test_foreign_camera_without_describe(gpu, checker, skull, ds):
     """A camera written against the reference's 10-slot vtable (no `describe`) still renders:
     its host screen2world is tabulated."""

@@ -254,3 +254,47 @@ def test_product_never_touches_the_oracle(vv):
                 assert "orc_" not in text and "libvoxoracle" not in text and "libvoxref" not in text, f
                 if f.endswith(".py"):
                     assert "import orc" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.parametrize("kind,name", [(0, "simple-camera"), (1, "doom-camera")])
+def test_screen_bounds_contain_every_hit_pixel(vv, port, skull, ds, kind, name):
+    """voxgpu_screen_bounds (the render kernel clears tiles outside it without casting their rays):
+    over random poses, no pixel whose ray the ORACLE lets into the root box -- let alone one that hits
+    a voxel -- may lie outside the bounds.  Host arithmetic only."""
+    import ctypes as C
+    g = vv.libs.gpu
+    g.voxgpu_screen_bounds.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(vv.api.GpuCamera), C.c_int, C.c_int, C.c_void_p]
+    # the root box alone as a tree: every ray that enters the box hits it (a dense leaf)
+    bb_min, bb_max = skull.min(0), skull.max(0) + 1
+    box = port.tree_from_flat({"bb_min": bb_min[None].astype(np.float32), "bb_max": bb_max[None].astype(np.float32),
+                               "flags": np.array([2], np.uint32), "dots_num": np.array([1], np.uint32),
+                               "center": np.zeros((1, 3), np.float32), "first_child": np.zeros(1, np.uint32),
+                               "child_mask": np.zeros(1, np.uint32), "dots_off": np.zeros(1, np.uint64),
+                               "dots": np.zeros((0, 3), np.float32)})
+    w, h = 160, 96
+    rng = np.random.default_rng(5 + kind)
+    bounded = 0
+    for trial in range(int(os.environ.get("VOX_BOUNDS_TRIALS", "60"))):
+        dist = [900.0, 400.0, 250.0, 170.0, 90.0, 0.0][trial % 6]
+        v = rng.normal(size=3)
+        pos = 128 + dist * v / np.linalg.norm(v) + rng.normal(size=3) * 3
+        look = 128 + rng.normal(size=3) * (60 if trial % 4 else 500)
+        fov = [0.2, 1.2, 3.0][trial % 3]
+        cam, ocam = vv.Camera(name), port.camera(kind)
+        rot = [float(x) for x in rng.normal(size=3) * (0.7 if trial % 2 else 0.0)]
+        for c_ in (cam, ocam):
+            ds.setup_camera(c_, pos, look, fov, w, h)
+            c_.rotate(rot)
+        gc = cam.gpu_camera()
+        out = (C.c_int * 4)()
+        mn, mx = np.ascontiguousarray(bb_min, np.float32), np.ascontiguousarray(bb_max, np.float32)
+        g.voxgpu_screen_bounds(mn.ctypes.data, mx.ctypes.data, C.byref(gc), w, h, out)
+        x0, x1, y0, y1 = list(out)
+        o, d = ocam.rays(w, h)
+        leaf, _, _ = box.rays(o, d)
+        enters = (leaf >= 0).reshape(h, w)
+        inside = np.zeros((h, w), bool)
+        inside[y0:y1, x0:x1] = True
+        assert not (enters & ~inside).any(), (trial, list(out))
+        bounded += int((x1 - x0) * (y1 - y0) < w * h)
+    assert bounded > 15          # the bounds do bite in many poses (VOX_BOUNDS_TRIALS=1500 was run once: no escape)

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <math.h>
 #include <atomic>
 #include <mutex>
 
@@ -178,7 +179,13 @@ struct voxgpu_tree
     float4 *ctr;     /* 16 B per node: split centre (inner nodes) */
     float4 *dots;
     float voxel[3];
+    float root_min[3], root_max[3];   /* host copy of node 0's box, for screen-space culling */
+    /* a cut through the tree for the screen mask (k_mark): every node of one level plus the leaves
+       above it, so that every voxel lies in the box of exactly one node of the cut */
+    unsigned *cut;
+    unsigned n_cut, cut_level;
 };
+#define VOXGPU_CUT_MAX 131072u
 
 extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
 {
@@ -191,6 +198,8 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
 
     voxgpu_tree *t = (voxgpu_tree*) calloc (1, sizeof *t);
     t->n_nodes = f->n_nodes; t->n_dots = f->n_dots; t->depth = f->depth;
+    memcpy (t->root_min, f->bb_min, sizeof t->root_min);
+    memcpy (t->root_max, f->bb_max, sizeof t->root_max);
     memcpy (t->voxel, f->voxel, sizeof t->voxel);
     if (cudaGetDevice (&t->device) != cudaSuccess) { fail ("no CUDA device: %s", cudaGetErrorString (cudaGetLastError ())); free (t); return NULL; }
 
@@ -257,13 +266,46 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
              (e = cudaStreamSynchronize (s)) != cudaSuccess))
         { fail ("voxgpu_tree_upload: dots copy: %s", cudaGetErrorString (e)); goto bad; }
     }
+    {
+        /* levels from the breadth-first links; the deepest level whose cut stays below VOXGPU_CUT_MAX nodes */
+        unsigned char *level = (unsigned char*) malloc (f->n_nodes);
+        uint64_t at[VOXGPU_MAX_DEPTH + 2] = {0}, leaves[VOXGPU_MAX_DEPTH + 2] = {0};
+        level[0] = 0;
+        for (uint64_t id=0; id<f->n_nodes; id++)
+        {
+            const unsigned l = level[id];
+            at[l]++;
+            if (f->flags[id] & 3u) { leaves[l]++; continue; }
+            const int nc = __builtin_popcount (f->child_mask[id] & 0xffu);
+            for (int j=0; j<nc; j++) level[f->first_child[id] + j] = (unsigned char) (l + 1);
+        }
+        unsigned best = 0;
+        uint64_t above = 0;
+        for (unsigned l=0; l<f->depth && l <= VOXGPU_MAX_DEPTH; l++)
+        {
+            if (at[l] + above <= VOXGPU_CUT_MAX) best = l;
+            above += leaves[l];
+        }
+        unsigned *ids = (unsigned*) stage_v;        /* n_cut <= VOXGPU_CUT_MAX entries fit any staging buffer >= 512 KB? no: size it */
+        unsigned n = 0;
+        unsigned *tmp = (unsigned*) malloc ((size_t) VOXGPU_CUT_MAX * sizeof (unsigned));
+        for (uint64_t id=0; id<f->n_nodes && n < VOXGPU_CUT_MAX; id++)
+            if (level[id] == best || (level[id] < best && (f->flags[id] & 3u))) tmp[n++] = (unsigned) id;
+        (void) ids;
+        free (level);
+        t->n_cut = n; t->cut_level = best;
+        if ((e = cudaMalloc (&t->cut, (size_t) (n ? n : 1) * sizeof (unsigned))) != cudaSuccess ||
+            (e = cudaMemcpy (t->cut, tmp, (size_t) n * sizeof (unsigned), cudaMemcpyHostToDevice)) != cudaSuccess)
+        { free (tmp); fail ("voxgpu_tree_upload: cut copy: %s", cudaGetErrorString (e)); goto bad; }
+        free (tmp);
+    }
     cudaFreeHost (stage_v);
     cudaStreamDestroy (s);
     return t;
 bad:
     if (stage_v) cudaFreeHost (stage_v);
     if (s) cudaStreamDestroy (s);
-    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots);
+    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut);
     free (t);
     return NULL;
 }
@@ -274,7 +316,7 @@ extern "C" void voxgpu_tree_free (voxgpu_tree *t)
     int cur = -1;
     cudaGetDevice (&cur);
     if (cur != t->device) cudaSetDevice (t->device);
-    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots);
+    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut);
     if (cur != t->device && cur >= 0) cudaSetDevice (cur);
     free (t);
 }
@@ -612,6 +654,13 @@ struct DevFrame
     unsigned char rloss, gloss, bloss, rshift, gshift, bshift;
     DevLights lt;
     int il_world, il_rank;          /* this launch draws the 4-row tile rows r with r % il_world == il_rank */
+    /* pixels outside [cx0, cx1) x [cy0, cy1) (frame coordinates) cannot see the tree's root box:
+       tiles entirely outside are only cleared (screen_bounds) */
+    int cx0, cx1, cy0, cy1;
+    /* screen mask (k_mark): one byte per 8x4 tile of the whole frame, 0 = no voxel can project into
+       the tile; mask[mask_tiles] is the "no bounds this frame" flag.  NULL: not in use */
+    const unsigned char *mask;
+    int mask_tiles;
 };
 
 /* vect-ops.c:8-16 vox_cross_product */
@@ -899,6 +948,21 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
         const int ry = ((int) (tile / tiles_x) * fr.il_world + fr.il_rank) * 4 + (lane >> 3);
         const int sy = fr.y0 + ry;
+        {
+            /* the whole 8x4 tile lies outside the root box's screen bounds: every ray misses
+               (search.c:22-27 at the root), the pixels are the zeros of vox_redraw's memset */
+            const int tx0 = sx - (lane & 7), ty0 = sy - (lane >> 3);
+            bool dark = tx0 >= fr.cx1 || tx0 + 8 <= fr.cx0 || ty0 >= fr.cy1 || ty0 + 4 <= fr.cy0;
+            if (!dark && fr.mask)
+                dark = !__ldg (fr.mask + (size_t) (ty0 >> 2) * tiles_x + (tx0 >> 3)) && !__ldg (fr.mask + fr.mask_tiles);
+            if (dark)
+            {
+                pixels[(size_t) ry * fr.pitch + sx] = 0u;
+                if (OUT_HITS && leaf_ids) leaf_ids[(size_t) ry * fr.w + sx] = -1;
+                if (sch.cost_next && lane == 0) sch.cost_next[tile] = 0;
+                continue;
+            }
+        }
         const V3 dir = screen2world (cam, sx, sy, fr.w);
         RayResult r;
         const int iterations = ray_tree_warp (tr, 0, origin, dir, true, stack, r);
@@ -1425,6 +1489,71 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
                                     const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                                     voxgpu_stream s, voxgpu_sched *sched);
 
+/*
+ * Screen-space bounds of the tree's root box for a pinhole camera: a primary ray through pixel
+ * (sx, sy) can only hit the box if (sx, sy) lies in the convex hull of the projections of the
+ * box's corners, because every point of the box in front of the camera projects into that hull
+ * and all points of a ray project onto its pixel.  The bounding rectangle of the eight projected
+ * corners, widened by 2 pixels -- three orders of magnitude more than fp32 rounding can move
+ * the reference's hit_box decision (geom.c:69-99) -- therefore contains every pixel whose ray the
+ * reference lets into the tree.  If a corner is not safely in front of the camera there are no
+ * bounds.  Projection = the inverse of screen2world (simple-camera.c:21-31, doom-camera.c:36-57),
+ * in double.
+ */
+static int g_cull = !(getenv ("VOXGPU_NO_CULL") && atoi (getenv ("VOXGPU_NO_CULL")));
+extern "C" void voxgpu_set_cull (int on) { g_cull = on != 0; }
+
+extern "C" void voxgpu_screen_bounds (const float root_min[3], const float root_max[3], const voxgpu_camera *c,
+                                      int w, int h, int out[4])
+{
+    out[0] = 0; out[1] = w; out[2] = 0; out[3] = h;
+    if ((c->kind != VOXGPU_CAMERA_SIMPLE && c->kind != VOXGPU_CAMERA_DOOM) || !(c->mul > 0.0f)) return;
+    double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 };
+    for (int k=0; k<8; k++)
+    {
+        const double p[3] = { (double) ((k & 1) ? root_max[0] : root_min[0]) - c->position[0],
+                              (double) ((k & 2) ? root_max[1] : root_min[1]) - c->position[1],
+                              (double) ((k & 4) ? root_max[2] : root_min[2]) - c->position[2] };
+        double v[3];
+        if (c->kind == VOXGPU_CAMERA_SIMPLE)
+        {
+            /* rotate by the conjugate quaternion: v = p + w*t' + u x t', t' = 2 (u x p), u = -q.ijk */
+            const double qw = c->rotation[0], u[3] = { -(double) c->rotation[1], -(double) c->rotation[2], -(double) c->rotation[3] };
+            const double n2 = qw*qw + u[0]*u[0] + u[1]*u[1] + u[2]*u[2];
+            if (!(n2 > 0.9999 && n2 < 1.0001)) return;       /* not a rotation: no claim */
+            const double tt[3] = { 2*(u[1]*p[2] - u[2]*p[1]), 2*(u[2]*p[0] - u[0]*p[2]), 2*(u[0]*p[1] - u[1]*p[0]) };
+            v[0] = p[0] + qw*tt[0] + (u[1]*tt[2] - u[2]*tt[1]);
+            v[1] = p[1] + qw*tt[1] + (u[2]*tt[0] - u[0]*tt[2]);
+            v[2] = p[2] + qw*tt[2] + (u[0]*tt[1] - u[1]*tt[0]);
+        }
+        else
+        {
+            /* doom: dir = (x cos - y sin, y cos + x sin, z) with ray = (x, 1, z + k): undo the yaw */
+            const double cs = c->cosphi, sn = c->sinphi;
+            const double n2 = cs*cs + sn*sn;
+            if (!(n2 > 0.9999 && n2 < 1.0001)) return;
+            v[0] = p[0]*cs + p[1]*sn;
+            v[1] = p[1]*cs - p[0]*sn;
+            v[2] = p[2];
+        }
+        const double depth = v[1];
+        const double scale = fabs (p[0]) + fabs (p[1]) + fabs (p[2]);
+        if (!(depth > 1e-3 * scale) || !(depth > 0.0)) return;           /* beside or behind the camera: no bounds */
+        const double rx = v[0] / depth, rz = v[2] / depth - (c->kind == VOXGPU_CAMERA_DOOM ? (double) c->k : 0.0);
+        const double sx = (rx + c->xsub) / c->mul, sy = (c->ysub - rz) / c->mul;
+        if (!(fabs (sx) < 1e8) || !(fabs (sy) < 1e8)) return;
+        if (sx < lo[0]) lo[0] = sx;
+        if (sx > hi[0]) hi[0] = sx;
+        if (sy < lo[1]) lo[1] = sy;
+        if (sy > hi[1]) hi[1] = sy;
+    }
+    const double x0 = floor (lo[0]) - 2, x1 = ceil (hi[0]) + 3, y0 = floor (lo[1]) - 2, y1 = ceil (hi[1]) + 3;
+    out[0] = x0 < 0 ? 0 : (x0 > w ? w : (int) x0);
+    out[1] = x1 < 0 ? 0 : (x1 > w ? w : (int) x1);
+    out[2] = y0 < 0 ? 0 : (y0 > h ? h : (int) y0);
+    out[3] = y1 < 0 ? 0 : (y1 > h ? h : (int) y1);
+}
+
 extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                               const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                               voxgpu_stream s)
@@ -1457,6 +1586,11 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
     df.rloss = f->fmt.rloss; df.gloss = f->fmt.gloss; df.bloss = f->fmt.bloss;
     df.rshift = f->fmt.rshift; df.gshift = f->fmt.gshift; df.bshift = f->fmt.bshift;
     memset (&df.lt, 0, sizeof df.lt);
+    {
+        int cull[4] = { 0, f->w, 0, f->h };
+        if (g_cull) voxgpu_screen_bounds (t->root_min, t->root_max, c, f->w, f->h, cull);
+        df.cx0 = cull[0]; df.cx1 = cull[1]; df.cy0 = cull[2]; df.cy1 = cull[3];
+    }
     df.il_world = f->interleave_world > 1 ? f->interleave_world : 1;
     df.il_rank = f->interleave_world > 1 ? f->interleave_rank : 0;
     if (df.il_rank < 0 || df.il_rank >= df.il_world) return fail ("voxgpu_render: interleave rank %d of %d", df.il_rank, df.il_world);
