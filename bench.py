@@ -50,6 +50,7 @@ METRIC = "Mrays/s primary-ray render (skull 1080p)"
 GATHER_BATCH = 8          # frames per NCCL gather
 RING = 2 * GATHER_BATCH   # device framebuffers per rank
 FRAME_STREAMS = int(os.environ.get("VOX_FRAME_STREAMS", "4"))         # frames in flight per GPU (independent frames of the scripted path)
+SHORT = bool(int(os.environ.get("VOX_BENCH_SHORT", "0")))   # profiling runs: skip the CPU baseline, one e2e pass
 E2E_CONTEXTS = int(os.environ.get("VOX_E2E_CONTEXTS", "6"))          # render contexts (host surfaces) taking the frames round-robin in the e2e leg
 
 
@@ -399,6 +400,8 @@ def run_own(args):
 
     e2e_steps = max(1, min(args.steps, 3))
     ring = [make_ctx() for _ in range(E2E_CONTEXTS)]
+    if SHORT:       # under ncu: one pass of each leg is enough for the launch list
+        e2e_steps = 1
     e2e_single_s = time_e2e(ring[:1], e2e_steps)
     e2e_s = time_e2e(ring, e2e_steps)
     if vv.last_error():
@@ -438,7 +441,7 @@ def run_own(args):
                 "note": "the 18 MB tree is L2-resident, so DRAM traffic is far below the algorithmic bytes; "
                         "the kernel is latency/issue bound (see profiles/)"}
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and not SHORT:
         O, kind = pick_cpu_oracle(orc)
         sample = list(range(0, FRAMES, 10))
         rate, secs = cpu_render_rate(ds, O, sample, 5, threads)

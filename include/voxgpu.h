@@ -251,9 +251,11 @@ VOXGPU_EXPORT void voxgpu_set_variant (int variant);
 /** Variant 3: refill a warp as soon as this many of its 32 lanes are idle (1..32). */
 VOXGPU_EXPORT void voxgpu_set_refill_min (int lanes);
 
-/** Screen-space culling of tiles that cannot see the tree's root box (on by default; also
-    $VOXGPU_NO_CULL=1).  Results do not depend on it: it only skips rays the search would reject at
-    the root.  Kept switchable for A/B runs and for the test that proves the independence. */
+/** Screen-space culling of 8x4 tiles that cannot show a voxel.  1 (default): the bounds of the tree's
+    root box AND a per-launch screen mask marked from the boxes of a cut through the tree (k_mark);
+    2: the root-box bounds only; 0: none ($VOXGPU_NO_CULL=1, $VOXGPU_NO_MASK=1 set the start-up value).
+    Results do not depend on it: it only skips rays whose search would come back empty.  Kept
+    switchable for A/B runs and for the tests that prove the independence. */
 VOXGPU_EXPORT void voxgpu_set_cull (int on);
 /** The bounds that culling uses (host arithmetic, no device needed): out = {x0, x1, y0, y1}, pixels outside
     [x0,x1) x [y0,y1) of a w x h frame cannot see the box; the whole frame if the camera gives no bounds. */

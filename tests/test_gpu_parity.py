@@ -408,8 +408,11 @@ def test_root_box_culling_changes_nothing(gpu, checker, skull, ds, camera):
             for c_ in (cam, ocam):
                 ds.setup_camera(c_, pos, look, fov, w, h)
                 c_.rotate(rot)
-            g.voxgpu_set_cull(1)
+            g.voxgpu_set_cull(2)                         # root-box bounds only
+            mid = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+            g.voxgpu_set_cull(1)                         # + the screen mask from the tree's cut
             on = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
+            assert np.array_equal(on[0], mid[0]) and np.array_equal(on[1], mid[1]), trial
             g.voxgpu_set_cull(0)
             off = render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt())
             assert np.array_equal(on[0], off[0]) and np.array_equal(on[1], off[1]), trial

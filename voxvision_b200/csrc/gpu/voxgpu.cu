@@ -286,12 +286,10 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
             if (at[l] + above <= VOXGPU_CUT_MAX) best = l;
             above += leaves[l];
         }
-        unsigned *ids = (unsigned*) stage_v;        /* n_cut <= VOXGPU_CUT_MAX entries fit any staging buffer >= 512 KB? no: size it */
         unsigned n = 0;
         unsigned *tmp = (unsigned*) malloc ((size_t) VOXGPU_CUT_MAX * sizeof (unsigned));
         for (uint64_t id=0; id<f->n_nodes && n < VOXGPU_CUT_MAX; id++)
             if (level[id] == best || (level[id] < best && (f->flags[id] & 3u))) tmp[n++] = (unsigned) id;
-        (void) ids;
         free (level);
         t->n_cut = n; t->cut_level = best;
         if ((e = cudaMalloc (&t->cut, (size_t) (n ? n : 1) * sizeof (unsigned))) != cudaSuccess ||
@@ -661,6 +659,7 @@ struct DevFrame
        the tile; mask[mask_tiles] is the "no bounds this frame" flag.  NULL: not in use */
     const unsigned char *mask;
     int mask_tiles;
+    unsigned mask_epoch;            /* a tile is marked iff its byte equals this (buffers are reused without clearing) */
 };
 
 /* vect-ops.c:8-16 vox_cross_product */
@@ -954,7 +953,8 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
             const int tx0 = sx - (lane & 7), ty0 = sy - (lane >> 3);
             bool dark = tx0 >= fr.cx1 || tx0 + 8 <= fr.cx0 || ty0 >= fr.cy1 || ty0 + 4 <= fr.cy0;
             if (!dark && fr.mask)
-                dark = !__ldg (fr.mask + (size_t) (ty0 >> 2) * tiles_x + (tx0 >> 3)) && !__ldg (fr.mask + fr.mask_tiles);
+                dark = __ldg (fr.mask + (size_t) (ty0 >> 2) * tiles_x + (tx0 >> 3)) != fr.mask_epoch &&
+                       __ldg (fr.mask + fr.mask_tiles) != fr.mask_epoch;
             if (dark)
             {
                 pixels[(size_t) ry * fr.pitch + sx] = 0u;
@@ -1485,6 +1485,78 @@ static int sched_prepare (voxgpu_sched *sc, int device, int w, int y0, int rows,
     return 0;
 }
 
+/*
+ * Screen mask.  Every voxel lies in the box of one node of the tree's cut (voxgpu_tree.cut); a ray that
+ * hits the voxel passes through that box, so its pixel lies in the convex hull of the box's projected
+ * corners (see voxgpu_screen_bounds for the argument) and therefore in their bounding rectangle.  One
+ * thread per cut node projects its box (fp32 here: the error is ~1e-3 pixel, the rectangle is widened by 2)
+ * and marks the 8x4 tiles the rectangle touches.  A tile nobody marked cannot show a voxel: the render
+ * kernel clears it without casting its rays -- on a C2 frame half of the primary rays enter the root box
+ * but only a fifth hit a voxel, and the ones in between cost 40-50 % of all node fetches.
+ * A box not safely in front of the camera, or covering more than 4096 tiles, raises the "no bounds"
+ * flag behind the mask instead (the frame is then rendered without the mask).
+ */
+__global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned n_cut, DevCamera cam,
+                        int w, int h, unsigned char * __restrict__ mask, int mask_tiles, unsigned char epoch)
+{
+    /* eight lanes per node, one per corner of its box; min/max over the eight by shuffles */
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = gid >> 3;
+    const int k = threadIdx.x & 7;
+    const bool live = i < n_cut;
+    float4 q0 = make_float4 (0, 0, 0, 0), q1 = q0;
+    if (live) load_rec (tr.rec + cut[i], q0, q1);
+    const float px = ((k & 1) ? q1.x : q0.x) - cam.px;
+    const float py = ((k & 2) ? q1.y : q0.y) - cam.py;
+    const float pz = ((k & 4) ? q1.z : q0.z) - cam.pz;
+    float vx, vy, vz;
+    if (cam.kind == VOXGPU_CAMERA_SIMPLE)
+    {
+        /* rotate by the conjugate quaternion */
+        const float ux = -cam.qi, uy = -cam.qj, uz = -cam.qk;
+        const float tx = 2.0f * (uy*pz - uz*py), ty = 2.0f * (uz*px - ux*pz), tz = 2.0f * (ux*py - uy*px);
+        vx = px + cam.qw*tx + (uy*tz - uz*ty);
+        vy = py + cam.qw*ty + (uz*tx - ux*tz);
+        vz = pz + cam.qw*tz + (ux*ty - uy*tx);
+    }
+    else
+    {
+        vx = px*cam.cosphi + py*cam.sinphi;
+        vy = py*cam.cosphi - px*cam.sinphi;
+        vz = pz;
+    }
+    const float scale = fabsf (px) + fabsf (py) + fabsf (pz);
+    bool bad = !(vy > 1e-3f * scale) || !(vy > 0.0f);
+    const float rz = vz / vy - (cam.kind == VOXGPU_CAMERA_DOOM ? cam.k : 0.0f);
+    const float sx = (vx / vy + cam.xsub) / cam.mul, sy = (cam.ysub - rz) / cam.mul;
+    bad = bad || !(fabsf (sx) < 1.0e7f) || !(fabsf (sy) < 1.0e7f);
+    float lox = bad ? 0.0f : sx, hix = lox, loy = bad ? 0.0f : sy, hiy = loy;
+    unsigned anybad = bad ? 1u : 0u;
+    #pragma unroll
+    for (int off = 4; off; off >>= 1)
+    {
+        lox = fminf (lox, __shfl_xor_sync (0xffffffffu, lox, off)); hix = fmaxf (hix, __shfl_xor_sync (0xffffffffu, hix, off));
+        loy = fminf (loy, __shfl_xor_sync (0xffffffffu, loy, off)); hiy = fmaxf (hiy, __shfl_xor_sync (0xffffffffu, hiy, off));
+        anybad |= __shfl_xor_sync (0xffffffffu, anybad, off);
+    }
+    if (!live) return;
+    if (!anybad)
+    {
+        const float x0 = floorf (lox) - 2.0f, x1 = ceilf (hix) + 3.0f, y0 = floorf (loy) - 2.0f, y1 = ceilf (hiy) + 3.0f;
+        if (x1 <= 0.0f || y1 <= 0.0f || x0 >= (float) w || y0 >= (float) h) return;       /* off screen */
+        const int tiles_x = w >> 3;
+        const int tx0 = max ((int) x0, 0) >> 3, tx1 = (min ((int) x1, w) + 7) >> 3;
+        const int ty0 = max ((int) y0, 0) >> 2, ty1 = (min ((int) y1, h) + 3) >> 2;
+        const int nx = tx1 - tx0, n = nx * (ty1 - ty0);
+        if (n <= 4096)
+        {
+            for (int j = k; j < n; j += 8) mask[(size_t) (ty0 + j / nx) * tiles_x + tx0 + j % nx] = epoch;
+            return;
+        }
+    }
+    if (k == 0) mask[mask_tiles] = epoch;   /* no bounds for this frame */
+}
+
 extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                                     const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                                     voxgpu_stream s, voxgpu_sched *sched);
@@ -1501,7 +1573,9 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
  * in double.
  */
 static int g_cull = !(getenv ("VOXGPU_NO_CULL") && atoi (getenv ("VOXGPU_NO_CULL")));
-extern "C" void voxgpu_set_cull (int on) { g_cull = on != 0; }
+static int g_mask = !(getenv ("VOXGPU_NO_MASK") && atoi (getenv ("VOXGPU_NO_MASK")));
+/* 0: no culling, 1: root-box bounds + screen mask (default), 2: root-box bounds only */
+extern "C" void voxgpu_set_cull (int on) { g_cull = on != 0; g_mask = on == 1; }
 
 extern "C" void voxgpu_screen_bounds (const float root_min[3], const float root_max[3], const voxgpu_camera *c,
                                       int w, int h, int out[4])
@@ -1561,9 +1635,67 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
     return voxgpu_render_sched (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, NULL);
 }
 
+/* Per-device ring of screen-mask buffers for launches that bring no mask of their own.  Launches rotate
+   through the slots like they do through the tile counters (launches in flight never share one unless more
+   than MASK_SLOTS are in flight).  A slot is never cleared between uses: "marked" is the slot's epoch value,
+   bumped per use, and the buffer is zeroed only when the epoch wraps or the slot grows. */
+#define MASK_SLOTS 64
+struct MaskSlot { unsigned char *buf; size_t cap; unsigned epoch; };
+static MaskSlot g_mask_slots[64][MASK_SLOTS];
+static std::atomic<unsigned> g_mask_seq{0};
+
+static unsigned char* mask_slot (int device, size_t bytes, cudaStream_t st, unsigned *epoch)
+{
+    MaskSlot &m = g_mask_slots[device][g_mask_seq++ % MASK_SLOTS];
+    if (m.cap < bytes)
+    {
+        if (m.buf) { cudaDeviceSynchronize (); cudaFree (m.buf); m.buf = NULL; m.cap = 0; }
+        if (cudaMalloc (&m.buf, bytes) != cudaSuccess) return NULL;
+        m.cap = bytes; m.epoch = 255;              /* forces the clear below */
+    }
+    if (++m.epoch > 255u)
+    {
+        m.epoch = 1;
+        if (cudaMemsetAsync (m.buf, 0, m.cap, st) != cudaSuccess) return NULL;
+    }
+    *epoch = m.epoch;
+    return m.buf;
+}
+
+static int mask_usable (const voxgpu_tree *t, const voxgpu_camera *c)
+{
+    return g_cull && g_mask && t->n_cut > 1 && (c->kind == VOXGPU_CAMERA_SIMPLE || c->kind == VOXGPU_CAMERA_DOOM) &&
+           c->mul > 0.0f && g_variant >= 1 && g_variant <= 2;
+}
+
+static DevCamera dev_camera (const voxgpu_camera *c)
+{
+    DevCamera dc;
+    dc.kind = c->kind;
+    dc.px = c->position[0]; dc.py = c->position[1]; dc.pz = c->position[2];
+    dc.mul = c->mul; dc.xsub = c->xsub; dc.ysub = c->ysub;
+    dc.qw = c->rotation[0]; dc.qi = c->rotation[1]; dc.qj = c->rotation[2]; dc.qk = c->rotation[3];
+    dc.sinphi = c->sinphi; dc.cosphi = c->cosphi; dc.k = c->k;
+    dc.table = (const float4*) c->dir_table;
+    return dc;
+}
+
+/* ext_mask / ext_epoch: a screen mask the caller has already marked for this frame (the presenter marks
+   one per frame and shares it between the bands); NULL: make one for this launch */
+static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                        const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                        voxgpu_stream s, voxgpu_sched *sched, const unsigned char *ext_mask, unsigned ext_epoch);
+
 extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                                     const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
                                     voxgpu_stream s, voxgpu_sched *sched)
+{
+    return render_impl (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, sched, NULL, 0);
+}
+
+static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                        const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                        voxgpu_stream s, voxgpu_sched *sched, const unsigned char *ext_mask, unsigned ext_epoch)
 {
     if (check_tree (t, 0, "voxgpu_render")) return -1;
     if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
@@ -1601,6 +1733,24 @@ extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c
     {
         if (f->lights->device != t->device) return fail ("voxgpu_render: lights live on device %d, tree on %d", f->lights->device, t->device);
         df.lt = f->lights->ref;
+    }
+
+    /* screen mask for this launch (stream-ordered scratch): clear, mark from the tree's cut, use, free */
+    unsigned char *mask = NULL;
+    df.mask = NULL; df.mask_tiles = 0; df.mask_epoch = 1;
+    if (ext_mask)
+    {
+        df.mask = ext_mask; df.mask_tiles = (f->w >> 3) * (f->h >> 2); df.mask_epoch = ext_epoch;
+    }
+    else if (mask_usable (t, c))
+    {
+        const int mtiles = (f->w >> 3) * (f->h >> 2);
+        unsigned epoch = 1;
+        mask = mask_slot (t->device, (size_t) mtiles + 4, (cudaStream_t) s, &epoch);
+        if (!mask) return fail ("voxgpu_render: cannot allocate the screen mask");
+        k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, (cudaStream_t) s>>> (tree_ref (t), t->cut, t->n_cut, dc, f->w, f->h, mask, mtiles, (unsigned char) epoch);
+        g_launches++;
+        df.mask = mask; df.mask_tiles = mtiles; df.mask_epoch = epoch;
     }
 
     const int ntiles = (df.w >> 3) * (df.rows >> 2);
@@ -1735,6 +1885,9 @@ struct voxgpu_present
     cudaEvent_t start;
     int in_flight;                        /* a frame has been queued and not yet waited for */
     int used_bands;                       /* bands of the frame in flight */
+    unsigned char *mask;                  /* screen mask shared by the bands of a frame (k_mark), w/8 * h/4 + 4 bytes */
+    unsigned epoch;                       /* value that means "marked" in the current frame: no clearing between frames */
+    cudaEvent_t marked;
     int fixed_bands;                      /* band count was asked for explicitly: never adapt */
 };
 
@@ -1754,7 +1907,9 @@ extern "C" void voxgpu_present_destroy (voxgpu_present *p)
         voxgpu_sched_destroy (p->sched[i]);
     }
     if (p->start) cudaEventDestroy (p->start);
+    if (p->marked) cudaEventDestroy (p->marked);
     if (p->in_flight) g_presents_in_flight--;
+    cudaFree (p->mask);
     cudaFree (p->fb);
     free (p);
 }
@@ -1779,6 +1934,9 @@ extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
     if ((e = cudaGetDevice (&p->device)) != cudaSuccess ||
         (e = cudaDeviceGetStreamPriorityRange (&least, &greatest)) != cudaSuccess ||
         (e = cudaMalloc (&p->fb, (size_t) w * h * 4)) != cudaSuccess ||
+        (e = cudaMalloc (&p->mask, (size_t) (w >> 3) * (h >> 2) + 4)) != cudaSuccess ||
+        (e = cudaMemset (p->mask, 0, (size_t) (w >> 3) * (h >> 2) + 4)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags (&p->marked, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate (&p->start)) != cudaSuccess) goto bad;
     for (int i=0; i<bands; i++)
     {
@@ -1815,17 +1973,33 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     const int others = g_presents_in_flight.load ();
     const int nbands = (!p->fixed_bands && others > 0) ? 1 : p->bands;
     CU (cudaEventRecord (p->start, p->stream[0]));
+    /* one screen mask per frame, marked on the first band's stream, shared by all bands */
+    const unsigned char *mask = NULL;
+    if (t && mask_usable (t, c) && (f->quality & 3u) == 0u)
+    {
+        const int mtiles = (p->w >> 3) * (p->h >> 2);
+        if (++p->epoch > 255u)
+        {
+            p->epoch = 1;
+            CU (cudaMemsetAsync (p->mask, 0, (size_t) mtiles + 4, p->stream[0]));
+        }
+        k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, p->stream[0]>>> (tree_ref (t), t->cut, t->n_cut, dev_camera (c), p->w, p->h,
+                                                                    p->mask, mtiles, (unsigned char) p->epoch);
+        g_launches++;
+        mask = p->mask;
+    }
+    CU (cudaEventRecord (p->marked, p->stream[0]));
     for (int i=0; i<nbands; i++)
     {
-        /* the later bands wait for the start mark so that the elapsed time covers all of them */
-        if (i) CU (cudaStreamWaitEvent (p->stream[i], p->start, 0));
+        /* the later bands wait for the mask (and with it the start mark: the elapsed time covers all of them) */
+        if (i) CU (cudaStreamWaitEvent (p->stream[i], p->marked, 0));
         const int y0 = (int) ((long long) units * i / nbands) * 4;
         const int y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
         if (y1 <= y0) { CU (cudaEventRecord (p->done[i], p->stream[i])); continue; }
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
         uint32_t *src = p->fb + (size_t) y0 * p->w;
-        if (voxgpu_render_sched (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], p->sched[i])) return -1;
+        if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], p->sched[i], mask, p->epoch)) return -1;
         char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
         if (host_pitch_bytes == (size_t) p->w * 4)
             CU (cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]));
