@@ -426,6 +426,38 @@ def test_root_box_culling_changes_nothing(gpu, checker, skull, ds, camera):
     assert culled_something > 5
 
 
+def test_many_launches_in_flight_on_three_streams(gpu, skull, ds):
+    """More launches queued than there are render slots (64 pairs of tile counters + screen masks), on a
+    number of streams that does not divide 64: a slot that comes round again while its previous borrower
+    is still running on another stream must wait for it (slot_acquire / slot_release)."""
+    t = gpu.Tree.build(skull)
+    w, h = 640, 360
+    ctx = gpu.Context(w, h)
+    api = gpu.api
+    g = api.libs.gpu
+    d_tex = gpu.DeviceBuffer.from_array(ctx.texture())
+    cams, want = [], []
+    cam = gpu.Camera()
+    for f in (10, 100, 190, 280):
+        ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, w, h)
+        cams.append(cam.gpu_camera())
+        want.append(render_device(gpu, t, cam, w, h, ctx.texture(), ctx.pixfmt(), want_hits=False)[0])
+    n = 200
+    bufs = [gpu.DeviceBuffer(w * h * 4) for _ in range(n)]
+    streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(3)]
+    fr = api.GpuFrame(w, h, 0, h, w, 0, ctx.pixfmt(), None)
+    for i in range(n):
+        assert g.voxgpu_render(t.device_handle(), C.byref(cams[i % 4]), C.byref(fr), d_tex.ptr, bufs[i].ptr, None, None,
+                               streams[i % 3]) == 0
+    g.voxgpu_synchronize(None)
+    for st in streams:
+        g.voxgpu_synchronize(st)
+    bad = [i for i in range(n) if not np.array_equal(bufs[i].download(np.uint32, (h, w)), want[i % 4])]
+    assert bad == []
+    for st in streams:
+        g.voxgpu_stream_destroy(st)
+
+
 def test_foreign_camera_without_describe(gpu, checker, skull, ds):
     """A camera written against the reference's 10-slot vtable (no `describe`) still renders:
     its host screen2world is tabulated."""

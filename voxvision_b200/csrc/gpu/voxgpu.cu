@@ -1378,7 +1378,17 @@ extern "C" void voxgpu_lights_free (voxgpu_lights *l)
 extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
 extern "C" void voxgpu_set_refill_min (int n) { g_refill_min = n < 1 ? 1 : (n > 32 ? 32 : n); }
 
-static unsigned* counter_slot (int device)
+/* A render launch borrows slot `idx` of its device: a pair of tile counters and a screen-mask buffer.
+   Launches rotate through COUNTER_SLOTS slots; should a slot come round again while its previous
+   borrower is still queued or running on ANOTHER stream, the new stream waits for it (slot_acquire /
+   slot_release: one event per slot), so sharing is always ordered. */
+struct SlotGuard { cudaEvent_t ev; cudaStream_t last; int used; };
+static SlotGuard g_guard[64][64];
+
+static unsigned slot_acquire (int device, cudaStream_t st);
+static void slot_release (int device, unsigned idx, cudaStream_t st);
+
+static unsigned* counter_slot (int device, unsigned idx)
 {
     if (!g_counters[device])
     {
@@ -1413,7 +1423,23 @@ static unsigned* counter_slot (int device)
         }
         g_counters[device] = p;
     }
-    return g_counters[device] + 2 * (g_counter_seq++ % COUNTER_SLOTS);
+    return g_counters[device] + 2 * idx;
+}
+
+static unsigned slot_acquire (int device, cudaStream_t st)
+{
+    const unsigned idx = g_counter_seq++ % COUNTER_SLOTS;
+    SlotGuard &g = g_guard[device][idx];
+    if (g.used && g.last != st) cudaStreamWaitEvent (st, g.ev, 0);
+    return idx;
+}
+
+static void slot_release (int device, unsigned idx, cudaStream_t st)
+{
+    SlotGuard &g = g_guard[device][idx];
+    if (!g.ev && cudaEventCreateWithFlags (&g.ev, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord (g.ev, st);
+    g.last = st; g.used = 1;
 }
 
 struct voxgpu_sched
@@ -1635,18 +1661,16 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
     return voxgpu_render_sched (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, NULL);
 }
 
-/* Per-device ring of screen-mask buffers for launches that bring no mask of their own.  Launches rotate
-   through the slots like they do through the tile counters (launches in flight never share one unless more
-   than MASK_SLOTS are in flight).  A slot is never cleared between uses: "marked" is the slot's epoch value,
+/* Per-device ring of screen-mask buffers for launches that bring no mask of their own, one per render
+   slot (slot_acquire).  A buffer is never cleared between uses: "marked" is the slot's epoch value,
    bumped per use, and the buffer is zeroed only when the epoch wraps or the slot grows. */
-#define MASK_SLOTS 64
+#define MASK_SLOTS COUNTER_SLOTS
 struct MaskSlot { unsigned char *buf; size_t cap; unsigned epoch; };
 static MaskSlot g_mask_slots[64][MASK_SLOTS];
-static std::atomic<unsigned> g_mask_seq{0};
 
-static unsigned char* mask_slot (int device, size_t bytes, cudaStream_t st, unsigned *epoch)
+static unsigned char* mask_slot (int device, unsigned idx, size_t bytes, cudaStream_t st, unsigned *epoch)
 {
-    MaskSlot &m = g_mask_slots[device][g_mask_seq++ % MASK_SLOTS];
+    MaskSlot &m = g_mask_slots[device][idx];
     if (m.cap < bytes)
     {
         if (m.buf) { cudaDeviceSynchronize (); cudaFree (m.buf); m.buf = NULL; m.cap = 0; }
@@ -1735,7 +1759,8 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         df.lt = f->lights->ref;
     }
 
-    /* screen mask for this launch (stream-ordered scratch): clear, mark from the tree's cut, use, free */
+    const unsigned slot = slot_acquire (t->device, (cudaStream_t) s);
+    /* screen mask for this launch: mark from the tree's cut into the slot's buffer */
     unsigned char *mask = NULL;
     df.mask = NULL; df.mask_tiles = 0; df.mask_epoch = 1;
     if (ext_mask)
@@ -1746,7 +1771,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
     {
         const int mtiles = (f->w >> 3) * (f->h >> 2);
         unsigned epoch = 1;
-        mask = mask_slot (t->device, (size_t) mtiles + 4, (cudaStream_t) s, &epoch);
+        mask = mask_slot (t->device, slot, (size_t) mtiles + 4, (cudaStream_t) s, &epoch);
         if (!mask) return fail ("voxgpu_render: cannot allocate the screen mask");
         k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, (cudaStream_t) s>>> (tree_ref (t), t->cut, t->n_cut, dc, f->w, f->h, mask, mtiles, (unsigned char) epoch);
         g_launches++;
@@ -1762,7 +1787,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
             return fail ("voxgpu_render: invalid quality %u (renderer.c:179-195)", f->quality);
         if (((size_t) d_pixels & 15) || (df.pitch & 3))
             return fail ("voxgpu_render: quality modes other than BEST need 16-byte aligned rows");
-        unsigned *counters = counter_slot (t->device);
+        unsigned *counters = counter_slot (t->device, slot);
         if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
         const int warps = (((df.w >> 2) + 7) >> 3) * (((df.rows >> 2) + 3) >> 2);
         int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
@@ -1779,8 +1804,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
             const size_t npix = (size_t) df.w * df.rows;
             CU (cudaMallocAsync (&pre_leaf, npix * sizeof (int), st));
             CU (cudaMallocAsync (&pre_pts, npix * sizeof (float4), st));
-            unsigned *c1 = counter_slot (t->device);
-            if (!c1) return fail ("voxgpu_render: cannot allocate tile counters");
+            unsigned *c1 = counters;      /* the two launches run one after the other on this stream; the counters reset themselves */
             int g1 = g_render_blocks[t->device][1];
             if (g1 > blocks) g1 = blocks;
             DevSched none;
@@ -1816,7 +1840,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
     }
     else
     {
-        unsigned *counters = counter_slot (t->device);
+        unsigned *counters = counter_slot (t->device, slot);
         if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
         const bool hits = d_leaf || d_pts;
         int grid = g_render_blocks[t->device][hits ? 1 : 0];
@@ -1854,6 +1878,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
     }
     g_launches++;
     CU (cudaGetLastError ());
+    slot_release (t->device, slot, (cudaStream_t) s);
     return 0;
 }
 
