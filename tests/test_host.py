@@ -298,3 +298,76 @@ def test_screen_bounds_contain_every_hit_pixel(vv, port, skull, ds, kind, name):
         assert not (enters & ~inside).any(), (trial, list(out))
         bounded += int((x1 - x0) * (y1 - y0) < w * h)
     assert bounded > 15          # the bounds do bite in many poses (VOX_BOUNDS_TRIALS=1500 was run once: no escape)
+
+
+def test_screen_mask_argument_on_the_host(vv, port, skull, ds):
+    """The argument behind the render kernel's screen mask (k_mark in voxgpu.cu), replayed in numpy: take
+    the same cut through the tree (deepest level with <= 131072 nodes plus the leaves above it), project
+    the eight corners of every cut box with the inverse of screen2world in fp32, widen the bounding
+    rectangle by 2 pixels, mark 8x4 tiles.  Every pixel the ORACLE finds a voxel for must lie in a marked
+    tile -- over random poses of both kinds of camera."""
+    t = vv.Tree.build(skull)
+    a = t.export()
+    n = len(a["flags"])
+    leafp = (a["flags"] & 3) != 0
+    level = np.zeros(n, np.int32)
+    for i in np.flatnonzero(~leafp):
+        nc, fc = bin(int(a["child_mask"][i])).count("1"), int(a["first_child"][i])
+        level[fc:fc + nc] = level[i] + 1
+    at, leaves = np.bincount(level), np.bincount(level[leafp], minlength=level.max() + 1)
+    best = above = 0
+    for lv in range(len(at)):
+        if at[lv] + above <= 131072:
+            best = lv
+        above += leaves[lv]
+    cut = np.flatnonzero((level == best) | ((level < best) & leafp))
+    mn, mx = a["bb_min"][cut], a["bb_max"][cut]
+    otree = port.tree(skull)
+    w, h = 320, 160
+    rng = np.random.default_rng(21)
+    f32 = np.float32
+    useful = 0
+    for trial in range(40):
+        kind = trial % 2
+        dist = [700.0, 330.0, 220.0, 150.0][trial % 4]
+        v = rng.normal(size=3)
+        pos = 128 + dist * v / np.linalg.norm(v)
+        look = 128 + rng.normal(size=3) * 30
+        cam, ocam = vv.Camera("doom-camera" if kind else "simple-camera"), port.camera(kind)
+        rot = [float(x) for x in rng.normal(size=3) * (0.4 if trial % 3 == 0 else 0.0)]
+        for c_ in (cam, ocam):
+            ds.setup_camera(c_, pos, look, [0.6, 1.2][trial % 2], w, h)
+            c_.rotate(rot)
+        gc = cam.gpu_camera()
+        p0 = np.array(gc.position, f32)
+        lo = np.full((len(cut), 2), np.inf, f32)
+        hi = -lo
+        front = np.ones(len(cut), bool)
+        for k in range(8):
+            c = np.where(np.array([k & 1, k & 2, k & 4], bool)[None, :], mx, mn).astype(f32) - p0
+            if kind == 0:
+                qw, u = f32(gc.rotation[0]), -np.array(gc.rotation[1:], f32)
+                tt = f32(2) * np.cross(u, c).astype(f32)
+                vv_ = (c + qw * tt + np.cross(u, tt)).astype(f32)
+            else:
+                cs, sn = f32(gc.cosphi), f32(gc.sinphi)
+                vv_ = np.stack([c[:, 0] * cs + c[:, 1] * sn, c[:, 1] * cs - c[:, 0] * sn, c[:, 2]], 1).astype(f32)
+            front &= vv_[:, 1] > f32(1e-3) * np.abs(c).sum(1)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rz = vv_[:, 2] / vv_[:, 1] - (f32(gc.k) if kind else f32(0))
+                s = np.stack([(vv_[:, 0] / vv_[:, 1] + f32(gc.xsub)) / f32(gc.mul), (f32(gc.ysub) - rz) / f32(gc.mul)], 1)
+            lo, hi = np.minimum(lo, s), np.maximum(hi, s)
+        leaf = otree.rays(*ocam.rays(w, h))[0].reshape(h, w)
+        if not front.all():
+            continue                    # the kernel raises its "no bounds" flag for such a frame
+        mask = np.zeros((h // 4, w // 8), bool)
+        x0 = np.clip(np.floor(lo[:, 0]) - 2, 0, w).astype(int) >> 3
+        x1 = (np.clip(np.ceil(hi[:, 0]) + 3, 0, w).astype(int) + 7) >> 3
+        y0 = np.clip(np.floor(lo[:, 1]) - 2, 0, h).astype(int) >> 2
+        y1 = (np.clip(np.ceil(hi[:, 1]) + 3, 0, h).astype(int) + 3) >> 2
+        for i in range(len(cut)):
+            mask[y0[i]:y1[i], x0[i]:x1[i]] = True
+        hit_tiles = (leaf >= 0).reshape(h // 4, 4, w // 8, 8).any((1, 3))
+        assert not (hit_tiles & ~mask).any(), trial
+        useful += int(mask.mean() < 0.9)
+    assert useful > 10
