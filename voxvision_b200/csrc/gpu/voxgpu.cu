@@ -804,8 +804,8 @@ k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restri
 }
 
 /*
- * Persistent form of K1 (the one voxgpu_render launches).  80% of the 8x4 tiles
- * of a typical frame miss the root box and finish in a few hundred cycles; with
+ * Persistent form of K1 (the one voxgpu_render launches).  70-80% of the 8x4 tiles
+ * of a C2 frame show no voxel (half of them do not even see the root box) and finish early; with
  * one CTA per 4 tiles the SMs spent a third of the kernel waiting for CTA
  * launches (profiles/r01_*).  Here the grid is sized to the resident capacity
  * of the GPU and every warp pulls tile indices from a global counter until the
@@ -918,8 +918,8 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
 
     /* Tiles are handed out strip-interleaved: consecutive tickets land in
        RENDER_STRIPS different horizontal strips of the frame.  In raster order
-       the empty top and bottom of a frame (80% of a skull frame misses the root
-       box) are done in two bursts that only store pixels while the middle only
+       the empty top and bottom of a frame (half of a skull frame misses the root
+       box, 70-80% of it shows no voxel) are done in two bursts that only store pixels while the middle only
        computes; interleaved, stores and traversal overlap for the whole kernel,
        which matters when the pixels go to mapped host memory over PCIe. */
     const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;

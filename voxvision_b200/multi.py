@@ -84,7 +84,7 @@ def row_bands(height, world):
 def interleaved_bands(height, world, bands_per_rank=4):
     """[[(y0, y1), ...] per rank]: the frame cut into world*bands_per_rank bands dealt round-robin,
     so that every rank gets a share of the expensive middle of the image (hit density is very
-    uneven: 80% of a skull frame misses the root box)."""
+    uneven: 70-80% of a skull frame shows no voxel)."""
     cuts = row_bands(height, world * bands_per_rank)
     return [[b for i, b in enumerate(cuts) if i % world == r and b[1] > b[0]] for r in range(world)]
 
