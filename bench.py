@@ -11,9 +11,10 @@ frame = 2 073 600 primary rays).  Prints ONE JSON line (rank 0).
   value      device-timed throughput: frames land in HBM, CUDA events on the
              launching stream, barrier + synchronize on both sides, max over ranks.
   e2e        the same frames through the reference-facing API (vox_render +
-             vox_redraw) into a HOST surface: per frame the camera goes host->device
-             and the 8.3 MB frame device->host (band kernels into a device
-             framebuffer, each band DMA-copied into the page-locked surface).
+             vox_redraw) into HOST surfaces: per frame the camera goes host->device
+             and the 8.3 MB frame device->host; the frames go round-robin through a
+             ring of contexts (a swap chain of page-locked surfaces), so a frame
+             crosses PCIe while the next ones render.  e2e.single_context = one context.
   roofline   for the dominant kernel k_render: algorithmic bytes per launch
              (node/dot records the reference's recursion touches, counted by the
              instrumented oracle on sampled frames, + 4 B per pixel) / mean launch time,
@@ -23,8 +24,10 @@ frame = 2 073 600 primary rays).  Prints ONE JSON line (rank 0).
 
 N > 1: one process per GPU (torchrun), tree replicated, every rank renders its
 own 360 frames (rank r's orbit is shifted by r/N of a frame step, so all N*360
-frames differ) and the finished frames are gathered to GPU 0 with NCCL in
-batches on a side stream while the next batch renders.  Weak scaling.
+frames differ) straight into a buffer on GPU 0 that it has mapped over NVLink
+(CUDA IPC): the gather is the render kernel's own pixel store.  If the peer
+mapping is unavailable the frames are gathered with NCCL in batches on a side
+stream instead.  torch.distributed (NCCL) is the control plane.  Weak scaling.
 """
 import argparse
 import ctypes as C
