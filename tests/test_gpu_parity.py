@@ -458,6 +458,27 @@ def test_many_launches_in_flight_on_three_streams(gpu, skull, ds):
         g.voxgpu_stream_destroy(st)
 
 
+def test_c_example_matches_the_oracle(gpu, checker, ds, tmp_path):
+    """examples/orbit.c -- a C program written against the reference's API only -- renders the frames the
+    oracle renders for the same scene and poses (FNV-1a of the surface bytes, lit pixel count)."""
+    import math
+    import subprocess
+    from test_host import build_c_example
+    exe = build_c_example(tmp_path)
+    out = subprocess.run([exe, "3"], capture_output=True, text=True, check=True).stdout.split("\n")
+    otree = checker.tree(ball_voxels(20))
+    tex = gpu.Context(16, 4).texture()
+    for f in range(3):
+        th = f * 2.0 * math.pi / 16
+        pos = (np.float32(70.0 * math.sin(th)), np.float32(-70.0 * math.cos(th)), np.float32(10.0))
+        ocam = ds.setup_camera(checker.camera(0), pos, (0, 0, 0), 1.0, 256, 128)
+        pix = otree.render(ocam, 256, 128, 0, tex, want_hits=False)
+        hsh = 1469598103934665603
+        for b in pix.astype("<u4").tobytes():
+            hsh = ((hsh ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert out[f] == f"frame {f} lit {int((pix != 0).sum())} hash {hsh:016x}", out[f]
+
+
 def test_foreign_camera_without_describe(gpu, checker, skull, ds):
     """A camera written against the reference's 10-slot vtable (no `describe`) still renders:
     its host screen2world is tabulated."""

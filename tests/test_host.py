@@ -13,6 +13,8 @@ import pytest
 
 from util import CROSS, ball_voxels, bits, check_tree_invariants, flat_equal, sha
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def declared_symbols(vv):
     """Every VOX_EXPORT / VOXGPU_EXPORT declaration in include/."""
@@ -371,3 +373,24 @@ def test_screen_mask_argument_on_the_host(vv, port, skull, ds):
         assert not (hit_tiles & ~mask).any(), trial
         useful += int(mask.mean() < 0.9)
     assert useful > 10
+
+
+def build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "orbit")
+    lib = os.path.join(ROOT, "voxvision_b200", "lib")
+    cmd = ["gcc", "-std=gnu11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "orbit.c"), "-L" + lib, "-lvoxrnd", "-lvoxtrees", "-lm",
+           "-Wl,-rpath," + lib, "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_c_example_compiles_against_the_headers(vv, tmp_path):
+    """examples/orbit.c: the reference's scene setup in plain C against include/, warnings as errors.
+    Without a CUDA device the program must fail loudly (exit code 2, the library's message), never render."""
+    import subprocess
+    exe = build_c_example(tmp_path)
+    if not vv.gpu_available():
+        r = subprocess.run([exe, "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CUDA device" in r.stderr
