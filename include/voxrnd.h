@@ -1,7 +1,7 @@
 /**
    @file voxrnd.h
    @brief Umbrella header of libvoxrnd (reference: src/voxrnd.h:7-14; the
-   fps-control and screenshot parts are out of scope).
+   fps-control part (a clang Block API) is out of scope).
 **/
 #ifndef VOXRND_H
 #define VOXRND_H
@@ -15,6 +15,7 @@ extern "C" {
 #include "voxrnd/renderer.h"
 #include "voxrnd/cd.h"
 #include "voxrnd/lights.h"
+#include "voxrnd/screenshot.h"
 #ifdef __cplusplus
 }
 #endif

@@ -394,3 +394,26 @@ def test_c_example_compiles_against_the_headers(vv, tmp_path):
     if not vv.gpu_available():
         r = subprocess.run([exe, "1"], capture_output=True, text=True)
         assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+def test_screenshot_is_a_readable_bmp(vv, tmp_path):
+    """vox_screenshot (screenshot.c:7-36): numbered 24-bit BMPs of the surface, host only."""
+    R = vv.libs.rnd
+    R.vox_screenshot.argtypes = [C.c_void_p, C.c_char_p]
+    R.vox_screenshot.restype = C.c_int
+    ctx = vv.Context(32, 8)
+    pix = ctx.pixels()
+    rng = np.random.default_rng(3)
+    pix[:] = rng.integers(0, 1 << 24, pix.shape, dtype=np.uint32)           # XRGB8888
+    want = pix.copy()
+    assert R.vox_screenshot(ctx.h, str(tmp_path).encode()) == 1
+    assert R.vox_screenshot(ctx.h, str(tmp_path).encode()) == 1
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and all(re.fullmatch(r"screenshot\d+\.bmp", f) for f in files)
+    raw = open(tmp_path / files[0], "rb").read()
+    assert raw[:2] == b"BM" and int.from_bytes(raw[18:22], "little") == 32 and int.from_bytes(raw[22:26], "little") == 8
+    assert int.from_bytes(raw[28:30], "little") == 24 and len(raw) == 54 + 32 * 3 * 8
+    bgr = np.frombuffer(raw[54:], np.uint8).reshape(8, 32, 3)[::-1]
+    assert np.array_equal(bgr[..., 2], (want >> 16) & 0xff) and np.array_equal(bgr[..., 1], (want >> 8) & 0xff)
+    assert np.array_equal(bgr[..., 0], want & 0xff)
+    assert R.vox_screenshot(ctx.h, b"/nonexistent-dir/xyz") == 0 and "vox_screenshot" in vv.last_error()
