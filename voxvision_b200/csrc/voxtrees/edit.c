@@ -443,7 +443,7 @@ int vox_store_sync (struct vox_tree_store *st)
     free (st->dots_off); free (st->handles);
     st->bb_min = nw->bb_min; st->bb_max = nw->bb_max; st->center = nw->center; st->dots = nw->dots;
     st->flags = nw->flags; st->dots_num = nw->dots_num; st->first_child = nw->first_child;
-    st->child_mask = nw->child_mask; st->dots_off = nw->dots_off; st->handles = nw->handles;
+    st->child_mask = nw->child_mask; st->dots_off = nw->dots_off; st->handles = NULL;
     st->cap_nodes = nw->cap_nodes; st->cap_dots = nw->cap_dots;
     st->n_nodes = n_nodes; st->n_dots = n_dots;
     pthread_mutex_destroy (&nw->lock);

@@ -45,7 +45,8 @@ struct vox_tree_store
     uint64_t *dots_off;
 
     struct vox_node root;                        /* handle of node 0: its address never changes */
-    struct vox_node *handles;                    /* handles of nodes 1.. (entry 0 unused); replaced by edits */
+    struct vox_node *handles;                    /* handles of nodes 1.. (entry 0 unused), made on first demand
+                                                    (vox_store_handle): a renderer never asks for one; dropped by edits */
     uint64_t cap_nodes, cap_dots;                /* allocated entries of the arrays above */
 
     /* online edits (edit.c): a linked, mutable mirror of the tree; the flat arrays and the
@@ -64,10 +65,7 @@ struct vox_tree_store* vox_store_alloc (uint64_t n_nodes, uint64_t n_dots);
 void vox_store_finish (struct vox_tree_store *st);   /* handles + statistics */
 void vox_store_free (struct vox_tree_store *st);
 int vox_node_valid (const struct vox_node *node);
-static inline struct vox_node* vox_store_handle (struct vox_tree_store *st, uint64_t id)
-{
-    return id ? &st->handles[id] : &st->root;
-}
+struct vox_node* vox_store_handle (struct vox_tree_store *st, uint64_t id);
 /* edit.c */
 void vox_edit_free (struct vox_edit *e);
 int vox_store_sync (struct vox_tree_store *st);      /* flat arrays <- edited tree, if dirty; 0 on failure */

@@ -52,10 +52,9 @@ struct vox_tree_store* vox_store_alloc (uint64_t n_nodes, uint64_t n_dots)
     st->first_child = calloc (nn, sizeof (uint32_t));
     st->child_mask = calloc (nn, sizeof (uint32_t));
     st->dots_off = calloc (nn, sizeof (uint64_t));
-    st->handles = malloc (nn * sizeof (struct vox_node));
     pthread_mutex_init (&st->lock, NULL);
     if (!st->bb_min || !st->bb_max || !st->center || !st->dots || !st->flags || !st->dots_num ||
-        !st->first_child || !st->child_mask || !st->dots_off || !st->handles)
+        !st->first_child || !st->child_mask || !st->dots_off)
     {
         vox_set_error ("out of memory for a tree of %llu nodes", (unsigned long long) n_nodes);
         vox_store_free (st);
@@ -65,19 +64,37 @@ struct vox_tree_store* vox_store_alloc (uint64_t n_nodes, uint64_t n_dots)
     return st;
 }
 
-/* Handles, per-kind counts and depth, from the flat arrays. */
+/* The handle of a node: the root's lives in the store, the others in an array that is only made when
+   somebody asks for one (vox_ray_tree_intersection returning a leaf, vox_tree_node). */
+struct vox_node* vox_store_handle (struct vox_tree_store *st, uint64_t id)
+{
+    if (id == 0) return &st->root;
+    if (!st->handles)
+    {
+        pthread_mutex_lock (&st->lock);
+        if (!st->handles)
+        {
+            struct vox_node *h = malloc ((st->n_nodes ? st->n_nodes : 1) * sizeof *h);
+            if (h)
+                for (uint64_t i=0; i<st->n_nodes; i++) { h[i].store = st; h[i].id = (uint32_t) i; h[i].magic = VOX_NODE_MAGIC; }
+            __atomic_store_n (&st->handles, h, __ATOMIC_RELEASE);
+        }
+        pthread_mutex_unlock (&st->lock);
+        if (!st->handles) return NULL;
+    }
+    return &st->handles[id];
+}
+
+/* Root handle, per-kind counts and depth, from the flat arrays. */
 void vox_store_finish (struct vox_tree_store *st)
 {
+    st->root.store = st; st->root.id = 0; st->root.magic = VOX_NODE_MAGIC;
     uint32_t *level = malloc ((st->n_nodes ? st->n_nodes : 1) * sizeof (uint32_t));
     st->n_inner = st->n_leaf = st->n_dense = st->n_overflow = 0;
     st->depth = 0;
     if (st->n_nodes) level[0] = 1;
     for (uint64_t id=0; id<st->n_nodes; id++)
     {
-        struct vox_node *hd = vox_store_handle (st, id);
-        hd->store = st;
-        hd->id = (uint32_t) id;
-        hd->magic = VOX_NODE_MAGIC;
         if (level[id] > st->depth) st->depth = level[id];
         uint32_t fl = st->flags[id];
         if (fl & VOX_DENSE_LEAF) st->n_dense++;
