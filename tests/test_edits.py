@@ -102,6 +102,27 @@ def test_reference_quirk_childless_inner_node(vv, ref):
     assert int(a["child_mask"][1]) == 0 and int(a["flags"][1]) == 0 and int(a["dots_num"][1]) == 0
 
 
+def test_quirk_tree_survives_export_import(vv):
+    """An edited tree holding the childless inner node must replicate like any other tree
+    (vox_tree_export -> vox_tree_import, what multi.broadcast_flat_tree does)."""
+    g = np.arange(0, 2)
+    v = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    v = np.concatenate([v, v + np.array([0, 0, 2], np.float32)])
+    t = vv.Tree.build(v)
+    t.delete([[1, 1, 3]])
+    a = t.export()
+    assert int(a["child_mask"][1]) == 0 and int(a["flags"][1]) == 0
+    b = vv.Tree.from_arrays(a).export()
+    assert flat_equal(a, b) == []
+    assert vv.Tree.from_arrays(a).voxels() == t.voxels() == 15
+    # the layout check itself still bites
+    bad = dict(a)
+    bad["first_child"] = a["first_child"].copy()
+    bad["first_child"][0] += 1
+    with pytest.raises(vv.VoxError):
+        vv.Tree.from_arrays(bad)
+
+
 def test_edit_api_contracts(vv):
     C = vv.api.C
     root = C.c_void_p(None)

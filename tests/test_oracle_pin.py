@@ -227,3 +227,28 @@ def test_reference_insertion_built_cross(ref, golden):
     fl = t.flatten()
     for k in ("bb_min", "bb_max", "flags", "dots_num", "center", "first_child", "child_mask", "dots_off", "dots"):
         assert np.array_equal(fl[k], arr["cross_ins_flat_" + k]), k
+
+
+def test_scalar_vs_sse_divergence_fixture(orc, ref, ds):
+    """tests/golden/sse_divergence.json (make_sse_divergence.py) states how far the reference's own two
+    builds are apart on the C2 golden frames; bench.py quotes it beside the SSE-timed CPU arm.  Re-measured
+    here for frame 0 on the same rays (the part that does not depend on the host's rsqrtps)."""
+    import json
+    if not orc.available("ref_sse"):
+        pytest.skip("oracle/_ref/libvoxref_sse.so not built")
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sse_divergence.json")) as f:
+        fx = json.load(f)
+    assert set(fx["frames"]) == {str(k) for k in ds.C2_KNOWN_HITS}
+    for k, want in ds.C2_KNOWN_HITS.items():
+        assert fx["frames"][str(k)]["same_rays"]["hits_scalar"] == want
+    sse = orc.Oracle("ref_sse")
+    vox = ds.volume_voxels("skull")
+    ts, tv = ref.tree(vox), sse.tree(vox)
+    cam = ds.setup_camera(ref.camera(0), *ds.orbit_pose(0, 360), 1.2, 1920, 1080)
+    o, d = cam.rays(1920, 1080)
+    ls, _, _ = ts.rays(o, d, threads=THREADS)
+    lv, _, _ = tv.rays(o, d, threads=THREADS)
+    got = fx["frames"]["0"]["same_rays"]
+    assert int((lv >= 0).sum()) == got["hits_sse"]
+    assert int((ls != lv).sum()) == got["leaf_differs"]
+    assert int(((ls >= 0) != (lv >= 0)).sum()) == got["hit_miss_differs"]

@@ -492,8 +492,10 @@ struct vox_node* vox_tree_import (const struct vox_tree_arrays *in, uint64_t n_n
             { vox_set_error ("vox_tree_import: leaf %llu points outside dots[]", (unsigned long long) id); return NULL; }
             continue;
         }
+        /* mask == 0 is legal: deleting the last voxel of an octant leaves the reference's childless
+           inner node behind (tree.c:695-756), and edited trees are exported / replicated like any other */
         uint32_t mask = in->child_mask[id];
-        if (mask == 0 || mask > 0xff || in->first_child[id] != expect_child)
+        if (mask > 0xff || in->first_child[id] != expect_child)
         { vox_set_error ("vox_tree_import: node %llu breaks the breadth-first child layout", (unsigned long long) id); return NULL; }
         expect_child += __builtin_popcount (mask);
     }
