@@ -1,26 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- Mrays/s of primary-ray rendering, skull 1920x1080 along the
-scripted 360-frame orbit (BASELINE.json configs[1], SURVEY.md 8d "C2").
+scripted 360-frame orbit (BASELINE.json configs[1], SURVEY.md 8d "C2"), with the
+other four configs of BASELINE.json carried in the same line.
 
     python bench.py --gpus N --steps K --warmup W            this repository's CUDA path
     python bench.py --impl reference --gpus N ...            the reference's CPU path (rank 0 only)
 
-A step = one pass over the 360-frame camera path (360 kernel launches, one
-frame = 2 073 600 primary rays).  Prints ONE JSON line (rank 0).
+A step = one pass over the 360-frame camera path (one frame = 2 073 600 primary
+rays).  Prints ONE JSON line (rank 0).
 
-  value      device-timed throughput: frames land in HBM, CUDA events on the
-             launching stream, barrier + synchronize on both sides, max over ranks.
-  e2e        the same frames through the reference-facing API (vox_render +
-             vox_redraw) into HOST surfaces: per frame the camera goes host->device
-             and the 8.3 MB frame device->host; the frames go round-robin through a
-             ring of contexts (a swap chain of page-locked surfaces), so a frame
-             crosses PCIe while the next ones render.  e2e.single_context = one context.
-  roofline   for the dominant kernel k_render: algorithmic bytes per launch
+  value      C2, device-timed: frames land in HBM, CUDA events on the launching stream,
+             barrier + synchronize on both sides, max over ranks.
+  e2e        C2 through the reference-facing API, called from C (examples/orbit_bench.c:
+             vox_context_set_camera -> vox_render -> vox_redraw per frame, one pixel of every
+             finished frame read by the host): per frame the camera goes host->device and the
+             8.3 MB frame device->host.  `value`: a ring of contexts (a swap chain of
+             page-locked surfaces) per rank; `single_context`: the reference demo's loop,
+             ONE context -- at N > 1 one process splitting every frame over all N GPUs
+             (vox_context_set_devices); `adaptive`: the reference's default quality;
+             `d2h_ceiling`: what plain DMA copies of frame-sized buffers reach on this box.
+  roofline   for the dominant kernel k_render_persistent: algorithmic bytes per launch
              (node/dot records the reference's recursion touches, counted by the
              instrumented oracle on sampled frames, + 4 B per pixel) / mean launch time,
-             against the measured HBM copy peak (MEASURED_PEAKS.json).
+             against the measured HBM copy peak (MEASURED_PEAKS.json); `issue_bound`: the
+             figure the kernel is really limited by (the tree is L2-resident).
   cpu_baseline  the reference's own C code (oracle/_ref, else the C restatement)
              rendering sampled frames on all host cores of this box.
+  c5         BASELINE.json configs[4]: ONE 7680x4320 frame of the ~100 M-voxel synthetic
+             volume, its tile rows dealt to the N GPUs, gathered on GPU 0 by peer stores;
+             strong scaling, with the one-GPU time of the same frames measured in the same
+             run, a gather check and an oracle sample.
+  configs    (N = 1) C1, C3, C4: device-resident rate, host-buffer rate through the C API,
+             the reference's CPU rate, roofline.
 
 N > 1: one process per GPU (torchrun), tree replicated, every rank renders its
 own 360 frames (rank r's orbit is shifted by r/N of a frame step, so all N*360
@@ -28,6 +39,8 @@ frames differ) straight into a buffer on GPU 0 that it has mapped over NVLink
 (CUDA IPC): the gather is the render kernel's own pixel store.  If the peer
 mapping is unavailable the frames are gathered with NCCL in batches on a side
 stream instead.  torch.distributed (NCCL) is the control plane.  Weak scaling.
+
+$VOX_BENCH_SKIP: comma-separated legs to leave out (c5, configs, e2e, cpu) for profiling runs.
 """
 import argparse
 import ctypes as C
@@ -53,8 +66,13 @@ METRIC = "Mrays/s primary-ray render (skull 1080p)"
 GATHER_BATCH = 8          # frames per NCCL gather
 RING = 2 * GATHER_BATCH   # device framebuffers per rank
 FRAME_STREAMS = int(os.environ.get("VOX_FRAME_STREAMS", "4"))         # frames in flight per GPU (independent frames of the scripted path)
-SHORT = int(os.environ.get("VOX_BENCH_SHORT", "0"))   # profiling runs: 1 = skip the CPU baseline, one e2e pass; 2 = no e2e leg at all
 E2E_CONTEXTS = int(os.environ.get("VOX_E2E_CONTEXTS", "6"))          # render contexts (host surfaces) taking the frames round-robin in the e2e leg
+SKIP = {s for s in os.environ.get("VOX_BENCH_SKIP", "").split(",") if s}
+if os.environ.get("VOX_BENCH_SHORT"):                                 # r01's knob: 1 = no CPU baseline, 2 = no e2e either
+    SKIP |= {"cpu", "configs", "c5"} | ({"e2e"} if int(os.environ["VOX_BENCH_SHORT"]) >= 2 else set())
+# B200: 148 SMs x 4 schedulers, one warp instruction each per cycle
+SM_COUNT, SCHEDULERS = 148, 4
+C5_W, C5_H, C5_SIDE, C5_BALLS, C5_POSES = 7680, 4320, 1024, 4096, 16
 
 
 def rank_env():
@@ -133,6 +151,25 @@ def cpu_render_rate(ds, O, sample_frames, repeats, threads, quality=0):
     return len(cams) * RAYS_PER_FRAME / best / 1e6, best
 
 
+def sse_divergence():
+    """tests/golden/sse_divergence.json: how far the reference's SSE build (the timed CPU arm) is from its
+    scalar build (the parity oracle) on the C2 golden frames, measured with the reference's own object code."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "sse_divergence.json")) as f:
+            fx = json.load(f)
+        same = [v["same_rays"] for v in fx["frames"].values()]
+        own = [v["own_camera"] for v in fx["frames"].values()]
+        return {"what": "reference SSE build vs reference scalar build, per 1080p frame over the 8 golden C2 frames (min..max); "
+                        "parity of this repository is against the scalar build, bit for bit",
+                "same_rays_leaf_differs": [min(x["leaf_differs"] for x in same), max(x["leaf_differs"] for x in same)],
+                "same_rays_hit_miss_differs": [min(x["hit_miss_differs"] for x in same), max(x["hit_miss_differs"] for x in same)],
+                "own_camera_leaf_differs": [min(x["leaf_differs"] for x in own), max(x["leaf_differs"] for x in own)],
+                "note": "own_camera: each build with its own look_at (the SSE one normalises with rsqrtps, vect-ops-sse.c:73-79)",
+                "source": "tests/golden/sse_divergence.json (tests/golden/make_sse_divergence.py)"}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank, _, world = rank_env()
     if rank != 0:
@@ -152,16 +189,19 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = args.steps * len(sample) * RAYS_PER_FRAME / dt / 1e6
-    sample_txt = f"{len(sample)} of the {FRAMES} orbit frames per step (every 10th), quality BEST"
+    sample_txt = f"{len(sample)} of the {FRAMES} orbit frames per step (every 10th), quality BEST; the rate is per ray"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "bundled skull volume (sample>40), scripted orbit",
-        "config": {"workload": "C2 skull 1920x1080 x 360-frame orbit (sampled)", "oracle": O.name,
-                   "threads": threads, "frames_per_step": len(sample)},
+        "config": {"workload": "C2: skull 1920x1080, 360-frame orbit, quality BEST, simple-camera", "oracle": O.name,
+                   "threads": threads, "frames_per_step": len(sample),
+                   "cpu_arm_sample": "a CPU step renders every 10th frame of the orbit (36 of 360); Mrays/s is per ray, so the "
+                                     "two arms compare directly"},
         "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
                          "sample": sample_txt},
+        "sse_divergence": sse_divergence(),
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -182,79 +222,106 @@ def algorithmic_bytes_per_frame(ds, orc_mod, sample_frames, threads):
     return total / len(sample_frames)
 
 
-def run_own(args):
-    rank, local_rank, world = rank_env()
-    import voxvision_b200 as vv
-    from voxvision_b200 import api
-    from tools import datasets as ds
+class OrbitBenchResult(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("checksum", C.c_ulonglong), ("frames", C.c_long), ("devices", C.c_int),
+                ("error", C.c_char * 256)]
 
-    if not vv.gpu_available():
-        raise SystemExit("bench.py: no CUDA device (" + vv.last_error() + "); there is no CPU fallback to time")
-    dist = torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    vv.set_device(local_rank)
-    g = api.libs.gpu
 
-    tree = vv.Tree.build(ds.volume_voxels("skull"))
+class Env:
+    """What the legs share: rank, libraries, the skull tree, torch.distributed if N > 1."""
+
+    def __init__(self):
+        self.rank, self.local_rank, self.world = rank_env()
+        import voxvision_b200 as vv
+        from voxvision_b200 import api
+        from tools import datasets as ds
+        self.vv, self.api, self.ds = vv, api, ds
+        if not vv.gpu_available():
+            raise SystemExit("bench.py: no CUDA device (" + vv.last_error() + "); there is no CPU fallback to time")
+        self.dist = self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist, self.torch = dist, torch
+        vv.set_device(self.local_rank)
+        self.g = api.libs.gpu
+        self.orbit = C.CDLL(os.path.join(api.LIB_DIR, "liborbitbench.so"))
+        self.orbit.orbit_bench_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                               C.c_uint, C.c_int, C.POINTER(OrbitBenchResult)]
+
+    def sync_all(self):
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+        else:
+            self.g.voxgpu_synchronize(None)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def share_buffer(self, nbytes):
+        """A device buffer on GPU 0 that every rank can store into: (pointer on this rank, owner's pointer or None, mode)."""
+        g, torch, dist = self.g, self.torch, self.dist
+        if self.world == 1:
+            buf = self.vv.DeviceBuffer(nbytes)
+            self._keep = getattr(self, "_keep", []) + [buf]
+            return buf.ptr, buf.ptr, "local"
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        base = None
+        if self.rank == 0:
+            base = g.voxgpu_malloc(nbytes)
+            if not base:
+                raise self.vv.VoxError(g.voxgpu_last_error().decode())
+            hb = (C.c_ubyte * 64)()
+            g.voxgpu_ipc_export(base, hb)
+            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+        dist.broadcast(handle, 0)
+        if self.rank == 0:
+            mine = base
+        else:
+            hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            mine = g.voxgpu_ipc_open(hb)
+        flag = torch.tensor([1 if mine else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return mine, base, ("peer-store" if int(flag.item()) else "nccl")
+
+
+def leg_c2_device(E, args, tree, gcams, frame_desc, d_tex):
+    """`value`: 360 launches per step, FRAME_STREAMS frames in flight; N > 1: gathered on GPU 0."""
+    vv, g, ds, world, rank = E.vv, E.g, E.ds, E.world, E.rank
     dev_tree = tree.device_handle()
-    ctx = vv.Context(W, H)
-    ctx.set_scene(tree)
-    ctx.set_quality(vv.QUALITY_BEST)
-    fmt, tex = ctx.pixfmt(), ctx.texture()
-
-    # per-frame cameras: host-side camera maths, through the camera module's vtable
-    cam = vv.Camera("simple-camera")
-    gcams, poses = [], []
-    for f in range(FRAMES):
-        pos, look = frame_pose(ds, f, rank, world)
-        ds.setup_camera(cam, pos, look, FOV, W, H)
-        gcams.append(cam.gpu_camera())
-        poses.append((pos, look))
-    frame_desc = api.GpuFrame(W, H, 0, H, W, vv.QUALITY_BEST, fmt)
-
-    # ---- device-resident leg ------------------------------------------------
-    # The frames of the path are independent: FRAME_STREAMS of them are in flight per GPU
-    # (frame f on stream f % FRAME_STREAMS, each into its own framebuffer), so the long tail
-    # of one frame's kernel (a few expensive tiles) is filled by the next frame's tiles.
     frame_bytes = W * H * 4
     streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(FRAME_STREAMS)]
     s_ptr = streams[0]
-    d_tex_b = vv.DeviceBuffer.from_array(tex)
-    d_tex = d_tex_b.ptr
     flush_b = vv.DeviceBuffer(256 << 20)
-    gather_mode, gather_base, peer_base = "none", None, None
+    gather_mode, gather_base = "none", None
+    region_bytes = FRAMES * frame_bytes
     if world > 1:
         # The gather to GPU 0 is fused into the render kernel's store: rank 0 owns a buffer with room
         # for every rank's 360 frames, the other ranks map it (CUDA IPC) and render straight into it
         # over NVLink.  No copy kernel, no NCCL kernel competing with the persistent render CTAs for SMs.
-        from voxvision_b200 import multi
-        region_bytes = FRAMES * frame_bytes
-        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            gather_base = g.voxgpu_malloc(world * region_bytes)
-            if not gather_base:
-                raise vv.VoxError(g.voxgpu_last_error().decode())
-            hb = (C.c_ubyte * 64)()
-            ok = g.voxgpu_ipc_export(gather_base, hb) == 0
-            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
-        dist.broadcast(handle, 0)
-        if rank == 0:
-            peer_base = gather_base
-        else:
-            hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
-            peer_base = g.voxgpu_ipc_open(hb)
-        flag = torch.tensor([1 if peer_base else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        gather_mode = "peer-store" if int(flag.item()) else "nccl"
+        peer_base, gather_base, gather_mode = E.share_buffer(world * region_bytes)
     if gather_mode == "peer-store":
         my_region = peer_base + rank * region_bytes
         ring_ptr = lambda i: my_region + (i % FRAMES) * frame_bytes
     elif gather_mode == "nccl":
         # fallback when peer mapping is unavailable: local ring, batches gathered with NCCL
+        from voxvision_b200 import multi
+        torch = E.torch
         tstreams = [torch.cuda.ExternalStream(st.value) for st in streams]
         comm_stream = torch.cuda.Stream(priority=-1)
         ring = torch.empty((2, GATHER_BATCH, H, W), dtype=torch.int32, device="cuda")
@@ -263,17 +330,11 @@ def run_own(args):
     else:
         bufs = [vv.DeviceBuffer(frame_bytes) for _ in range(RING)]
         ring_ptr = lambda i: bufs[i % RING].ptr
-    # the frame-to-frame tile schedule (voxgpu_sched) is off here: with several frames in flight the
-    # tails it removes are already filled, and its sorting kernel costs 6 us per frame (profiles/)
-    scheds = [None for _ in streams]
-
-    def flush_l2():
-        g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)
 
     def device_step():
         """360 launches back to back, FRAME_STREAMS frames in flight.  N>1: the pixels land in GPU 0's
         memory as they are produced (peer stores); fallback: NCCL gather of every GATHER_BATCH frames."""
-        flush_l2()
+        g.voxgpu_memset(flush_b.ptr, 0, 256 << 20, s_ptr)      # L2 flush
         for st in streams[1:]:
             g.voxgpu_stream_join(st, s_ptr)      # the step's first mark / flush precedes every stream's frames
         batch_done = []
@@ -281,8 +342,7 @@ def run_own(args):
             k = f % FRAME_STREAMS
             if gather_mode == "nccl" and f >= 2 * GATHER_BATCH and f % GATHER_BATCH < FRAME_STREAMS:
                 tstreams[k].wait_event(batch_done[f // GATHER_BATCH - 2])      # this half of the ring is free again
-            rc = g.voxgpu_render_sched(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None,
-                                       streams[k], scheds[k])
+            rc = g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, ring_ptr(f), None, None, streams[k])
             if rc:
                 raise vv.VoxError(g.voxgpu_last_error().decode())
             if gather_mode == "nccl" and f % GATHER_BATCH == GATHER_BATCH - 1:
@@ -298,19 +358,11 @@ def run_own(args):
         if gather_mode == "nccl":
             tstreams[0].wait_stream(comm_stream)
 
-    def sync_all():
-        if world > 1:
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-        else:
-            g.voxgpu_synchronize(None)
-
     timer = vv.Timer()
     for _ in range(max(args.warmup, 3)):
         device_step()
-    sync_all()
-    sampler = ClockSampler(local_rank)
+    E.sync_all()
+    sampler = ClockSampler(E.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
@@ -319,18 +371,15 @@ def run_own(args):
     for _ in range(args.steps):
         device_step()
     timer.stop(s_ptr)
-    sync_all()
-    ms_total = timer.elapsed_ms()
+    E.sync_all()
+    ms_total = E.max_over_ranks(timer.elapsed_ms())
     launches = vv.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     # N>1: what landed on GPU 0 must be the frames the ranks rendered
     gather_check = None
     if gather_mode == "peer-store" and rank == 0:
+        cam = vv.Camera("simple-camera")
         scratch = vv.DeviceBuffer(frame_bytes)
         got = np.empty((H, W), np.uint32)
         bad = 0
@@ -344,117 +393,333 @@ def run_own(args):
                 bad += int(not np.array_equal(got, scratch.download(np.uint32, (H, W))))
         gather_check = "ok" if bad == 0 else f"{bad} of {3 * world} sampled frames differ"
 
-    # kernel-only duration (no gather, no flush): CUDA events around each launch, same stream
+    # kernel-only duration (no gather, no flush): CUDA events around each launch (k_mark + k_list + K1), same stream
     kt = vv.Timer()
     kscratch = vv.DeviceBuffer(frame_bytes)
     kernel_ms = []
-    for f in range(0, FRAMES, 4):
-        kt.start(s_ptr)
-        g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, kscratch.ptr, None, None, s_ptr)
-        kt.stop(s_ptr)
-        kernel_ms.append(kt.elapsed_ms())
-    sync_all()
+    for rep in range(2):                # the first round touches every render slot once (first use allocates its mask)
+        kernel_ms = []
+        for f in range(0, FRAMES, 4):
+            kt.start(s_ptr)
+            g.voxgpu_render(dev_tree, C.byref(gcams[f]), C.byref(frame_desc), d_tex, kscratch.ptr, None, None, s_ptr)
+            kt.stop(s_ptr)
+            kernel_ms.append(kt.elapsed_ms())
+    E.sync_all()
+    return {"ms_total": ms_total, "launches": int(launches), "clocks": clocks, "gather_mode": gather_mode,
+            "gather_check": gather_check, "kernel_ms": kernel_ms,
+            "nvlink_gbs_into_gpu0": (round((world - 1) * args.steps * region_bytes / (ms_total * 1e-3) / 1e9, 1)
+                                     if gather_mode == "peer-store" else None)}
 
-    # ---- end-to-end leg: the reference-facing API with host surfaces ----------
-    # Every frame: camera setters -> vox_context_set_camera -> vox_render -> vox_redraw, the frame
-    # ends up in surface->pixels (host memory) and one pixel of it is read by the host.
-    # E2E_CONTEXTS contexts (each with its own page-locked surface, like a swap chain) take the
-    # frames round-robin, so frame f+1.. render while frame f crosses PCIe; with one context
-    # (`e2e.single_context`) render and copy-out of consecutive frames cannot overlap.
-    def make_ctx():
-        c = vv.Context(W, H)
-        c.set_scene(tree)
-        c.set_quality(vv.QUALITY_BEST)
-        return c, vv.Camera("simple-camera")
 
-    def e2e_step(ring):
-        k, acc = len(ring), 0
-        for f in range(FRAMES):
-            c, cm = ring[f % k]
-            if f >= k:
-                c.redraw()                                   # frame f-k is now in its surface->pixels
-                acc ^= int(c.pixels()[H // 2, W // 2])
-            pos, look = poses[f]
-            cm.set_position(pos)
-            cm.look_at(look)
-            c.set_camera(cm)
-            c.render()
-        for f in range(FRAMES, FRAMES + k):
-            c, _ = ring[f % k]
-            c.redraw()
-            acc ^= int(c.pixels()[H // 2, W // 2])
-        return acc
+def leg_e2e(E, args, tree, poses):
+    """The reference-facing API from C (examples/orbit_bench.c), host surfaces, every frame looked at."""
+    world, rank = E.world, E.rank
+    pose_arr = np.ascontiguousarray([list(p) + list(l) for p, l in poses], np.float32)
+    steps = max(1, min(args.steps, 3))
 
-    def time_e2e(ring, steps):
-        for _, cm in ring:
-            cm.set_fov(FOV)
-        e2e_step(ring)
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            e2e_step(ring)
-        sync_all()
-        dt = time.perf_counter() - t0
+    def run(contexts, devices, quality, all_ranks=True, nframes=FRAMES):
+        """-> (Mrays/s over the ranks that took part, devices used)"""
+        res = OrbitBenchResult()
+        E.sync_all()
+        secs = 0.0
+        if all_ranks or rank == 0:
+            rc = E.orbit.orbit_bench_run(tree.h, W, H, nframes, pose_arr.ctypes.data, FOV, contexts, devices, quality, steps, C.byref(res))
+            if rc:
+                raise E.vv.VoxError("orbit_bench_run: " + res.error.decode())
+            secs = res.seconds
+        secs = E.max_over_ranks(secs)
+        E.sync_all()
+        ranks = world if all_ranks else 1
+        return ranks * steps * nframes * RAYS_PER_FRAME / secs / 1e6, int(res.devices)
+
+    out = {}
+    ring, _ = run(E2E_CONTEXTS, 1, 0)
+    one, _ = run(1, 1, 0)
+    ada_ring, _ = run(E2E_CONTEXTS, 1, 2)
+    ada_one, _ = run(1, 1, 2)
+    out.update({"value": round(ring, 2), "unit": "Mrays/s", "steps": steps, "contexts_in_flight": E2E_CONTEXTS,
+                "single_context": round(one, 2),
+                "adaptive": {"value": round(ada_ring, 2), "single_context": round(ada_one, 2),
+                             "what": "the same legs in the reference's DEFAULT quality (ADAPTIVE, renderer.c:78): "
+                                     "K1 root searches + the block-sequential walk, two launches per band"}})
+    if world > 1:
+        # one PROCESS, all N GPUs: rank 0 alone, the other ranks wait at the barrier with idle GPUs
+        out["single_context_per_rank"] = out["single_context"]
+        split_one, used = run(1, 0, 0, all_ranks=False)
+        split_ring, _ = run(E2E_CONTEXTS, 0, 0, all_ranks=False)
+        out["single_context"] = round(split_one, 2)
+        out["in_process"] = {"devices": used, "single_context": round(split_one, 2), "ring": round(split_ring, 2),
+                             "what": "ONE process (rank 0; the other ranks idle) drives all GPUs behind vox_render: every frame's tile "
+                                     "rows dealt to the devices (vox_context_set_devices), each device DMA-copies its rows into the "
+                                     "surface over its own PCIe link"}
+    # what the host side of this box absorbs: plain DMA copies of frame-sized buffers, all ranks at once
+    g, vv = E.g, E.vv
+    frame_bytes = W * H * 4
+    d_src = vv.DeviceBuffer(frame_bytes)
+    hosts = [g.voxgpu_host_alloc(frame_bytes) for _ in range(4)]
+    st = C.c_void_p(g.voxgpu_stream_create())
+    for h in hosts:
+        g.voxgpu_memcpy_d2h(h, d_src.ptr, frame_bytes, st)
+    E.sync_all()
+    t0 = time.perf_counter()
+    copies = 400
+    for i in range(copies):
+        g.voxgpu_memcpy_d2h(hosts[i % 4], d_src.ptr, frame_bytes, st)
+    g.voxgpu_synchronize(st)
+    mine = copies * frame_bytes / (time.perf_counter() - t0) / 1e9
+    total = E.sum_over_ranks(mine)
+    E.sync_all()
+    for h in hosts:
+        g.voxgpu_host_free(h)
+    out["d2h_ceiling"] = {"gbs_all_ranks": round(total, 1), "gbs_this_rank": round(mine, 1),
+                          "mrays_equivalent": round(total * 1e9 / 4 / 1e6, 1),
+                          "what": f"{copies} back-to-back cudaMemcpyAsync of one 8.3 MB frame device->pinned host per rank, all "
+                                  f"{world} ranks at once: the rate no e2e figure on this box can exceed (4 B per ray)"}
+    out["h2d_bytes_per_step"] = FRAMES * (C.sizeof(E.api.GpuCamera) + C.sizeof(E.api.GpuFrame))
+    out["d2h_bytes_per_step"] = FRAMES * frame_bytes
+    out["path"] = ("examples/orbit_bench.c: vox_context_set_camera + vox_render + vox_redraw per frame and a host read of the "
+                   "finished surface, on a ring of contexts (each with its own page-locked surface): band kernels into a "
+                   "device framebuffer, each band DMA-copied into the surface while the next band / next frame renders")
+    return out
+
+
+def leg_c5(E, args):
+    """BASELINE.json configs[4]: the 7680x4320 frame of the ~100 M-voxel volume, tile rows interleaved over the ranks,
+    every rank storing its rows into the ONE frame buffer on GPU 0 (peer mapping), each with a screen mask of its rows."""
+    vv, api, ds, g, world, rank = E.vv, E.api, E.ds, E.g, E.world, E.rank
+    from voxvision_b200 import multi
+    t0 = time.perf_counter()
+    flat, n_vox, tree = None, 0, None
+    if rank == 0:
+        vox = ds.ball_union_voxels(C5_SIDE, C5_BALLS)
+        n_vox = len(vox)
+        t_gen = time.perf_counter() - t0
+        tree = vv.Tree.build(vox)
+        del vox
+        t_build = time.perf_counter() - t0 - t_gen
+        flat = tree.export()
+    t1 = time.perf_counter()
+    if world > 1:
+        got = multi.broadcast_flat_tree(flat, 0, device=E.torch.device("cuda", E.local_rank))
+        if rank != 0:
+            tree = vv.Tree.from_arrays(got)
+        del got
+        E.torch.cuda.empty_cache()
+    t_repl = time.perf_counter() - t1
+    dev_tree = tree.device_handle()
+
+    scale = C5_SIDE / 256.0
+    centre = (C5_SIDE / 2.0,) * 3
+    cam = vv.Camera("simple-camera")
+    gcams, cposes = [], []
+    for k in range(C5_POSES):
+        pos, look = ds.orbit_pose(k * 360.0 / C5_POSES, 360, centre, 328.0 * scale)
+        ds.setup_camera(cam, pos, look, FOV, C5_W, C5_H)
+        gcams.append(cam.gpu_camera())
+        cposes.append((pos, look))
+    ctx = vv.Context(16, 4)
+    fmt, tex = ctx.pixfmt(), ctx.texture()
+    d_tex = vv.DeviceBuffer.from_array(tex)
+    frame_bytes = C5_W * C5_H * 4
+    base, owner_base, mode = E.share_buffer(frame_bytes)
+    if mode == "nccl":
+        raise SystemExit("bench.py: peer mapping of GPU 0's frame buffer failed: " + g.voxgpu_last_error().decode())
+    streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(4)]
+    s0 = streams[0]
+
+    def render_frame(k, vrank, vworld, target):
+        fr = api.GpuFrame(C5_W, C5_H, 0, C5_H, C5_W, vv.QUALITY_BEST, fmt, None, vworld, vrank)
+        if g.voxgpu_render(dev_tree, C.byref(gcams[k]), C.byref(fr), d_tex.ptr, target, None, None, streams[k % 4]):
+            raise vv.VoxError(g.voxgpu_last_error().decode())
+
+    def step(vrank, vworld, target):
+        for st in streams[1:]:
+            g.voxgpu_stream_join(st, s0)
+        for k in range(C5_POSES):
+            render_frame(k, vrank, vworld, target)
+        for st in streams[1:]:
+            g.voxgpu_stream_join(s0, st)
+
+    timer = vv.Timer()
+    steps = max(1, min(args.steps, 3))
+    for _ in range(2):
+        step(rank, world, base)
+    E.sync_all()
+    timer.start(s0)
+    for _ in range(steps):
+        step(rank, world, base)
+    timer.stop(s0)
+    E.sync_all()
+    ms = E.max_over_ranks(timer.elapsed_ms())
+    # Frames of the timed region overlap on four streams and share the one frame buffer; for the check every
+    # rank draws its share of the LAST pose once more, alone.
+    render_frame(C5_POSES - 1, rank, world, base)
+    E.sync_all()
+
+    out = None
+    if rank == 0:
+        # the same frames on ONE GPU, in the same run: the base of the strong-scaling figure
+        own = vv.DeviceBuffer(frame_bytes)
+        ms_n1 = ms
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
+            step(0, 1, own.ptr)
+            g.voxgpu_synchronize(None)
+            timer.start(s0)
+            for _ in range(steps):
+                step(0, 1, own.ptr)
+            timer.stop(s0)
+            ms_n1 = timer.elapsed_ms()
+        last = C5_POSES - 1
+        gathered = np.empty((C5_H, C5_W), np.uint32)
+        g.voxgpu_memcpy_d2h(gathered.ctypes.data, owner_base, frame_bytes, None)
+        g.voxgpu_synchronize(None)
+        fr = api.GpuFrame(C5_W, C5_H, 0, C5_H, C5_W, vv.QUALITY_BEST, fmt, None)
+        d_leaf, d_pts = vv.DeviceBuffer(C5_W * C5_H * 4), vv.DeviceBuffer(C5_W * C5_H * 16)
+        if g.voxgpu_render(dev_tree, C.byref(gcams[last]), C.byref(fr), d_tex.ptr, own.ptr, d_leaf.ptr, d_pts.ptr, None):
+            raise vv.VoxError(g.voxgpu_last_error().decode())
+        alone = own.download(np.uint32, (C5_H, C5_W))
+        gather_ok = bool(np.array_equal(gathered, alone))
+        # oracle sample: every 4th pixel of every 4th row of that frame, searched by the CPU restatement on the same flat tree
+        from oracle import orc
+        P = orc.Oracle("port")
+        ocam = ds.setup_camera(P.camera(0), *cposes[last], FOV, C5_W, C5_H)
+        org, dirs = ocam.rays(C5_W, C5_H)
+        sel = (np.arange(0, C5_H, 4)[:, None] * C5_W + np.arange(0, C5_W, 4)[None, :]).reshape(-1)
+        so, sd = np.ascontiguousarray(org[sel]), np.ascontiguousarray(dirs[sel])
+        del org, dirs
+        threads = os.cpu_count() or 1
+        otree = P.tree_from_flat(flat)
+        oleaf, ohit, _, st = otree.rays(so, sd, threads=threads, want_stats=True)
+        del otree
+        leaf = d_leaf.download(np.int32, (C5_H * C5_W,))[sel]
+        pts = d_pts.download(np.float32, (C5_H * C5_W, 4))[sel][:, :3]
+        m = oleaf >= 0
+        oracle_sample = {"rays": int(len(sel)), "hits": int(m.sum()), "leaf_ids_equal": bool(np.array_equal(leaf, oleaf)),
+                         "hit_bits_equal": bool(np.array_equal(pts[m].view(np.uint32), ohit[m].view(np.uint32))),
+                         "oracle": P.name}
+        bytes_per_ray = (st["inner"] * BYTES_INNER + st["leaf"] * BYTES_LEAF + st["dense"] * BYTES_DENSE +
+                         st["dots_tested"] * BYTES_DOT) / len(sel) + BYTES_PIXEL
+        rays = steps * C5_POSES * C5_W * C5_H
+        value = rays / (ms * 1e-3) / 1e6
+        peak, _ = measured_peak()
+        ti = tree.info()
+        out = {"metric": "Mrays/s primary-ray render (synthetic 1024^3 volume, 7680x4320)", "value": round(value, 2), "unit": "Mrays/s",
+               "n_gpus": world, "scaling": "strong", "steps": steps, "frames_per_step": C5_POSES,
+               "ms_per_frame": round(ms / steps / C5_POSES, 4),
+               "ms_per_frame_one_gpu_same_run": round(ms_n1 / steps / C5_POSES, 4),
+               "strong_efficiency_vs_n1": round(ms_n1 / (world * ms), 4),
+               "gather": mode, "gather_check": "ok" if gather_ok else "gathered frame differs from the one-GPU frame",
+               "nvlink_gbs_into_gpu0": round((world - 1) / world * rays * 4 / (ms * 1e-3) / 1e9, 1) if world > 1 else None,
+               "oracle_sample": oracle_sample, "lit_pixels": int((alone != 0).sum()),
+               "partition": f"4-row tile rows interleaved over {world} GPU(s) (rank r draws rows r, r+{world}, ...; one k_mark + k_list + K1 per "
+                            f"frame per rank, each rank marking only its rows), tree built once on rank 0 and replicated over NCCL, "
+                            f"pixels stored into the frame buffer on GPU 0 ({mode})",
+               "data": f"synthetic: union of {C5_BALLS} balls with 1-in-8 hash holes in a {C5_SIDE}^3 grid, {n_vox} voxels",
+               "tree": {"nodes": int(ti.n_nodes), "inner": int(ti.n_inner), "leaf": int(ti.n_leaf), "dense": int(ti.n_dense),
+                        "dots": int(ti.n_dots), "depth": int(ti.depth), "device_bytes": int(g.voxgpu_tree_device_bytes(dev_tree))},
+               "host_seconds": {"generate": round(t_gen, 1), "vox_make_tree": round(t_build, 1), "replicate": round(t_repl, 1)},
+               "roofline": {"bound": "hbm", "bytes_per_ray": round(bytes_per_ray, 2),
+                            "achieved": round(bytes_per_ray * value * 1e6 / 1e9 / world, 2), "peak": peak, "unit": "GB/s per GPU",
+                            "frac": round(bytes_per_ray * value * 1e6 / 1e9 / world / peak, 5),
+                            "l2": "the 2.6 GB device tree does not fit the 126 MB L2: this config streams from HBM"}}
+    E.sync_all()
+    tree.destroy()
+    return out
 
-    e2e_steps = max(1, min(args.steps, 3))
-    ring = [make_ctx() for _ in range(E2E_CONTEXTS)]
-    if SHORT:       # under ncu: one pass of each leg is enough for the launch list
-        e2e_steps = 1
-    if SHORT >= 2:
-        e2e_single_s = e2e_s = float("inf")
-    else:
-        e2e_single_s = time_e2e(ring[:1], e2e_steps)
-        e2e_s = time_e2e(ring, e2e_steps)
+
+def run_own(args):
+    E = Env()
+    vv, api, ds, g, rank, world = E.vv, E.api, E.ds, E.g, E.rank, E.world
+
+    tree = vv.Tree.build(ds.volume_voxels("skull"))
+    ctx = vv.Context(W, H)
+    fmt, tex = ctx.pixfmt(), ctx.texture()
+    del ctx
+    # per-frame cameras: host-side camera maths, through the camera module's vtable
+    cam = vv.Camera("simple-camera")
+    gcams, poses = [], []
+    for f in range(FRAMES):
+        pos, look = frame_pose(ds, f, rank, world)
+        ds.setup_camera(cam, pos, look, FOV, W, H)
+        gcams.append(cam.gpu_camera())
+        poses.append((pos, look))
+    frame_desc = api.GpuFrame(W, H, 0, H, W, vv.QUALITY_BEST, fmt)
+    d_tex_b = vv.DeviceBuffer.from_array(tex)
+
+    dev = leg_c2_device(E, args, tree, gcams, frame_desc, d_tex_b.ptr)
+    e2e = leg_e2e(E, args, tree, poses) if "e2e" not in SKIP else None
     if vv.last_error():
         raise vv.VoxError(vv.last_error())
+    c5 = leg_c5(E, args) if "c5" not in SKIP else None
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            E.dist.destroy_process_group()
         return
 
+    ms_total = dev["ms_total"]
     total_rays = world * args.steps * FRAMES * RAYS_PER_FRAME
     value = total_rays / (ms_total * 1e-3) / 1e6
-    e2e_value = world * e2e_steps * FRAMES * RAYS_PER_FRAME / e2e_s / 1e6
 
     # ---- roofline + CPU baseline (rank 0; oracle = checker/baseline only) ----
     from oracle import orc
     threads = os.cpu_count() or 1
     peak, peak_src = measured_peak()
     bytes_per_launch = algorithmic_bytes_per_frame(ds, orc, list(range(0, FRAMES, 45)), threads)
+    kernel_ms = dev["kernel_ms"]
     mean_kernel_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_launch / (mean_kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, warp_inst = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "k_render_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, warp_inst = tj.get("dram_bytes_per_launch"), tj.get("warp_instructions_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_render", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+    in_flight_ms = ms_total / args.steps / FRAMES
+    clk = (dev["clocks"] or {}).get("sm_mhz") or 1965
+    issue_bound = None
+    if warp_inst:
+        peak_issue = SM_COUNT * SCHEDULERS * clk * 1e6          # warp instructions per second
+        issue_bound = {"warp_inst_per_frame": int(warp_inst),
+                       "peak_warp_inst_per_s": peak_issue, "sm_mhz_used": clk,
+                       "pct_of_peak_issue_lone": round(100 * warp_inst / (mean_kernel_ms * 1e-3) / peak_issue, 2),
+                       "pct_of_peak_issue_in_flight": round(100 * warp_inst / (in_flight_ms * 1e-3) / peak_issue, 2),
+                       "what": "warp instructions of one K1 launch (ncu smsp__inst_executed.sum, profiles/) / launch time / "
+                               "(148 SMs x 4 schedulers x SM clock): the tree is L2-resident, so this -- not HBM -- is the ceiling K1 runs against"}
+    roofline = {"bound": "hbm", "kernel": "k_render_persistent (+ k_mark, k_list: the launch as voxgpu_render queues it)",
+                "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": round(bytes_per_launch), "bytes_per_ray": round(bytes_per_launch / RAYS_PER_FRAME, 2),
                 "kernel_ms_mean": round(mean_kernel_ms, 5), "kernel_ms_min": round(float(np.min(kernel_ms)), 5),
                 "how": "achieved/frac: one launch at a time (CUDA events around each of 90 lone launches after the timed region); "
                        "in_flight: the timed region itself, ms_per_step / launches with FRAME_STREAMS launches overlapping",
-                "in_flight": {"ms_per_launch": round(ms_total / args.steps / FRAMES, 5),
-                              "achieved": round(bytes_per_launch / (ms_total / args.steps / FRAMES * 1e-3) / 1e9, 2),
-                              "frac": round(bytes_per_launch / (ms_total / args.steps / FRAMES * 1e-3) / 1e9 / peak, 5)},
+                "in_flight": {"ms_per_launch": round(in_flight_ms, 5),
+                              "achieved": round(bytes_per_launch / (in_flight_ms * 1e-3) / 1e9, 2),
+                              "frac": round(bytes_per_launch / (in_flight_ms * 1e-3) / 1e9 / peak, 5)},
+                "issue_bound": issue_bound,
                 "note": "the 18 MB tree is L2-resident, so DRAM traffic is far below the algorithmic bytes; "
-                        "the kernel is latency/issue bound (see profiles/)"}
+                        "the kernel is latency/issue bound (see issue_bound and profiles/)"}
     cpu_baseline = None
-    if world == 1 and not SHORT:
+    if world == 1 and "cpu" not in SKIP:
         O, kind = pick_cpu_oracle(orc)
         sample = list(range(0, FRAMES, 10))
         rate, secs = cpu_render_rate(ds, O, sample, 5, threads)
+        ada_rate, _ = cpu_render_rate(ds, O, sample[::4], 2, threads, quality=2)
         cpu_baseline = {"value": round(rate, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
-                        "oracle": O.name,
+                        "oracle": O.name, "adaptive": round(ada_rate, 3),
                         "sample": f"{len(sample)} of the {FRAMES} orbit frames (every 10th), quality BEST, "
-                                  f"OpenMP over 4x4 blocks on all {threads} host threads, best of 5 passes ({secs:.2f} s each)"}
+                                  f"OpenMP over 4x4 blocks on all {threads} host threads, best of 5 passes ({secs:.2f} s each); "
+                                  f"adaptive: 9 frames in the reference's default quality, best of 2"}
+    configs = None
+    if world == 1 and "configs" not in SKIP:
+        from tools import configs_bench as cb
+        configs = {}
+        for name, fn in (("C1", cb.c1), ("C3", cb.c3), ("C4", cb.c4)):
+            try:
+                configs[name] = fn()
+            except Exception as e:                      # noqa: BLE001 - a failing side config must not lose the headline
+                configs[name] = {"error": repr(e)}
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
@@ -465,25 +730,27 @@ def run_own(args):
         "config": {"workload": "C2: skull 1920x1080, 360-frame orbit, quality BEST, simple-camera",
                    "frames_per_step_per_gpu": FRAMES, "rays_per_frame": RAYS_PER_FRAME,
                    "frames_in_flight_per_gpu": FRAME_STREAMS,
-                   "parallelism": f"frames x{world} (tree replicated" + (f", frames gathered on GPU 0 in the timed region: {gather_mode})" if world > 1 else ")"),
-                   "gather": gather_mode, "gather_check": gather_check,
+                   "parallelism": f"frames x{world} (tree replicated" + (f", frames gathered on GPU 0 in the timed region: {dev['gather_mode']})" if world > 1 else ")"),
+                   "gather": dev["gather_mode"], "gather_check": dev["gather_check"],
+                   "nvlink_gbs_into_gpu0": dev["nvlink_gbs_into_gpu0"],
+                   "cpu_arm_sample": "the CPU arm (--impl reference, cpu_baseline) renders every 10th frame of the orbit (36 of 360) per "
+                                     "step; Mrays/s is per ray, so the arms compare directly",
                    "l2": "256 MB L2 flush at the start of every step; within a step the 18 MB tree stays "
                          "L2-resident across frames by design (every frame has a different camera and its own framebuffer)"},
-        "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s",
-                "h2d_bytes_per_step": FRAMES * (C.sizeof(api.GpuCamera) + C.sizeof(api.GpuFrame)),
-                "d2h_bytes_per_step": FRAMES * frame_bytes, "steps": e2e_steps,
-                "contexts_in_flight": E2E_CONTEXTS,
-                "single_context": round(world * e2e_steps * FRAMES * RAYS_PER_FRAME / e2e_single_s / 1e6, 2),
-                "path": "vox_render + vox_redraw per frame on a ring of contexts (each with its own page-locked surface): band kernels into a device framebuffer, each band DMA-copied into the surface while the next band / next frame renders"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": dev["launches"],
+        "clocks": dev["clocks"],
         "roofline": roofline,
+        "c5": c5,
+        "sse_divergence": sse_divergence(),
     }
     if cpu_baseline:
         out["cpu_baseline"] = cpu_baseline
+    if configs:
+        out["configs"] = configs
     print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        E.dist.destroy_process_group()
 
 
 def main():

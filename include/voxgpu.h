@@ -111,6 +111,10 @@ typedef struct
        other pixel of the band untouched, so N GPUs writing into ONE frame buffer get statistically
        identical shares of the image in one launch each.  0 / 1: the whole band.  Quality BEST only. */
     int interleave_world, interleave_rank;
+    /* The node the searches start from: 0 = the whole tree; the breadth-first id of an inner node or leaf
+       renders that subtree only (the reference accepts any node as a scene: vox_context_set_scene with
+       what vox_ray_tree_intersection returned, renderer.c:297). */
+    uint32_t start_node;
 } voxgpu_frame;
 
 /** Counters of the instrumented ("stats") variant of the ray kernel. */
@@ -155,6 +159,8 @@ VOXGPU_EXPORT int   voxgpu_stream_join (voxgpu_stream waiter, voxgpu_stream othe
 VOXGPU_EXPORT int   voxgpu_ipc_export (const void *dptr, unsigned char handle[VOXGPU_IPC_HANDLE_BYTES]);
 VOXGPU_EXPORT void* voxgpu_ipc_open (const unsigned char handle[VOXGPU_IPC_HANDLE_BYTES]);
 VOXGPU_EXPORT int   voxgpu_ipc_close (void *dptr);
+/** One process, several devices: kernels of the current device may then store into `peer_device`'s memory. */
+VOXGPU_EXPORT int   voxgpu_enable_peer (int peer_device);
 
 /* ---- tree ---- */
 /** Convert to the device layout and upload (cudaMemcpyAsync from pinned staging) on the current device. */
@@ -177,6 +183,16 @@ VOXGPU_EXPORT int voxgpu_rays_device (const voxgpu_tree *tree, uint32_t start_no
                                       const float *d_origins, const float *d_dirs, size_t n,
                                       int32_t *d_leaf_ids, float *d_points, int32_t *d_voxels,
                                       voxgpu_stream stream);
+/** Order in which voxgpu_rays_device searches a batch: -1 (default; $VOXGPU_RAYS_SORT sets the start-up value)
+    = batches of 262 144 rays and more in the order of the Morton code of the point where each ray enters the
+    start node's box (two-pass radix sort of the ray indices on the device, results scattered back to the
+    caller's positions), smaller ones as given; 0 = always as given; 1 = always in entry order.  Results do
+    not depend on it: the search of a ray is a function of the ray. */
+VOXGPU_EXPORT void voxgpu_set_rays_sort (int mode);
+/** Batches searched in entry order run on persistent warps whose lanes take a new ray as soon as this many
+    lanes of the warp are idle (1..32; default 8, $VOXGPU_RAYS_REFILL sets the start-up value); 0 = one ray per
+    thread for the lifetime of the warp.  Results do not depend on it. */
+VOXGPU_EXPORT void voxgpu_set_rays_refill (int lanes);
 /** Host buffers: copies in, runs, copies out, synchronises. n_hits may be NULL. */
 VOXGPU_EXPORT int voxgpu_rays_host (const voxgpu_tree *tree, uint32_t start_node,
                                     const float *origins, const float *dirs, size_t n,
@@ -187,6 +203,17 @@ VOXGPU_EXPORT int voxgpu_rays_stats (const voxgpu_tree *tree, uint32_t start_nod
                                      const float *d_origins, const float *d_dirs, size_t n,
                                      int32_t *d_leaf_ids, float *d_points, int32_t *d_voxels,
                                      voxgpu_stats *stats);
+
+/* ---- raw volume -> voxel list (reference: src/voxtrees/datareader.c:51-76) ----
+ * `volume`: dim[0]*dim[1]*dim[2] samples of `samplesize` (1..4) bytes, little-endian, x outer / z inner, in HOST
+ * memory.  Keeps the samples with min <= sample < max_excl (datareader.c's Block reduced to the range
+ * predicate of the Lua binding, src/voxengine/modules/voxtrees.c:306-342; "sample > t" is [t+1, 2^32)).
+ * The volume is uploaded, thresholded and stream-compacted on the device in the reference's order; on
+ * success *count voxels {i*voxel[0], j*voxel[1], k*voxel[2], 0} (float4 = vox_dot) are in *dots, page-locked
+ * host memory the caller releases with voxgpu_host_free (NULL when *count == 0). */
+VOXGPU_EXPORT int voxgpu_volume_extract (const void *volume, const unsigned dim[3], unsigned samplesize,
+                                         unsigned min, unsigned long long max_excl, const float voxel[3],
+                                         float **dots, size_t *count);
 
 /* ---- batched ball queries (K3) ---- centers: float4 per ball; out: 1 byte per ball. */
 VOXGPU_EXPORT int voxgpu_balls_device (const voxgpu_tree *tree, const float *d_centers,
@@ -207,20 +234,6 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
                                  uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
                                  voxgpu_stream stream);
 
-/** Frame-to-frame tile schedule for voxgpu_render_sched: tiles in whose neighbourhood the
-    previous launch on this schedule found expensive tiles are handed out first in the next
-    one (one extra small kernel per launch).  Launches sharing a schedule must
-    be ordered (same stream).  Purely a performance hint: results do not depend on it.
-    $VOXGPU_HEAVY_ITERS / $VOXGPU_MID_ITERS set the class thresholds (HEAVY = 0: off). */
-typedef struct voxgpu_sched voxgpu_sched;
-VOXGPU_EXPORT voxgpu_sched* voxgpu_sched_create (void);
-VOXGPU_EXPORT void voxgpu_sched_destroy (voxgpu_sched *sched);
-/** voxgpu_render with a schedule (NULL = none). */
-VOXGPU_EXPORT int voxgpu_render_sched (const voxgpu_tree *tree, const voxgpu_camera *camera,
-                                       const voxgpu_frame *frame, const uint8_t *d_texture,
-                                       uint32_t *d_pixels, int32_t *d_leaf_ids, float *d_points,
-                                       voxgpu_stream stream, voxgpu_sched *sched);
-
 /* ---- frames to host memory ----
  * What vox_render + vox_redraw (renderer.c:200-327) use when the surface is in
  * host memory: the frame is rendered into a device framebuffer in `bands`
@@ -228,7 +241,10 @@ VOXGPU_EXPORT int voxgpu_render_sched (const voxgpu_tree *tree, const voxgpu_cam
  * stream and each followed by a DMA copy into `host_pixels`, which must be
  * page-locked (voxgpu_host_alloc / voxgpu_host_register).  _render returns as
  * soon as the work is queued; _wait returns once every band has landed.
- * frame->y0/y1/pitch_pixels are ignored (the whole frame is drawn). */
+ * frame->y0/y1/pitch_pixels are ignored (the whole frame is drawn) -- or, with
+ * frame->interleave_world = N > 1, this device's share of a frame that N devices
+ * split: the tile rows r with r % N == interleave_rank, one launch, one strided
+ * DMA copy of exactly those rows into `host_pixels` (needs host_pitch_bytes == 4*w). */
 typedef struct voxgpu_present voxgpu_present;
 VOXGPU_EXPORT voxgpu_present* voxgpu_present_create (int w, int h, int bands);
 VOXGPU_EXPORT void voxgpu_present_destroy (voxgpu_present *p);
@@ -242,15 +258,27 @@ VOXGPU_EXPORT float voxgpu_present_last_ms (voxgpu_present *p);
 /** The device framebuffer the last frame was rendered into (w*h pixels, pitch w). */
 VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p);
 
-/** Development knob: 0 = the first, one-CTA-per-4-tiles render kernel with the
-    plain (lazy, reference-shaped) traversal, 1 = the persistent kernel with the
-    eager traversal and strip-interleaved tile order (default), 2 = as 1 with
-    raster tile order, 3 = per-lane work refill (k_render_stream).  Kept for A/B
-    measurements; results are identical. */
-VOXGPU_EXPORT void voxgpu_set_variant (int variant);
-/** Variant 3: refill a warp as soon as this many of its 32 lanes are idle (1..32). */
-VOXGPU_EXPORT void voxgpu_set_refill_min (int lanes);
+/* ---- one frame on all GPUs of the process ----
+ * The in-process counterpart of the reference's fan-out inside vox_render (dispatch_apply over the
+ * blocks, renderer.c:214-226): device i of `devices` draws the tile rows r with r % ndev == i and
+ * DMA-copies them into the page-locked `host_pixels` over its own PCIe link; one worker thread per
+ * device queues its share.  trees[i] / d_tex[i] / lights[i] are the replicas on devices[i] (lights may
+ * be NULL).  Quality BEST only.  _render returns when every share is queued, _wait when all have landed. */
+typedef struct voxgpu_multi voxgpu_multi;
+VOXGPU_EXPORT voxgpu_multi* voxgpu_multi_create (int w, int h, int ndev, const int *devices);
+VOXGPU_EXPORT void voxgpu_multi_destroy (voxgpu_multi *m);
+VOXGPU_EXPORT int voxgpu_multi_devices (const voxgpu_multi *m);
+VOXGPU_EXPORT int voxgpu_multi_device (const voxgpu_multi *m, int i);
+VOXGPU_EXPORT int voxgpu_multi_render (voxgpu_multi *m, const voxgpu_tree *const *trees, const voxgpu_camera *camera,
+                                       const voxgpu_frame *frame, const uint8_t *const *d_tex,
+                                       const voxgpu_lights *const *lights, void *host_pixels, size_t host_pitch_bytes);
+VOXGPU_EXPORT int voxgpu_multi_wait (voxgpu_multi *m);
+/** Slowest device's time from its launch to the arrival of its share in host memory, ms (waits). */
+VOXGPU_EXPORT float voxgpu_multi_last_ms (voxgpu_multi *m);
 
+/** Development knob: 1 = strip-interleaved tile order in the dark-tile / unmasked phase of the render
+    kernel (default), 2 = raster order.  Kept for A/B measurements; results are identical. */
+VOXGPU_EXPORT void voxgpu_set_variant (int variant);
 /** Screen-space culling of 8x4 tiles that cannot show a voxel.  1 (default): the bounds of the tree's
     root box AND a per-launch screen mask marked from the boxes of a cut through the tree (k_mark);
     2: the root-box bounds only; 0: none ($VOXGPU_NO_CULL=1, $VOXGPU_NO_MASK=1 set the start-up value).
@@ -262,9 +290,9 @@ VOXGPU_EXPORT void voxgpu_set_cull (int on);
 VOXGPU_EXPORT void voxgpu_screen_bounds (const float root_min[3], const float root_max[3], const voxgpu_camera *camera,
                                          int w, int h, int out[4]);
 
-/** Development trace: when non-NULL, every following voxgpu_render launch (persistent
-    variants) records per 8x4 tile {start ns, end ns, smid<<32 | warp} (3 x uint64 per
-    tile of the launch's band, device memory supplied by the caller).  NULL switches it off. */
+/** Development trace: when non-NULL, every following unlit BEST voxgpu_render launch records per
+    traversed 8x4 tile {start ns, end ns, smid<<32 | node visits of the slowest lane} (3 x uint64 per
+    tile of the WHOLE frame, device memory supplied by the caller).  NULL switches it off. */
 VOXGPU_EXPORT void voxgpu_set_trace (void *d_trace);
 
 /** Number of kernels this library has launched in this process (for bench.py's gpu_launches). */

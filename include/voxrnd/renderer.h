@@ -86,6 +86,18 @@ VOX_EXPORT void vox_render (struct vox_rnd_ctx *ctx);
 VOX_EXPORT void vox_context_set_texture (struct vox_rnd_ctx *ctx, const Uint8 *texture);
 VOX_EXPORT const Uint8* vox_context_get_texture (const struct vox_rnd_ctx *ctx);
 
+/**
+   \brief Draw every frame of this context on up to `n` CUDA devices of the process (0 = all visible
+   devices, 1 = only the device that is current at the first vox_render(): the default, or what
+   $VOXVISION_DEVICES says).  This is the counterpart of the reference's fan-out over all cores inside
+   vox_render (dispatch_apply over the blocks, renderer.c:214-226): device k draws the 4-row tile rows
+   r with r % n == k and copies them into surface->pixels over its own PCIe link; the tree, the texture
+   and the lights are replicated on first use.  Applies to quality BEST; the other quality modes, whose
+   blocks depend on their own previous pixels, stay on the first device.  Returns the number of devices
+   that will be used, 0 if there is no device.  vox_render / vox_redraw are called as before.
+**/
+VOX_EXPORT int vox_context_set_devices (struct vox_rnd_ctx *ctx, int n);
+
 /** Time in milliseconds the GPU spent in the last completed vox_render() kernel. */
 VOX_EXPORT float vox_context_last_kernel_ms (struct vox_rnd_ctx *ctx);
 

@@ -32,6 +32,20 @@ VOX_EXPORT struct vox_node* vox_read_raw_data_threshold (const char *filename, u
                                                          unsigned int threshold,
                                                          const char **error);
 
+/**
+   \brief Same, keeping samples with min <= sample < max, the predicate of the reference's Lua binding
+   (`voxtrees.read_raw_data_ranged`, src/voxengine/modules/voxtrees.c:306-342).
+
+   This and vox_read_raw_data_threshold() extract the voxel list ON THE DEVICE when a CUDA device is
+   present (libvoxgpu: volume upload, threshold, stable stream compaction in the reference's x-outer /
+   z-inner order, voxgpu_volume_extract) and hand it to vox_make_tree(); without a device the host loop of
+   vox_read_raw_data_fn() does it.  $VOXTREES_LOADER=host|gpu forces one of the two (tests compare them).
+**/
+VOX_EXPORT struct vox_node* vox_read_raw_data_range (const char *filename, unsigned int dim[],
+                                                     unsigned int samplesize,
+                                                     unsigned int min, unsigned int max,
+                                                     const char **error);
+
 /** \brief Find a data file in the usual places (datareader.c:105-125). **/
 VOX_EXPORT int vox_find_data_file (const char *filename, char *fullpath);
 

@@ -688,9 +688,10 @@ def test_lights_follow_changes(gpu, checker, skull, ds):
 # ------------------------------------------------- full-size configs, by properties
 
 def test_c3_full_size_properties(gpu, port, ds):
-    """C3: 16 Mi rays against the ~10 M-voxel random tree.  Too big for the CPU oracle in
-    seconds, so: known voxel count, a 64 Ki-ray oracle sample bit-exact, and size-independent
-    properties on the full batch (hit point on the hit voxel; leaf id is a leaf; determinism)."""
+    """C3: 16 Mi rays against the ~10 M-voxel random tree: known voxel count and tree shape, size-independent
+    properties on the full batch (hit point on the hit voxel; leaf id is a leaf; determinism; the order the
+    batch is searched in changes nothing) and EVERY ray against the oracle, bit for bit (the CPU search does
+    ~10 Mrays/s on this tree with all host threads: seconds, not minutes)."""
     vox, _ = ds.random_voxels()
     assert len(vox) == 10063815                     # SURVEY.md 8d
     t = gpu.Tree.build(vox)
@@ -710,12 +711,17 @@ def test_c3_full_size_properties(gpu, port, ds):
     assert ((p >= lo) & (p <= lo + 1)).all()        # the hit point lies on the hit voxel
     dm = m & (voxel < 0)
     assert ((pts[dm] >= fl["bb_min"][leaf[dm]]) & (pts[dm] <= fl["bb_max"][leaf[dm]])).all()
-    leaf2, pts2, _ = t.rays(o[: 1 << 20], d[: 1 << 20])
-    assert np.array_equal(leaf2, leaf[: 1 << 20]) and np.array_equal(bits(pts2), bits(pts[: 1 << 20]))
-    # oracle sample (the port builds the same tree in a few seconds)
+    g = gpu.api.libs.gpu
+    try:
+        g.voxgpu_set_rays_sort(0)                   # as given (the full batch above went in entry order)
+        leaf2, pts2, _ = t.rays(o[: 1 << 21], d[: 1 << 21])
+    finally:
+        g.voxgpu_set_rays_sort(-1)
+    assert np.array_equal(leaf2, leaf[: 1 << 21]) and np.array_equal(bits(pts2), bits(pts[: 1 << 21]))
+    # the whole batch against the oracle (the port builds the same tree in a few seconds)
     ot = port.tree(vox)
-    k = 1 << 16
-    assert_rays_equal((leaf[:k], pts[:k], voxel[:k]), ot.rays(o[:k], d[:k], threads=THREADS))
+    assert flat_equal(fl, ot.flatten()) == []
+    assert_rays_equal((leaf, pts, voxel), ot.rays(o, d, threads=THREADS))
 
 
 def test_c4_full_size(gpu, checker, ds, skull):

@@ -227,6 +227,25 @@ def test_raw_volume_loader(vv, port, ds, tmp_path, skull):
         vv.Tree.from_raw_file(str(tmp_path / "missing.dat"), (2, 2, 2), 1, 0)
 
 
+def test_raw_volume_range_loader(vv, tmp_path, monkeypatch):
+    """vox_read_raw_data_range: min <= sample < max (modules/voxtrees.c:306-342), 2-byte little-endian samples,
+    x outer / z inner (datareader.c:51-76).  The host loop, whatever the machine has."""
+    monkeypatch.setenv("VOXTREES_LOADER", "host")
+    rng = np.random.default_rng(5)
+    dim = (20, 17, 23)
+    samples = rng.integers(0, 1 << 16, dim[0] * dim[1] * dim[2], dtype=np.uint32)
+    path = str(tmp_path / "v16.dat")
+    samples.astype("<u2").tofile(path)
+    idx = np.flatnonzero((samples >= 20000) & (samples < 30000))
+    want = np.stack([idx // (dim[1] * dim[2]), (idx // dim[2]) % dim[1], idx % dim[2]], 1).astype(np.float32)
+    t = vv.Tree.from_raw_file(path, dim, 2, sample_range=(20000, 30000))
+    assert t.voxels() == len(idx)
+    assert flat_equal(t.export(), vv.Tree.build(want).export()) == []
+    monkeypatch.setenv("VOXTREES_LOADER", "nonsense")
+    with pytest.raises(vv.VoxError, match="host or gpu"):
+        vv.Tree.from_raw_file(path, dim, 2, sample_range=(0, 5))
+
+
 def test_no_gpu_means_loud_failure(vv):
     """The product has no CPU search path: without a device every query raises."""
     if vv.gpu_available():

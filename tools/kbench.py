@@ -1,13 +1,14 @@
 #!/usr/bin/env python
-"""Kernel A/B harness: for each variant, render the eight golden C2 frames,
-check them against the golden digests, and print CUDA-event kernel times with
-the frame going (a) to device memory and (b) to mapped pinned host memory.
+"""Kernel A/B harness: render the eight golden C2 frames, check them against the golden digests, and print
+CUDA-event times of LONE launches (the figure bench.py's roofline is computed from) for each heavy-tile
+threshold given (voxgpu_set_heavy_threshold; 0 = no heavy class).
 
-    python tools/kbench.py [variant ...]      variants: see voxgpu_set_variant
+    python tools/kbench.py [threshold ...]           default: 0
+    KBENCH_CULL=0|1|2                                voxgpu_set_cull for all runs (default 1)
 """
 import ctypes as C
-import json
 import hashlib
+import json
 import os
 import sys
 
@@ -21,9 +22,9 @@ from tools import datasets as ds
 W, H = 1920, 1080
 sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 gold = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "golden.json")))
-variants = [int(a) for a in sys.argv[1:]] or [1]
+thresholds = [int(a) for a in sys.argv[1:]] or [0]
 g = api.libs.gpu
-g.voxgpu_set_variant.argtypes = [C.c_int]
+g.voxgpu_set_cull(int(os.environ.get("KBENCH_CULL", "1")))
 tree = vv.Tree.build(ds.volume_voxels("skull"))
 dev = tree.device_handle()
 ctx = vv.Context(W, H)
@@ -31,29 +32,22 @@ d_tex = vv.DeviceBuffer.from_array(ctx.texture())
 d_pix = vv.DeviceBuffer(W * H * 4)
 d_leaf = vv.DeviceBuffer(W * H * 4)
 d_pts = vv.DeviceBuffer(W * H * 16)
-h_pix = g.voxgpu_host_alloc(W * H * 4)
-m_pix = g.voxgpu_host_device_pointer(h_pix)
-h_view = np.ctypeslib.as_array(C.cast(h_pix, C.POINTER(C.c_uint32)), (H, W))
 cam = vv.Camera()
 fr = api.GpuFrame(W, H, 0, H, W, 0, ctx.pixfmt())
 t = vv.Timer()
 frames = sorted(int(k) for k in gold["c2"])
 
 
-sched = g.voxgpu_sched_create()
-
-
-def timed(gc, target, reps=9, sc=None):
+def timed(gc, target, reps=15):
     ms = []
     for _ in range(reps):
-        t.start(); g.voxgpu_render_sched(dev, C.byref(gc), C.byref(fr), d_tex.ptr, target, None, None, None, sc); t.stop()
+        t.start(); g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, target, None, None, None); t.stop()
         ms.append(t.elapsed_ms())
     return sorted(ms)
 
 
-for v in variants:
-    g.voxgpu_set_variant(v)
-    tot_d = tot_m = tot_s = 0.0
+for thr in thresholds:
+    tot = 0.0
     for f in frames:
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
         gc = cam.gpu_camera()
@@ -65,24 +59,8 @@ for v in variants:
         ok = [sha(leaf) == want["leaf_sha"], sha(pts[m]) == want["hit_sha"], sha(pix) == want["pix_sha"]]
         md = timed(gc, d_pix.ptr)
         ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
-        # scheduled: as in an animation, every timed launch follows a launch of the frame one orbit step before
-        ds.setup_camera(cam, *ds.orbit_pose(f - 1), 1.2, W, H)
-        gprev = cam.gpu_camera()
-        ms_ = []
-        for _ in range(9):
-            g.voxgpu_render_sched(dev, C.byref(gprev), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None, sched)
-            ms_ += timed(gc, d_pix.ptr, reps=1, sc=sched)
-        ms_.sort()
-        ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
-        tot_s += ms_[len(ms_) // 2]
-        h_view[:] = 0xdeadbeef
-        mm = timed(gc, m_pix)
-        g.voxgpu_synchronize(None)
-        ok.append(sha(h_view) == want["pix_sha"])
-        tot_d += md[len(md) // 2]; tot_m += mm[len(mm) // 2]
-        print(f"variant {v} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
-              f"device min {md[0]:.4f} med {md[len(md)//2]:.4f} | scheduled min {ms_[0]:.4f} med {ms_[len(ms_)//2]:.4f} | mapped min {mm[0]:.4f} med {mm[len(mm)//2]:.4f} ms", flush=True)
+        tot += md[len(md) // 2]
+        print(f"heavy_t {thr:3d} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
+              f"lone launch min {md[0]:.4f} med {md[len(md)//2]:.4f} max {md[-1]:.4f} ms", flush=True)
     n = len(frames)
-    print(f"variant {v}: mean of per-frame medians: device {tot_d/n:.4f} ms -> {W*H/(tot_d/n)/1e3:.0f} Mrays/s | "
-          f"scheduled {tot_s/n:.4f} ms -> {W*H/(tot_s/n)/1e3:.0f} Mrays/s | "
-          f"mapped {tot_m/n:.4f} ms -> {W*H/(tot_m/n)/1e3:.0f} Mrays/s", flush=True)
+    print(f"heavy_t {thr}: mean of per-frame medians {tot/n:.4f} ms -> {W*H/(tot/n)/1e3:.0f} Mrays/s", flush=True)

@@ -101,7 +101,7 @@ class GpuPixFmt(C.Structure):
 class GpuFrame(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("pitch_pixels", C.c_int),
                 ("quality", C.c_uint), ("fmt", GpuPixFmt), ("lights", C.c_void_p),
-                ("interleave_world", C.c_int), ("interleave_rank", C.c_int)]
+                ("interleave_world", C.c_int), ("interleave_rank", C.c_int), ("start_node", C.c_uint32)]
 
 
 class GpuLightsFlat(C.Structure):
@@ -175,9 +175,16 @@ class _Libs:
         g.voxgpu_rays_stats.argtypes = [_vp, u32, _vp, _vp, sz, _vp, _vp, _vp, C.POINTER(GpuStats)]
         g.voxgpu_balls_device.argtypes = [_vp, _vp, _vp, sz, _vp, _vp]
         g.voxgpu_render.argtypes = [_vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, _vp, _vp, _vp]
-        g.voxgpu_render_sched.argtypes = [_vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, _vp, _vp, _vp, _vp]
-        g.voxgpu_sched_create.restype = _vp
-        g.voxgpu_sched_destroy.argtypes = [_vp]
+        g.voxgpu_set_cull.argtypes = [_i]
+        g.voxgpu_set_rays_sort.argtypes = [_i]
+        g.voxgpu_set_rays_refill.argtypes = [_i]
+        g.voxgpu_volume_extract.argtypes = [_vp, C.POINTER(C.c_uint * 3), C.c_uint, C.c_uint, C.c_ulonglong,
+                                            C.POINTER(C.c_float * 3), C.POINTER(_vp), C.POINTER(sz)]
+        g.voxgpu_set_trace.argtypes = [_vp]
+        g.voxgpu_present_create.restype = _vp; g.voxgpu_present_create.argtypes = [_i, _i, _i]
+        g.voxgpu_present_destroy.argtypes = [_vp]
+        g.voxgpu_present_render.argtypes = [_vp, _vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, sz]
+        g.voxgpu_present_wait.argtypes = [_vp]
         g.voxgpu_launch_count.restype = C.c_ulonglong
         g.voxgpu_timer_create.restype = _vp
         g.voxgpu_timer_destroy.argtypes = [_vp]
@@ -213,6 +220,9 @@ class _Libs:
         t.vox_read_raw_data_threshold.restype = _vp
         t.vox_read_raw_data_threshold.argtypes = [C.c_char_p, C.POINTER(C.c_uint * 3), C.c_uint, C.c_uint,
                                                   C.POINTER(C.c_char_p)]
+        t.vox_read_raw_data_range.restype = _vp
+        t.vox_read_raw_data_range.argtypes = [C.c_char_p, C.POINTER(C.c_uint * 3), C.c_uint, C.c_uint, C.c_uint,
+                                              C.POINTER(C.c_char_p)]
         t.vox_abs_metric.restype = _f; t.vox_abs_metric.argtypes = [_vp, _vp]
         t.vox_sqr_metric.restype = _f; t.vox_sqr_metric.argtypes = [_vp, _vp]
         t.vox_sqr_norm.restype = _f; t.vox_sqr_norm.argtypes = [_vp]
@@ -233,6 +243,7 @@ class _Libs:
         r.vox_context_set_texture.argtypes = [C.POINTER(_Ctx), _vp]
         r.vox_context_get_texture.restype = _vp; r.vox_context_get_texture.argtypes = [C.POINTER(_Ctx)]
         r.vox_context_last_kernel_ms.restype = _f; r.vox_context_last_kernel_ms.argtypes = [C.POINTER(_Ctx)]
+        r.vox_context_set_devices.restype = _i; r.vox_context_set_devices.argtypes = [C.POINTER(_Ctx), _i]
         r.vox_context_set_light_manager.argtypes = [C.POINTER(_Ctx), _vp]
         r.vox_make_light_manager.restype = _vp
         r.vox_destroy_light_manager.argtypes = [_vp]
@@ -382,10 +393,14 @@ class Tree:
         return cls(h)
 
     @classmethod
-    def from_raw_file(cls, path, dim, samplesize, threshold):
+    def from_raw_file(cls, path, dim, samplesize, threshold=None, sample_range=None):
+        """vox_read_raw_data_threshold (sample > threshold) or vox_read_raw_data_range (min <= sample < max)."""
         err = C.c_char_p()
         d = (C.c_uint * 3)(*dim)
-        h = libs.trees.vox_read_raw_data_threshold(path.encode(), C.byref(d), samplesize, threshold, C.byref(err))
+        if sample_range is not None:
+            h = libs.trees.vox_read_raw_data_range(path.encode(), C.byref(d), samplesize, sample_range[0], sample_range[1], C.byref(err))
+        else:
+            h = libs.trees.vox_read_raw_data_threshold(path.encode(), C.byref(d), samplesize, threshold, C.byref(err))
         if not h:
             raise VoxError((err.value or b"?").decode())
         return cls(h)
@@ -682,6 +697,10 @@ class Context:
 
     def set_quality(self, q):
         return bool(libs.rnd.vox_context_set_quality(self.h, q))
+
+    def set_devices(self, n):
+        """vox_context_set_devices: split every frame over up to n devices of this process (0 = all)."""
+        return int(libs.rnd.vox_context_set_devices(self.h, n))
 
     def set_texture(self, tex):
         tex = np.ascontiguousarray(tex, np.uint8)

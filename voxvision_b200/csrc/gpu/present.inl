@@ -1,5 +1,5 @@
 /* present.inl -- part of the single translation unit voxgpu.cu (included there, in this order):
-   frames to host memory: voxgpu_present_*. */
+   frames to host memory: voxgpu_present_* (one device) and voxgpu_multi_* (all devices of the process). */
 /* --------------------------------------------------- frames to host memory */
 
 /*
@@ -15,8 +15,14 @@
  * kernels are in flight at once, the block scheduler drains them in order, the
  * tail of one band is back-filled by the next, and the copy engine moves band i
  * while band i+1 renders.  Only the last band's copy is exposed.
+ *
+ * A presenter can also draw ONE SHARE of a frame that several GPUs split
+ * (frame->interleave_world / interleave_rank: the 4-row tile rows r with
+ * r % world == rank): one launch, then one strided DMA copy of exactly those rows
+ * into the surface over this GPU's own PCIe link.  voxgpu_multi_* below drives
+ * one such presenter per device.
  */
-#define PRESENT_MAX_BANDS 16
+#define PRESENT_MAX_BANDS MASK_MAX_BANDS
 
 struct voxgpu_present
 {
@@ -24,12 +30,10 @@ struct voxgpu_present
     uint32_t *fb;                         /* device framebuffer, w*h */
     cudaStream_t stream[PRESENT_MAX_BANDS];
     cudaEvent_t done[PRESENT_MAX_BANDS];
-    voxgpu_sched *sched[PRESENT_MAX_BANDS];  /* heavy-first tile order, frame to frame */
     cudaEvent_t start;
     int in_flight;                        /* a frame has been queued and not yet waited for */
     int used_bands;                       /* bands of the frame in flight */
-    unsigned char *mask;                  /* screen mask shared by the bands of a frame (k_mark), w/8 * h/4 + 4 bytes */
-    unsigned epoch;                       /* value that means "marked" in the current frame: no clearing between frames */
+    MaskBuf mask;                         /* screen mask shared by the bands of a frame (k_mark) */
     cudaEvent_t marked;
     int fixed_bands;                      /* band count was asked for explicitly: never adapt */
 };
@@ -43,17 +47,20 @@ static std::atomic<int> g_presents_in_flight (0);
 extern "C" void voxgpu_present_destroy (voxgpu_present *p)
 {
     if (!p) return;
+    int cur = -1;
+    cudaGetDevice (&cur);
+    if (cur != p->device) cudaSetDevice (p->device);
     for (int i=0; i<p->bands; i++)
     {
         if (p->stream[i]) { cudaStreamSynchronize (p->stream[i]); cudaStreamDestroy (p->stream[i]); }
         if (p->done[i]) cudaEventDestroy (p->done[i]);
-        voxgpu_sched_destroy (p->sched[i]);
     }
     if (p->start) cudaEventDestroy (p->start);
     if (p->marked) cudaEventDestroy (p->marked);
     if (p->in_flight) g_presents_in_flight--;
-    cudaFree (p->mask);
+    maskbuf_free (p->mask);
     cudaFree (p->fb);
+    if (cur != p->device && cur >= 0) cudaSetDevice (cur);
     free (p);
 }
 
@@ -71,14 +78,13 @@ extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
     if (bands > PRESENT_MAX_BANDS) bands = PRESENT_MAX_BANDS;
     if (bands > h / 4) bands = h / 4;
     voxgpu_present *p = (voxgpu_present*) calloc (1, sizeof *p);
+    if (!p) { fail ("voxgpu_present_create: out of memory"); return NULL; }
     p->w = w; p->h = h; p->bands = bands; p->fixed_bands = fixed;
     int least = 0, greatest = 0;
     cudaError_t e;
     if ((e = cudaGetDevice (&p->device)) != cudaSuccess ||
         (e = cudaDeviceGetStreamPriorityRange (&least, &greatest)) != cudaSuccess ||
         (e = cudaMalloc (&p->fb, (size_t) w * h * 4)) != cudaSuccess ||
-        (e = cudaMalloc (&p->mask, (size_t) (w >> 3) * (h >> 2) + 4)) != cudaSuccess ||
-        (e = cudaMemset (p->mask, 0, (size_t) (w >> 3) * (h >> 2) + 4)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags (&p->marked, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate (&p->start)) != cudaSuccess) goto bad;
     for (int i=0; i<bands; i++)
@@ -87,9 +93,6 @@ extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
         if (prio > least) prio = least;
         if ((e = cudaStreamCreateWithPriority (&p->stream[i], cudaStreamNonBlocking, prio)) != cudaSuccess ||
             (e = cudaEventCreate (&p->done[i])) != cudaSuccess) goto bad;
-        /* opt-in: measured on C2 the schedule shortens a lone kernel by 9% but the bands already
-           fill each other's tails, so end to end it only adds its sorting kernel */
-        if (getenv ("VOXGPU_SCHED") && atoi (getenv ("VOXGPU_SCHED"))) p->sched[i] = voxgpu_sched_create ();
     }
     return p;
 bad:
@@ -104,66 +107,90 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
                                       const voxgpu_frame *f, const uint8_t *d_tex,
                                       void *host_pixels, size_t host_pitch_bytes)
 {
-    if (!p || !f || !host_pixels) return fail ("voxgpu_present_render: NULL argument");
+    if (!p || !f || !c || !host_pixels) return fail ("voxgpu_present_render: NULL argument");
     if (f->w != p->w || f->h != p->h) return fail ("voxgpu_present_render: frame is %dx%d, presenter %dx%d", f->w, f->h, p->w, p->h);
     if (host_pitch_bytes < (size_t) p->w * 4) return fail ("voxgpu_present_render: pitch %zu too small", host_pitch_bytes);
     int cur = -1;
     CU (cudaGetDevice (&cur));
     if (cur != p->device) return fail ("voxgpu_present_render: presenter lives on device %d, current device is %d", p->device, cur);
+    const int il_world = f->interleave_world > 1 ? f->interleave_world : 1;
+    const int il_rank = il_world > 1 ? f->interleave_rank : 0;
+    if (il_rank < 0 || il_rank >= il_world) return fail ("voxgpu_present_render: interleave rank %d of %d", il_rank, il_world);
+    if (il_world > 1 && host_pitch_bytes != (size_t) p->w * 4)
+        return fail ("voxgpu_present_render: a share of an interleaved frame needs pitch == 4*w");
 
     const int units = p->h / 4;             /* bands are multiples of 4 rows (renderer.c:97-100) */
     if (p->in_flight && voxgpu_present_wait (p)) return -1;   /* the previous frame owns fb and the events */
     const int others = g_presents_in_flight.load ();
-    const int nbands = (!p->fixed_bands && others > 0) ? 1 : p->bands;
+    const int nbands = il_world > 1 ? 1 : ((!p->fixed_bands && others > 0) ? 1 : p->bands);
     CU (cudaEventRecord (p->start, p->stream[0]));
     /* one screen mask per frame, marked on the first band's stream, shared by all bands */
-    const unsigned char *mask = NULL;
-    if (t && mask_usable (t, c) && (f->quality & 3u) == 0u)
+    bool masked = false;
+    if (t && mask_usable (t, c))
     {
-        const int mtiles = (p->w >> 3) * (p->h >> 2);
-        if (++p->epoch > 255u)
-        {
-            p->epoch = 1;
-            CU (cudaMemsetAsync (p->mask, 0, (size_t) mtiles + 4, p->stream[0]));
-        }
-        k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, p->stream[0]>>> (tree_ref (t), t->cut, t->n_cut, dev_camera (c), p->w, p->h,
-                                                                    p->mask, mtiles, (unsigned char) p->epoch, 0, p->h);
-        g_launches++;
-        mask = p->mask;
+        const size_t mtiles = (size_t) (p->w >> 3) * (p->h >> 2);
+        if (maskbuf_begin (p->mask, mtiles, p->stream[0])) return -1;
+        MarkBands mb;
+        mb.y0 = 0; mb.y1 = p->h; mb.nbands = nbands; mb.il_world = il_world; mb.il_rank = il_rank;
+        if (mark_launch (t, c, p->w, p->h, p->mask, mb, p->stream[0])) return -1;
+        masked = true;
     }
     CU (cudaEventRecord (p->marked, p->stream[0]));
-    for (int i=0; i<nbands; i++)
+    int rc = 0, queued = 0;
+    for (int i=0; i<nbands && !rc; i++)
     {
         /* the later bands wait for the mask (and with it the start mark: the elapsed time covers all of them) */
-        if (i) CU (cudaStreamWaitEvent (p->stream[i], p->marked, 0));
+        if (i && cudaStreamWaitEvent (p->stream[i], p->marked, 0) != cudaSuccess) { rc = fail ("voxgpu_present_render: cudaStreamWaitEvent failed"); break; }
         const int y0 = (int) ((long long) units * i / nbands) * 4;
         const int y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
-        if (y1 <= y0) { CU (cudaEventRecord (p->done[i], p->stream[i])); continue; }
+        if (y1 <= y0) { cudaEventRecord (p->done[i], p->stream[i]); queued++; continue; }
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
         uint32_t *src = p->fb + (size_t) y0 * p->w;
-        if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], p->sched[i], mask, p->epoch)) return -1;
+        DevMask mk;
+        if (masked) mk = maskbuf_band (p->mask, i, (size_t) (y0 >> 2) * (p->w >> 3));
+        if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], masked ? &mk : NULL)) { rc = -1; break; }
         char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
-        if (host_pitch_bytes == (size_t) p->w * 4)
-            CU (cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]));
+        cudaError_t e;
+        if (il_world > 1)
+        {
+            /* this GPU's share: tile rows rank, rank + world, ...  Four rows are contiguous on both sides */
+            const int own = il_rank < units ? (units - il_rank + il_world - 1) / il_world : 0;
+            const size_t row4 = (size_t) p->w * 16;
+            e = own ? cudaMemcpy2DAsync (dst + (size_t) il_rank * row4, row4 * il_world, (const char*) src + (size_t) il_rank * row4,
+                                         row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[i]) : cudaSuccess;
+        }
+        else if (host_pitch_bytes == (size_t) p->w * 4)
+            e = cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]);
         else
-            CU (cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0,
-                                   cudaMemcpyDeviceToHost, p->stream[i]));
-        CU (cudaEventRecord (p->done[i], p->stream[i]));
+            e = cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0,
+                                   cudaMemcpyDeviceToHost, p->stream[i]);
+        if (e != cudaSuccess) { rc = fail ("voxgpu_present_render: copy to the surface failed: %s", cudaGetErrorString (e)); }
+        cudaEventRecord (p->done[i], p->stream[i]);
+        queued++;
     }
-    p->used_bands = nbands;
-    p->in_flight = 1;
-    g_presents_in_flight++;
-    return 0;
+    if (rc && masked && queued < nbands) maskbuf_reset_lists (p->mask, p->stream[0]);   /* lists nobody will consume */
+    p->used_bands = queued;
+    if (queued)
+    {
+        p->in_flight = 1;
+        g_presents_in_flight++;
+    }
+    return rc;
 }
 
 extern "C" int voxgpu_present_wait (voxgpu_present *p)
 {
     if (!p || !p->in_flight) return 0;
-    for (int i=0; i<p->used_bands; i++) CU (cudaEventSynchronize (p->done[i]));
+    int rc = 0;
+    for (int i=0; i<p->used_bands; i++)
+    {
+        cudaError_t e = cudaEventSynchronize (p->done[i]);
+        if (e != cudaSuccess && !rc) rc = fail ("voxgpu_present_wait: %s", cudaGetErrorString (e));
+    }
     p->in_flight = 0;
     g_presents_in_flight--;
-    return 0;
+    return rc;
 }
 
 extern "C" float voxgpu_present_last_ms (voxgpu_present *p)
@@ -181,3 +208,197 @@ extern "C" float voxgpu_present_last_ms (voxgpu_present *p)
 }
 
 extern "C" const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p) { return p ? p->fb : NULL; }
+
+/* ------------------------------------------- one frame on all GPUs of the process
+ *
+ * The reference fans a frame out over all cores inside vox_render (dispatch_apply over the 4x4 blocks,
+ * renderer.c:214-226).  voxgpu_multi does the same over the CUDA devices of ONE process: device k draws
+ * the tile rows r with r % N == k of the frame (statistically identical shares, one launch each) into its
+ * own framebuffer and DMA-copies exactly those rows into the page-locked surface over ITS OWN PCIe link --
+ * no funnel through GPU 0, no peer traffic at all; the "gather" is the host surface itself.  Each device
+ * has a worker thread (bound to the device once, so no cudaSetDevice on the frame path) that queues the
+ * device's share when voxgpu_multi_render posts a frame; the N submissions run in parallel and
+ * voxgpu_multi_render returns when all are queued.  voxgpu_multi_wait = every share has landed.
+ */
+struct MultiJob
+{
+    const voxgpu_tree *tree;
+    const uint8_t *d_tex;
+    const voxgpu_lights *lights;
+    voxgpu_camera cam;
+    voxgpu_frame frame;
+    void *host_pixels;
+    size_t pitch;
+};
+
+struct MultiWorker
+{
+    std::thread th;
+    int device, rank;
+    voxgpu_present *p;
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<unsigned> posted, finished;     /* sequence numbers of frames posted to / queued by this worker */
+    std::atomic<int> quit;
+    MultiJob job;
+    int rc;
+    char err[512];
+};
+
+struct voxgpu_multi
+{
+    int n, w, h;
+    MultiWorker *wk;
+    int in_flight;
+};
+
+static void multi_worker_main (voxgpu_multi *mu, MultiWorker *w)
+{
+    w->rc = 0; w->err[0] = 0;
+    if (cudaSetDevice (w->device) != cudaSuccess) { w->rc = -1; snprintf (w->err, sizeof w->err, "cudaSetDevice (%d) failed", w->device); }
+    else
+    {
+        w->p = voxgpu_present_create (mu->w, mu->h, 1);
+        if (!w->p) { w->rc = -1; snprintf (w->err, sizeof w->err, "%s", g_err); }
+    }
+    w->finished.store (1, std::memory_order_release);            /* "frame 1" = the setup */
+    unsigned seen = 1;
+    for (;;)
+    {
+        /* a short spin (the next frame usually follows within microseconds), then sleep */
+        int spins = 0;
+        while (w->posted.load (std::memory_order_acquire) == seen && !w->quit.load (std::memory_order_acquire))
+        {
+            if (++spins < 4000) { __builtin_ia32_pause (); continue; }
+            std::unique_lock<std::mutex> lk (w->m);
+            w->cv.wait (lk, [&] { return w->posted.load (std::memory_order_acquire) != seen || w->quit.load (std::memory_order_acquire); });
+        }
+        if (w->quit.load (std::memory_order_acquire)) break;
+        seen = w->posted.load (std::memory_order_acquire);
+        MultiJob &j = w->job;
+        voxgpu_frame fr = j.frame;
+        fr.lights = j.lights;
+        fr.interleave_world = mu->n; fr.interleave_rank = w->rank;
+        w->rc = w->p ? voxgpu_present_render (w->p, j.tree, &j.cam, &fr, j.d_tex, j.host_pixels, j.pitch) : -1;
+        if (w->rc) snprintf (w->err, sizeof w->err, "%s", w->p ? g_err : "worker has no presenter");
+        w->finished.store (seen, std::memory_order_release);
+    }
+    if (w->p) { voxgpu_present_destroy (w->p); w->p = NULL; }
+}
+
+static void multi_post (MultiWorker *w, unsigned seq)
+{
+    {
+        std::lock_guard<std::mutex> lk (w->m);
+        w->posted.store (seq, std::memory_order_release);
+    }
+    w->cv.notify_one ();
+}
+
+static void multi_await (MultiWorker *w, unsigned seq)
+{
+    int spins = 0;
+    while (w->finished.load (std::memory_order_acquire) != seq)
+    {
+        if (++spins < 20000) __builtin_ia32_pause ();
+        else std::this_thread::yield ();
+    }
+}
+
+extern "C" void voxgpu_multi_destroy (voxgpu_multi *mu)
+{
+    if (!mu) return;
+    for (int i=0; i<mu->n; i++)
+    {
+        MultiWorker *w = &mu->wk[i];
+        if (!w->th.joinable ()) continue;
+        {
+            std::lock_guard<std::mutex> lk (w->m);
+            w->quit.store (1, std::memory_order_release);
+        }
+        w->cv.notify_one ();
+        w->th.join ();
+    }
+    delete[] mu->wk;
+    free (mu);
+}
+
+extern "C" voxgpu_multi* voxgpu_multi_create (int w, int h, int ndev, const int *devices)
+{
+    if (w <= 0 || h <= 0 || (w & 0xf) || (h & 0x3)) { fail ("voxgpu_multi_create: bad geometry %dx%d", w, h); return NULL; }
+    if (ndev < 1 || ndev > 64 || !devices) { fail ("voxgpu_multi_create: %d devices", ndev); return NULL; }
+    voxgpu_multi *mu = (voxgpu_multi*) calloc (1, sizeof *mu);
+    if (!mu) { fail ("voxgpu_multi_create: out of memory"); return NULL; }
+    mu->n = ndev; mu->w = w; mu->h = h;
+    mu->wk = new MultiWorker[ndev];
+    for (int i=0; i<ndev; i++)
+    {
+        MultiWorker *k = &mu->wk[i];
+        k->device = devices[i]; k->rank = i; k->p = NULL;
+        k->posted.store (1); k->finished.store (0); k->quit.store (0);
+        k->th = std::thread (multi_worker_main, mu, k);
+    }
+    int bad = -1;
+    for (int i=0; i<ndev; i++)
+    {
+        multi_await (&mu->wk[i], 1);
+        if (mu->wk[i].rc && bad < 0) bad = i;
+    }
+    if (bad >= 0)
+    {
+        fail ("voxgpu_multi_create: device %d: %s", mu->wk[bad].device, mu->wk[bad].err);
+        voxgpu_multi_destroy (mu);
+        return NULL;
+    }
+    return mu;
+}
+
+extern "C" int voxgpu_multi_devices (const voxgpu_multi *mu) { return mu ? mu->n : 0; }
+extern "C" int voxgpu_multi_device (const voxgpu_multi *mu, int i) { return (mu && i >= 0 && i < mu->n) ? mu->wk[i].device : -1; }
+
+extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *trees, const voxgpu_camera *c,
+                                    const voxgpu_frame *f, const uint8_t *const *d_tex, const voxgpu_lights *const *lights,
+                                    void *host_pixels, size_t host_pitch_bytes)
+{
+    if (!mu || !trees || !c || !f || !d_tex || !host_pixels) return fail ("voxgpu_multi_render: NULL argument");
+    if ((f->quality & 3u) != 0u) return fail ("voxgpu_multi_render: a frame split over devices needs quality BEST");
+    if (mu->in_flight && voxgpu_multi_wait (mu)) return -1;
+    const unsigned seq = mu->wk[0].posted.load () + 1;
+    for (int i=0; i<mu->n; i++)
+    {
+        MultiJob &j = mu->wk[i].job;
+        j.tree = trees[i]; j.d_tex = d_tex[i]; j.lights = lights ? lights[i] : NULL;
+        j.cam = *c; j.frame = *f; j.host_pixels = host_pixels; j.pitch = host_pitch_bytes;
+        multi_post (&mu->wk[i], seq);
+    }
+    int rc = 0;
+    for (int i=0; i<mu->n; i++)
+    {
+        multi_await (&mu->wk[i], seq);
+        if (mu->wk[i].rc && !rc) rc = fail ("voxgpu_multi_render: device %d: %s", mu->wk[i].device, mu->wk[i].err);
+    }
+    mu->in_flight = 1;
+    return rc;
+}
+
+extern "C" int voxgpu_multi_wait (voxgpu_multi *mu)
+{
+    if (!mu || !mu->in_flight) return 0;
+    int rc = 0;
+    /* cudaEventSynchronize does not care which device is current */
+    for (int i=0; i<mu->n; i++) if (mu->wk[i].p && voxgpu_present_wait (mu->wk[i].p)) rc = -1;
+    mu->in_flight = 0;
+    return rc;
+}
+
+extern "C" float voxgpu_multi_last_ms (voxgpu_multi *mu)
+{
+    if (!mu) return -1.0f;
+    float worst = -1.0f;
+    for (int i=0; i<mu->n; i++)
+    {
+        const float ms = mu->wk[i].p ? voxgpu_present_last_ms (mu->wk[i].p) : -1.0f;
+        if (ms > worst) worst = ms;
+    }
+    return worst;
+}

@@ -10,20 +10,22 @@
 #ifndef VOXGPU_RAYS_MIN_BLOCKS
 #define VOXGPU_RAYS_MIN_BLOCKS 8
 #endif
-template <bool STATS>
+/* PERM: thread p searches ray perm[p] (entry order, sort.inl) and writes its result to the ray's own position */
+template <bool STATS, bool PERM>
 __global__ void __launch_bounds__(RAYS_BLOCK, VOXGPU_RAYS_MIN_BLOCKS)
 k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const float4 * __restrict__ dirs,
         size_t n, int * __restrict__ leaf_ids, float4 * __restrict__ points, int * __restrict__ voxels,
-        unsigned long long *stats)
+        unsigned long long *stats, const unsigned * __restrict__ perm)
 {
-    const size_t i = (size_t) blockIdx.x * RAYS_BLOCK + threadIdx.x;
-    const bool live = i < n;            /* the production traversal is warp-synchronous: nobody leaves early */
-    float4 stack[VOXGPU_RAY_STACK];
+    const size_t p = (size_t) blockIdx.x * RAYS_BLOCK + threadIdx.x;
+    const bool live = p < n;            /* the production traversal is warp-synchronous: nobody leaves early */
+    const size_t i = (PERM && live) ? (size_t) __ldg (perm + p) : p;
+    VOXGPU_DECLARE_STACK (stack);
     const float4 o = live ? __ldg (origins + i) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
     const float4 d = live ? __ldg (dirs + i) : make_float4 (1.0f, 1.0f, 1.0f, 0.0f);
     RayResult r;
     RayCounters c = {0, 0, 0, 0, 0, 0, 0};
-    if (STATS) { if (live) ray_tree<true> (tr, start, v3 (o), v3 (d), stack, r, &c); }
+    if (STATS) { if (live) ray_tree<true> (tr, start, v3 (o), v3 (d), stack.loc, r, &c); }
     else ray_tree_warp (tr, start, v3 (o), v3 (d), live, stack, r);
     if (!live) return;
     if (leaf_ids) leaf_ids[i] = r.leaf;
@@ -43,6 +45,109 @@ k_rays (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const f
     }
 }
 
+/*
+ * K2 with per-LANE refill, the form large batches take.  In k_rays a warp keeps its 32 rays until the
+ * slowest has finished: on C3 (every ray hits after ~20 node visits, but anywhere between 3 and 80) the
+ * average instruction ran with 13 of 32 lanes, and the kernel is bound by instruction issue (ncu, r02:
+ * 66-73 % of the issue slots busy, DRAM at 13 %), so the idle lanes are the loss.  Here the warps are
+ * persistent and draw rays from a global counter in batches; whenever at least `refill_min` lanes of a
+ * warp are idle, they retire their finished rays (results go to the rays' own positions), take the next
+ * rays of the warp's batch, and join the search at the start node while the other lanes carry on where they
+ * were.  The traversal itself is warp_search_step, unchanged: the result of a ray does not depend on which
+ * lane or in which company it is searched.  Combined with the entry order of sort.inl (PERM) the rays a
+ * warp takes one after the other are neighbours, so the refilled lanes walk through nodes the warp has
+ * just had in L1.
+ */
+#define RAYS_STREAM_BATCH 256u
+template <bool PERM>
+__global__ void __launch_bounds__(RAYS_BLOCK, VOXGPU_RAYS_MIN_BLOCKS)
+k_rays_stream (TreeRef tr, unsigned start, const float4 * __restrict__ origins, const float4 * __restrict__ dirs,
+               unsigned n, int * __restrict__ leaf_ids, float4 * __restrict__ points, int * __restrict__ voxels,
+               const unsigned * __restrict__ perm, unsigned *counters, int refill_min)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned total_warps = gridDim.x * (RAYS_BLOCK/32);
+    VOXGPU_DECLARE_STACK (stack);
+    LaneSearch s;
+    V3 zero; zero.x = zero.y = zero.z = 0.0f;
+    lane_search_begin (s, start, zero, false);
+    V3 one; one.x = one.y = one.z = 1.0f;
+    RayK k = ray_constants (one);
+    unsigned mine = 0xffffffffu;        /* the ray this lane is working on (position in the caller's arrays) */
+    /* warp-uniform: the warp's batch of positions [next, next + have) in search order, and whether the
+       global counter has run out.  One atomic per RAYS_STREAM_BATCH rays. */
+    unsigned next = 0, have = 0;
+    bool dry = false;
+
+    for (;;)
+    {
+        unsigned idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
+        if ((have || !dry) && __popc (idle) >= refill_min)
+        {
+            if (s.cur == VOXGPU_DEAD && mine != 0xffffffffu)
+            {
+                RayResult r;
+                lane_search_result (s, stack, r);
+                if (leaf_ids) leaf_ids[mine] = r.leaf;
+                if (voxels) voxels[mine] = r.voxel;
+                if (points && r.leaf >= 0) points[mine] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+                mine = 0xffffffffu;
+            }
+            if (have == 0)
+            {
+                if (lane == 0) next = atomicAdd (&counters[0], RAYS_STREAM_BATCH);
+                next = __shfl_sync (0xffffffffu, next, 0);
+                if (next >= n) dry = true; else have = min (RAYS_STREAM_BATCH, n - next);
+            }
+            const unsigned take = min ((unsigned) __popc (idle), have);
+            const unsigned rank = (unsigned) __popc (idle & ((1u << lane) - 1u));
+            if (s.cur == VOXGPU_DEAD && rank < take)
+            {
+                const unsigned p = next + rank;
+                mine = PERM ? __ldg (perm + p) : p;
+                const float4 o = __ldg (origins + mine), d = __ldg (dirs + mine);
+                k = ray_constants (v3 (d));
+                lane_search_begin (s, start, v3 (o), true);
+            }
+            next += take; have -= take;
+            idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
+        }
+        if (idle == 0xffffffffu)
+        {
+            if (!have && dry) break;
+            continue;                   /* the batch ran out between two refills */
+        }
+        warp_search_step (tr, k, s, stack, lane);
+    }
+    if (mine != 0xffffffffu)
+    {
+        RayResult r;
+        lane_search_result (s, stack, r);
+        if (leaf_ids) leaf_ids[mine] = r.leaf;
+        if (voxels) voxels[mine] = r.voxel;
+        if (points && r.leaf >= 0) points[mine] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
+    }
+    if (lane == 0)
+    {
+        const unsigned done = atomicAdd (&counters[1], 1u);
+        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
+    }
+}
+
+/* -1: batches of RAYS_SORT_AUTO_MIN rays and more are searched in entry order (default), 0: never, 1: always */
+#define RAYS_SORT_AUTO_MIN (1u << 18)
+#ifndef VOXGPU_RAYS_REFILL_DEFAULT
+#define VOXGPU_RAYS_REFILL_DEFAULT 8
+#endif
+static int g_rays_sort = getenv ("VOXGPU_RAYS_SORT") ? atoi (getenv ("VOXGPU_RAYS_SORT")) : -1;
+extern "C" void voxgpu_set_rays_sort (int mode) { g_rays_sort = mode; }
+/* batches searched in entry order: lanes idle before a warp refills (k_rays_stream); 0 = one ray per thread (k_rays) */
+static int g_rays_refill = getenv ("VOXGPU_RAYS_REFILL") ? atoi (getenv ("VOXGPU_RAYS_REFILL")) : VOXGPU_RAYS_REFILL_DEFAULT;
+extern "C" void voxgpu_set_rays_refill (int lanes) { g_rays_refill = lanes < 0 ? 0 : (lanes > 32 ? 32 : lanes); }
+
+static int rays_stream_launch (const voxgpu_tree *t, uint32_t start, const float *d_o, const float *d_d, size_t n,
+                               int32_t *d_leaf, float *d_pts, int32_t *d_vox, const unsigned *perm, cudaStream_t st);
+
 extern "C" int voxgpu_rays_device (const voxgpu_tree *t, uint32_t start, const float *d_o, const float *d_d,
                                    size_t n, int32_t *d_leaf, float *d_pts, int32_t *d_vox, voxgpu_stream s)
 {
@@ -50,8 +155,30 @@ extern "C" int voxgpu_rays_device (const voxgpu_tree *t, uint32_t start, const f
     if (n == 0) return 0;
     const size_t blocks = (n + RAYS_BLOCK - 1) / RAYS_BLOCK;
     if (blocks > 0x7fffffffull) return fail ("voxgpu_rays_device: too many rays");
-    k_rays<false><<<(unsigned) blocks, RAYS_BLOCK, 0, (cudaStream_t) s>>> (
-        tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, NULL);
+    cudaStream_t st = (cudaStream_t) s;
+    const bool sorted = n < 0x7fffffffull && (g_rays_sort > 0 || (g_rays_sort < 0 && n >= RAYS_SORT_AUTO_MIN));
+    if (sorted)
+    {
+        /* entry order (sort.inl): the scratch belongs to this call until the search is queued behind the sort */
+        SortScratch &sc = g_sort[t->device];
+        std::lock_guard<std::mutex> guard (sc.lock);
+        const unsigned *perm = NULL;
+        if (sort_rays (t, start, (const float4*) d_o, (const float4*) d_d, n, st, &perm)) return -1;
+        int rc = 0;
+        if (g_rays_refill > 0) rc = rays_stream_launch (t, start, d_o, d_d, n, d_leaf, d_pts, d_vox, perm, st);
+        else
+        {
+            k_rays<false, true><<<(unsigned) blocks, RAYS_BLOCK, 0, st>>> (
+                tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, NULL, perm);
+            g_launches++;
+            const cudaError_t e = cudaGetLastError ();
+            if (e != cudaSuccess) rc = fail ("voxgpu_rays_device: launch failed: %s", cudaGetErrorString (e));
+        }
+        sort_release (t, st);
+        return rc;
+    }
+    k_rays<false, false><<<(unsigned) blocks, RAYS_BLOCK, 0, st>>> (
+        tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, NULL, NULL);
     g_launches++;
     CU (cudaGetLastError ());
     return 0;
@@ -67,8 +194,8 @@ extern "C" int voxgpu_rays_stats (const voxgpu_tree *t, uint32_t start, const fl
     if (n)
     {
         const size_t blocks = (n + RAYS_BLOCK - 1) / RAYS_BLOCK;
-        k_rays<true><<<(unsigned) blocks, RAYS_BLOCK>>> (
-            tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, d_st);
+        k_rays<true, false><<<(unsigned) blocks, RAYS_BLOCK>>> (
+            tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, n, d_leaf, (float4*) d_pts, d_vox, d_st, NULL);
         g_launches++;
     }
     cudaError_t e = cudaMemcpy (h, d_st, sizeof h, cudaMemcpyDeviceToHost);

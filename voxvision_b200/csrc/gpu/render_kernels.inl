@@ -1,5 +1,5 @@
 /* render_kernels.inl -- part of the single translation unit voxgpu.cu (included there, in this order):
-   K1: device camera / frame / lights, shading, k_render, k_sched_build, k_render_persistent, k_render_stream, k_render_blocks. */
+   K1: device camera / frame / lights / mask, shading, k_render_persistent, k_render_blocks. */
 /* -------------------------------------------------------------- K1: render */
 
 #define RENDER_BLOCK 128
@@ -35,11 +35,6 @@ struct DevFrame
     /* pixels outside [cx0, cx1) x [cy0, cy1) (frame coordinates) cannot see the tree's root box:
        tiles entirely outside are only cleared (screen_bounds) */
     int cx0, cx1, cy0, cy1;
-    /* screen mask (k_mark): one byte per 8x4 tile of the whole frame, 0 = no voxel can project into
-       the tile; mask[mask_tiles] is the "no bounds this frame" flag.  NULL: not in use */
-    const unsigned char *mask;
-    int mask_tiles;
-    unsigned mask_epoch;            /* a tile is marked iff its byte equals this (buffers are reused without clearing) */
 };
 
 /* vect-ops.c:8-16 vox_cross_product */
@@ -147,50 +142,40 @@ __device__ __forceinline__ unsigned shade (const TreeRef &tr, const DevFrame &fr
 }
 
 /*
- * One warp renders an 8x4 pixel tile (coherent rays, 32-byte row segments on
- * the store); a block of 4 warps covers a 16x8 tile pair.  Every pixel of the
- * band is written, 0 on a miss: that is vox_redraw's memset of the squares
- * (renderer.c:324) folded into the store.
+ * Screen mask of one frame (k_mark, render_launch.inl): per 8x4 tile of the WHOLE frame one word, the epoch of
+ * the last frame in which the projection of a cut box touched the tile; a tile whose word is not the current
+ * epoch is dark: no voxel can project into it.  Buffers are reused without clearing.  Besides the words,
+ * per band of the frame (a band = the rows one render launch draws), the compact list of its marked tiles in
+ * the order they were first marked.
  */
-template <bool OUT_HITS>
-__global__ void __launch_bounds__(RENDER_BLOCK)
-k_render (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
-          unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points)
+struct DevMask
 {
-    const int tiles_x = fr.w >> 3;
-    const int ntiles = tiles_x * (fr.rows >> 2);
-    const int tile = blockIdx.x * (RENDER_BLOCK/32) + (threadIdx.x >> 5);
-    if (tile >= ntiles) return;
-    const int lane = threadIdx.x & 31;
-    const int sx = (tile % tiles_x) * 8 + (lane & 7);
-    const int ry = (tile / tiles_x) * 4 + (lane >> 3);   /* row inside the band */
-    const int sy = fr.y0 + ry;
-
-    float4 stack[VOXGPU_RAY_STACK];
-    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
-    const V3 dir = screen2world (cam, sx, sy, fr.w);
-    RayResult r;
-    ray_tree<false> (tr, 0, origin, dir, stack, r, NULL);
-
-    unsigned color = 0;
-    if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
-    pixels[(size_t) ry * fr.pitch + sx] = color;
-    if (OUT_HITS)
-    {
-        const size_t pos = (size_t) ry * fr.w + sx;
-        if (leaf_ids) leaf_ids[pos] = r.leaf;
-        if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
-    }
-}
+    const unsigned *mark;       /* NULL: no mask for this launch */
+    const unsigned *list;       /* this band's marked tiles (frame tile indices) */
+    unsigned *ctl;              /* this band's control words: [0] marked tiles (zeroed again by the render kernel),
+                                   [1] == epoch: a box gave no bounds, draw everything */
+    unsigned epoch;
+};
 
 /*
- * Persistent form of K1 (the one voxgpu_render launches).  70-80% of the 8x4 tiles
- * of a C2 frame show no voxel (half of them do not even see the root box) and finish early; with
- * one CTA per 4 tiles the SMs spent a third of the kernel waiting for CTA
- * launches (profiles/r01_*).  Here the grid is sized to the resident capacity
- * of the GPU and every warp pulls tile indices from a global counter until the
- * frame is done.  The counter resets itself: the last warp to leave zeroes it,
- * so no memset precedes the launch.
+ * K1: one warp renders an 8x4 pixel tile (coherent rays, 32-byte row segments on the store).
+ * Every pixel of the band is written, 0 on a miss: that is vox_redraw's memset of the squares
+ * (renderer.c:324) folded into the store.
+ *
+ * PERSISTENT: 70-80% of the 8x4 tiles of a C2 frame show no voxel (half of them do not even see the
+ * root box) and finish at once, 1% take 70-170 us.  The grid is sized to the resident capacity of the
+ * GPU and every warp pulls tickets from a global counter until the frame is done.  The counter resets
+ * itself: the last warp to leave zeroes it, so no memset precedes the launch.
+ *
+ * TICKET ORDER.  With a screen mask the tickets run through two phases: (M) the band's marked tiles, one
+ * per ticket; (D) the band's tile rows in groups of 32 tiles per ticket, one tile per lane, where the
+ * marked tiles are skipped (done already) and the dark ones are cleared.  The r01 profile showed a lone
+ * launch with its SMs busy only 75-80 % of the elapsed time: the longest tiles of a frame (60-80 node
+ * visits of dependent loads and arithmetic, ~0.1 ms) were handed out wherever the raster order put them,
+ * and the kernel ended when the last of them did.  Now everything that traverses starts first and the
+ * dark tiles -- 75 % of a skull frame, stores only -- fill the tail, 2 000 tickets instead of 48 000
+ * on the one counter.  Without a mask (foreign cameras, culling off, a box behind the camera) all tiles
+ * are drawn, one per ticket, in strip-interleaved order.  Results do not depend on the order.
  */
 __device__ __forceinline__ unsigned long long globaltimer_ns ()
 {
@@ -205,62 +190,6 @@ __device__ __forceinline__ unsigned smid ()
     return r;
 }
 
-/*
- * Expensive-tiles-first scheduling across consecutive frames.  A few percent of
- * the tiles of a frame (rays grazing along a surface) take 30-100 times longer
- * than the median tile; when such a tile is handed out late the whole GPU waits
- * for it (the per-tile trace showed the last 40% of the kernel to be a tail).
- * Frames of an animation are coherent, so every launch records the cost of each
- * tile (iterations of its warp), and before the next launch on the same schedule
- * a small kernel sorts the tiles into three classes by the largest cost seen in
- * their 5x5-tile neighbourhood (exactly which tile is expensive changes with the
- * slightest camera move; that its neighbourhood is does not).  The render kernel
- * then hands out class 0, 1, 2 in that order.  A pure performance hint: every
- * tile is still rendered exactly once and results do not depend on it.
- */
-struct DevSched
-{
-    const unsigned *list[3];      /* tiles by class, filled by k_sched_build */
-    unsigned *count;              /* [3]; zeroed again by the render kernel's last warp */
-    unsigned char *cost_next;     /* per tile, written by this launch */
-};
-
-#define SCHED_RADIUS 2
-
-__global__ void k_sched_build (const unsigned char * __restrict__ cost_prev, int tiles_x, int tiles_y,
-                               unsigned t_heavy, unsigned t_mid,
-                               unsigned *list0, unsigned *list1, unsigned *list2, unsigned *count)
-{
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ntiles = tiles_x * tiles_y;
-    unsigned cls = 3;
-    if (tile < ntiles)
-    {
-        const int tx = tile % tiles_x, ty = tile / tiles_x;
-        unsigned m = 0;
-        for (int dy=-SCHED_RADIUS; dy<=SCHED_RADIUS; dy++)
-            for (int dx=-SCHED_RADIUS; dx<=SCHED_RADIUS; dx++)
-            {
-                const int x = tx + dx, y = ty + dy;
-                if (x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) m = max (m, (unsigned) __ldg (cost_prev + y * tiles_x + x));
-            }
-        cls = m >= t_heavy ? 0u : (m >= t_mid ? 1u : 2u);
-    }
-    /* warp-aggregated append to the three lists */
-    const int lane = threadIdx.x & 31;
-    unsigned *lists[3] = {list0, list1, list2};
-    #pragma unroll
-    for (unsigned c=0; c<3; c++)
-    {
-        const unsigned m = __ballot_sync (0xffffffffu, cls == c);
-        if (!m) continue;
-        unsigned base = 0;
-        if (lane == __ffs (m) - 1) base = atomicAdd (count + c, (unsigned) __popc (m));
-        base = __shfl_sync (0xffffffffu, base, __ffs (m) - 1);
-        if (cls == c) lists[c][base + __popc (m & ((1u << lane) - 1u))] = (unsigned) tile;
-    }
-}
-
 /* Resident CTAs per SM the compiler must allow for K1.  Measured on C2 (tools/ab_variants.sh):
    7 (72 registers, what ptxas picks on its own) 12.31 Grays/s, 8 (61 registers, no spills) 12.48,
    9 (56 registers, 12 bytes spilled) 12.01. */
@@ -269,9 +198,9 @@ __global__ void k_sched_build (const unsigned char * __restrict__ cost_prev, int
 #endif
 template <bool OUT_HITS, unsigned STRIPS, bool LIT>
 __global__ void __launch_bounds__(RENDER_BLOCK, VOXGPU_RENDER_MIN_BLOCKS)
-k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
+k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, DevMask mk, const unsigned char * __restrict__ tex,
                      unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
-                     unsigned *counters, unsigned long long *trace, DevSched sch)
+                     unsigned *counters, unsigned long long *trace)
 {
     const int tiles_x = fr.w >> 3;
     /* tile rows of the band this launch owns (all of them unless the frame is interleaved over GPUs) */
@@ -280,7 +209,7 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
     const unsigned ntiles = (unsigned) (tiles_x * own_rows);
     const int lane = threadIdx.x & 31;
     const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
-    float4 stack[VOXGPU_RAY_STACK];
+    VOXGPU_DECLARE_STACK (stack);
     V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
 #if VOXGPU_SMEM_TOP
     /* the top levels of the tree (breadth-first order: simply the first nodes), once per persistent CTA */
@@ -296,16 +225,20 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
     tr.top_rec = s_top; tr.top_ctr = s_top + 2*VOXGPU_SMEM_TOP; tr.ntop = tr.ntop_avail;
 #endif
 
-    /* Tiles are handed out strip-interleaved: consecutive tickets land in
-       RENDER_STRIPS different horizontal strips of the frame.  In raster order
-       the empty top and bottom of a frame (half of a skull frame misses the root
-       box, 70-80% of it shows no voxel) are done in two bursts that only store pixels while the middle only
-       computes; interleaved, stores and traversal overlap for the whole kernel,
-       which matters when the pixels go to mapped host memory over PCIe. */
+    /* No mask: tiles are handed out strip-interleaved, consecutive tickets land in STRIPS different
+       horizontal strips of the band, so that stores and traversal overlap for the whole kernel instead of
+       coming in bursts (the empty top and bottom of a frame only store). */
     const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
-    unsigned n0 = 0, n1 = 0;
-    if (sch.count) { n0 = sch.count[0]; n1 = n0 + sch.count[1]; }
-    const unsigned tickets = sch.count ? ntiles : per_strip * STRIPS;
+    unsigned n_listed = 0;
+    bool masked = false;
+    if (mk.mark)
+    {
+        masked = mk.ctl[1] != mk.epoch;
+        if (masked) n_listed = mk.ctl[0];
+    }
+    const unsigned groups_x = ((unsigned) tiles_x + 31u) >> 5;          /* phase D: 32 tiles of a row per ticket */
+    const unsigned tickets = masked ? n_listed + groups_x * (unsigned) own_rows : per_strip * STRIPS;
+    const int band_ty0 = fr.y0 >> 2;
 
     for (;;)
     {
@@ -313,40 +246,69 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         if (lane == 0) ticket = atomicAdd (&counters[0], 1u);
         ticket = __shfl_sync (0xffffffffu, ticket, 0);
         if (ticket >= tickets) break;
-        unsigned tile;
-        if (sch.count)
-            tile = ticket < n0 ? sch.list[0][ticket] : (ticket < n1 ? sch.list[1][ticket - n0] : sch.list[2][ticket - n1]);
+
+        int tx, ty;                     /* the tile, in tiles of the whole frame */
+        if (ticket < n_listed)
+        {
+            const unsigned gt = mk.list[ticket];
+            tx = (int) (gt % (unsigned) tiles_x); ty = (int) (gt / (unsigned) tiles_x);
+        }
+        else if (masked)
+        {
+            /* phase D: lane l looks at tile 32*g + l of one tile row and clears it unless it is listed */
+            const unsigned t = ticket - n_listed;
+            const int gx = (int) ((t % groups_x) << 5) + lane;
+            const int gy = band_ty0 + (int) (t / groups_x) * fr.il_world + fr.il_rank;
+            if (gx < tiles_x && mk.mark[(size_t) gy * tiles_x + gx] != mk.epoch)
+            {
+                const int ry0 = (gy << 2) - fr.y0;
+                #pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    unsigned *row = pixels + (size_t) (ry0 + r) * fr.pitch + (gx << 3);
+                    if ((((size_t) row) & 15) == 0)
+                    {
+                        ((uint4*) row)[0] = make_uint4 (0u, 0u, 0u, 0u);
+                        ((uint4*) row)[1] = make_uint4 (0u, 0u, 0u, 0u);
+                    }
+                    else for (int c = 0; c < 8; c++) row[c] = 0u;
+                    if (OUT_HITS && leaf_ids)
+                    {
+                        int *lrow = leaf_ids + (size_t) (ry0 + r) * fr.w + (gx << 3);
+                        for (int c = 0; c < 8; c++) lrow[c] = -1;
+                    }
+                }
+            }
+            continue;
+        }
         else
         {
-            tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
+            const unsigned tile = (ticket % STRIPS) * per_strip + ticket / STRIPS;
             if (tile >= ntiles) continue;
+            tx = (int) (tile % (unsigned) tiles_x);
+            ty = band_ty0 + (int) (tile / (unsigned) tiles_x) * fr.il_world + fr.il_rank;
+        }
+        const int sx = (tx << 3) + (lane & 7);
+        const int sy = (ty << 2) + (lane >> 3);
+        const int ry = sy - fr.y0;                      /* row inside the band */
+        if (!masked)
+        {
+            /* the whole 8x4 tile lies outside the root box's screen bounds: every ray misses
+               (search.c:22-27 at the root), the pixels are the zeros of vox_redraw's memset */
+            const int tx0 = tx << 3, ty0 = ty << 2;
+            if (tx0 >= fr.cx1 || tx0 + 8 <= fr.cx0 || ty0 >= fr.cy1 || ty0 + 4 <= fr.cy0)
+            {
+                pixels[(size_t) ry * fr.pitch + sx] = 0u;
+                if (OUT_HITS && leaf_ids) leaf_ids[(size_t) ry * fr.w + sx] = -1;
+                continue;
+            }
         }
 
         unsigned long long t0 = 0;
         if (trace) t0 = globaltimer_ns ();
-        const int sx = (int) (tile % tiles_x) * 8 + (lane & 7);
-        const int ry = ((int) (tile / tiles_x) * fr.il_world + fr.il_rank) * 4 + (lane >> 3);
-        const int sy = fr.y0 + ry;
-        {
-            /* the whole 8x4 tile lies outside the root box's screen bounds: every ray misses
-               (search.c:22-27 at the root), the pixels are the zeros of vox_redraw's memset */
-            const int tx0 = sx - (lane & 7), ty0 = sy - (lane >> 3);
-            bool dark = tx0 >= fr.cx1 || tx0 + 8 <= fr.cx0 || ty0 >= fr.cy1 || ty0 + 4 <= fr.cy0;
-            if (!dark && fr.mask)
-                dark = __ldg (fr.mask + (size_t) (ty0 >> 2) * tiles_x + (tx0 >> 3)) != fr.mask_epoch &&
-                       __ldg (fr.mask + fr.mask_tiles) != fr.mask_epoch;
-            if (dark)
-            {
-                pixels[(size_t) ry * fr.pitch + sx] = 0u;
-                if (OUT_HITS && leaf_ids) leaf_ids[(size_t) ry * fr.w + sx] = -1;
-                if (sch.cost_next && lane == 0) sch.cost_next[tile] = 0;
-                continue;
-            }
-        }
         const V3 dir = screen2world (cam, sx, sy, fr.w);
         RayResult r;
-        const int iterations = ray_tree_warp (tr, 0, origin, dir, true, stack, r);
-        if (sch.cost_next && lane == 0) sch.cost_next[tile] = (unsigned char) min (iterations, 255);
+        const int iterations = ray_tree_warp (tr, start, origin, dir, true, stack, r);
 
         unsigned color = 0;
         if (r.leaf >= 0) color = shade<LIT> (tr, fr, tex, r.point);
@@ -360,10 +322,11 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         __syncwarp ();
         if (trace && lane == 0)
         {
-            /* development trace (voxgpu_set_trace): when and where each tile ran */
-            trace[3*(size_t) tile] = t0;
-            trace[3*(size_t) tile + 1] = globaltimer_ns ();
-            trace[3*(size_t) tile + 2] = ((unsigned long long) smid () << 32) | (unsigned) iterations;
+            /* development trace (voxgpu_set_trace): when and where each tile ran, per tile of the FRAME */
+            const size_t gt = (size_t) ty * tiles_x + tx;
+            trace[3*gt] = t0;
+            trace[3*gt + 1] = globaltimer_ns ();
+            trace[3*gt + 2] = ((unsigned long long) smid () << 32) | (unsigned) iterations;
         }
     }
     if (lane == 0)
@@ -372,123 +335,9 @@ k_render_persistent (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char
         if (done + 1 == total_warps)
         {
             counters[0] = 0; counters[1] = 0;
-            if (sch.count) { sch.count[0] = 0; sch.count[1] = 0; sch.count[2] = 0; }   /* for the next k_sched_build */
+            if (mk.mark) mk.ctl[0] = 0;                         /* for the next k_mark into this buffer */
             __threadfence ();
         }
-    }
-}
-
-/*
- * K1 with per-LANE work refill (the form voxgpu_render launches for BEST).  In the
- * tile form above a warp keeps its 32 rays until the slowest has finished: on C2 the
- * average instruction ran with 21 of 32 lanes, most of the missing ones being lanes whose
- * ray was already done.  Here the ticket counter hands out PIXELS (in tile order, so
- * that rays fetched together are neighbours): whenever at least `refill_min` lanes of
- * a warp are idle, they retire their finished pixels, draw new ones with one warp-
- * aggregated atomicAdd (ballot + popc rank), generate their rays and join the search
- * at the root while the other lanes carry on where they were.  The traversal itself
- * is warp_search_step, unchanged; results do not depend on which lane or in which
- * company a ray is searched.
- */
-#define STREAM_BATCH 64u
-template <bool OUT_HITS, unsigned STRIPS>
-__global__ void __launch_bounds__(RENDER_BLOCK, 7)
-k_render_stream (TreeRef tr, DevCamera cam, DevFrame fr, const unsigned char * __restrict__ tex,
-                 unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
-                 unsigned *counters, int refill_min)
-{
-    const int tiles_x = fr.w >> 3;
-    const unsigned ntiles = (unsigned) (tiles_x * (fr.rows >> 2));
-    const int lane = threadIdx.x & 31;
-    const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
-    const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
-    const unsigned tickets = per_strip * STRIPS * 32u;     /* pixel tickets; some map to no tile */
-    float4 stack[VOXGPU_RAY_STACK];
-    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
-
-    LaneSearch s;
-    lane_search_begin (s, 0, origin, false);
-    RayK k = ray_constants (origin);
-    int pix_x = -1, pix_y = 0;          /* the pixel this lane is working on, -1 = none */
-    /* warp-uniform: the warp's batch of pixel tickets [next, next + have), and whether the
-       global counter has run out.  One atomic per STREAM_BATCH pixels, so that lanes in
-       the middle of a long search do not wait for one every time their neighbours refill. */
-    unsigned next = 0, have = 0;
-    bool dry = false;
-
-    for (;;)
-    {
-        unsigned idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
-        if ((have || !dry) && __popc (idle) >= refill_min)
-        {
-            /* retire */
-            if (s.cur == VOXGPU_DEAD && pix_x >= 0)
-            {
-                RayResult r;
-                lane_search_result (s, stack, r);
-                unsigned color = 0;
-                if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
-                pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
-                if (OUT_HITS)
-                {
-                    const size_t pos = (size_t) pix_y * fr.w + pix_x;
-                    if (leaf_ids) leaf_ids[pos] = r.leaf;
-                    if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
-                }
-                pix_x = -1;
-            }
-            if (have == 0)
-            {
-                if (lane == 0) next = atomicAdd (&counters[0], STREAM_BATCH);
-                next = __shfl_sync (0xffffffffu, next, 0);
-                if (next >= tickets) dry = true; else have = STREAM_BATCH;     /* tickets is a multiple of the batch */
-            }
-            const unsigned n = (unsigned) __popc (idle);
-            const unsigned take = n < have ? n : have;
-            const unsigned rank = (unsigned) __popc (idle & ((1u << lane) - 1u));
-            if (s.cur == VOXGPU_DEAD && rank < take)
-            {
-                const unsigned ticket = next + rank;
-                const unsigned tt = ticket >> 5;
-                const unsigned tile = (tt % STRIPS) * per_strip + tt / STRIPS;
-                if (tile < ntiles)
-                {
-                    const unsigned in = ticket & 31u;
-                    pix_x = (int) (tile % tiles_x) * 8 + (int) (in & 7u);
-                    pix_y = (int) (tile / tiles_x) * 4 + (int) (in >> 3);
-                    const V3 dir = screen2world (cam, pix_x, fr.y0 + pix_y, fr.w);
-                    k = ray_constants (dir);
-                    lane_search_begin (s, 0, origin, true);
-                }
-            }
-            next += take; have -= take;
-            idle = __ballot_sync (0xffffffffu, s.cur == VOXGPU_DEAD);
-        }
-        if (idle == 0xffffffffu)
-        {
-            if (!have && dry) break;
-            continue;                   /* only tickets without a tile were drawn, or the batch ran out */
-        }
-        warp_search_step (tr, k, s, stack, lane);
-    }
-    if (pix_x >= 0)
-    {
-        RayResult r;
-        lane_search_result (s, stack, r);
-        unsigned color = 0;
-        if (r.leaf >= 0) color = shade<false> (tr, fr, tex, r.point);
-        pixels[(size_t) pix_y * fr.pitch + pix_x] = color;
-        if (OUT_HITS)
-        {
-            const size_t pos = (size_t) pix_y * fr.w + pix_x;
-            if (leaf_ids) leaf_ids[pos] = r.leaf;
-            if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
-        }
-    }
-    if (lane == 0)
-    {
-        const unsigned done = atomicAdd (&counters[1], 1u);
-        if (done + 1 == total_warps) { counters[0] = 0; counters[1] = 0; __threadfence (); }
     }
 }
 
@@ -526,7 +375,7 @@ __device__ __forceinline__ float sqr_norm3 (const V3 a)
  */
 template <bool OUT_HITS, bool LIT, bool PRE>
 __global__ void __launch_bounds__(RENDER_BLOCK)
-k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const unsigned char * __restrict__ tex,
+k_render_blocks (TreeRef tr, unsigned root, DevCamera cam, DevFrame fr, unsigned quality, const unsigned char * __restrict__ tex,
                  unsigned * __restrict__ pixels, int * __restrict__ leaf_ids, float4 * __restrict__ points,
                  unsigned *counters, const int * __restrict__ pre_leaf, const float4 * __restrict__ pre_pts)
 {
@@ -537,7 +386,7 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
     const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
     const unsigned rnd_mode = quality & 3u, merge_mode = quality & 12u;
     const bool adaptive = rnd_mode == 2u;
-    float4 stack[VOXGPU_RAY_STACK];
+    VOXGPU_DECLARE_STACK (stack);
     unsigned sq[16];
     V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
 
@@ -584,10 +433,10 @@ k_render_blocks (TreeRef tr, DevCamera cam, DevFrame fr, unsigned quality, const
                 in_range = valid && i >= istart && i < iend;
             }
             bool want;
-            unsigned start = 0;
+            unsigned start = root;
             if (step == 0) want = valid;
             else if (step == 1) want = valid && c1;
-            else if (phase_leaf) { want = in_range && !merge && blk_mode == 1u && leaf >= 0; start = leaf >= 0 ? (unsigned) leaf : 0u; }
+            else if (phase_leaf) { want = in_range && !merge && blk_mode == 1u && leaf >= 0; start = leaf >= 0 ? (unsigned) leaf : root; }
             else want = in_range && !merge && (blk_mode == 0u || leaf < 0);
 
             RayResult r;

@@ -1,16 +1,11 @@
 /* render_launch.inl -- part of the single translation unit voxgpu.cu (included there, in this order):
-   host side of K1: render slots, lights upload, tile schedule, k_mark + screen bounds, voxgpu_render. */
-/* Per-device pool of self-resetting tile counters; launches rotate through the
-   slots so that renders in flight on different streams never share one. */
-#define COUNTER_SLOTS 64
-static unsigned *g_counters[64] = {0};
-static int g_render_blocks[64][7] = {{0}};
-static std::atomic<unsigned> g_counter_seq{0};
-static int g_variant = 1;
-static int g_refill_min = 8;
+   host side of K1: per-device render state (slots), lights upload, k_mark + screen bounds, voxgpu_render. */
+
 static unsigned long long *g_trace = NULL;
+static int g_variant = 1;
 
 extern "C" void voxgpu_set_trace (void *d_trace) { g_trace = (unsigned long long*) d_trace; }
+extern "C" void voxgpu_set_variant (int v) { g_variant = v == 2 ? 2 : 1; }
 
 /* ------------------------------------------------------------------ lights */
 
@@ -27,6 +22,7 @@ extern "C" voxgpu_lights* voxgpu_lights_upload (const voxgpu_lights_flat *f)
     voxgpu_lights *l = (voxgpu_lights*) calloc (1, sizeof *l);
     const size_t n4 = 2 * ((size_t) f->n_nodes + f->n_spheres);
     float4 *host = (float4*) malloc ((n4 ? n4 : 1) * sizeof (float4));
+    if (!l || !host) { fail ("voxgpu_lights_upload: out of memory"); free (l); free (host); return NULL; }
     for (uint32_t i=0; i<f->n_nodes; i++)
     {
         host[2*i] = make_float4 (f->node_bounds[4*i], f->node_bounds[4*i+1], f->node_bounds[4*i+2], f->node_bounds[4*i+3]);
@@ -62,156 +58,180 @@ extern "C" void voxgpu_lights_free (voxgpu_lights *l)
     free (l);
 }
 
-extern "C" void voxgpu_set_variant (int v) { g_variant = v; }
-extern "C" void voxgpu_set_refill_min (int n) { g_refill_min = n < 1 ? 1 : (n > 32 ? 32 : n); }
+/* ------------------------------------------------------- screen-mask buffers */
 
-/* A render launch borrows slot `idx` of its device: a pair of tile counters and a screen-mask buffer.
-   Launches rotate through COUNTER_SLOTS slots; should a slot come round again while its previous
-   borrower is still queued or running on ANOTHER stream, the new stream waits for it (slot_acquire /
-   slot_release: one event per slot), so sharing is always ordered. */
-struct SlotGuard { cudaEvent_t ev; cudaStream_t last; int used; };
-static SlotGuard g_guard[64][64];
+#define MASK_MAX_BANDS 16
+#define MASK_CTL_WORDS (4 * MASK_MAX_BANDS)
 
-static unsigned slot_acquire (int device, cudaStream_t st);
-static void slot_release (int device, unsigned idx, cudaStream_t st);
-
-static unsigned* counter_slot (int device, unsigned idx)
+/* One frame's screen mask (see DevMask): mark[mtiles] | list[mtiles] | ctl[MASK_CTL_WORDS].
+   Zeroed when allocated and when the epoch wraps; otherwise never cleared. */
+struct MaskBuf
 {
-    if (!g_counters[device])
-    {
-        unsigned *p = NULL;
-        if (cudaMalloc (&p, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
-        if (cudaMemset (p, 0, COUNTER_SLOTS * 2 * sizeof (unsigned)) != cudaSuccess) return NULL;
-        int sms = 0, b0 = 0, b1 = 0;
-        cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b0, k_render_persistent<false, RENDER_STRIPS, false>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b1, k_render_persistent<true, RENDER_STRIPS, false>, RENDER_BLOCK, 0);
-        g_render_blocks[device][0] = sms * (b0 > 0 ? b0 : 1);
-        g_render_blocks[device][1] = sms * (b1 > 0 ? b1 : 1);
-        int b2 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b2, k_render_blocks<true, false, false>, RENDER_BLOCK, 0);
-        g_render_blocks[device][2] = sms * (b2 > 0 ? b2 : 1);
-        int b5 = 0, b6 = 0;     /* with a light manager attached */
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b5, k_render_persistent<true, RENDER_STRIPS, true>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b6, k_render_blocks<true, true, false>, RENDER_BLOCK, 0);
-        g_render_blocks[device][5] = sms * (b5 > 0 ? b5 : 1);
-        g_render_blocks[device][6] = sms * (b6 > 0 ? b6 : 1);
-        int b3 = 0, b4 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b3, k_render_stream<false, RENDER_STRIPS>, RENDER_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b4, k_render_stream<true, RENDER_STRIPS>, RENDER_BLOCK, 0);
-        g_render_blocks[device][3] = sms * (b3 > 0 ? b3 : 1);
-        g_render_blocks[device][4] = sms * (b4 > 0 ? b4 : 1);
-        /* stream-ordered scratch (cudaMallocAsync in voxgpu_render): keep freed blocks in the pool */
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool (&pool, device) == cudaSuccess)
-        {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        g_counters[device] = p;
-    }
-    return g_counters[device] + 2 * idx;
-}
-
-static unsigned slot_acquire (int device, cudaStream_t st)
-{
-    const unsigned idx = g_counter_seq++ % COUNTER_SLOTS;
-    SlotGuard &g = g_guard[device][idx];
-    if (g.used && g.last != st) cudaStreamWaitEvent (st, g.ev, 0);
-    return idx;
-}
-
-static void slot_release (int device, unsigned idx, cudaStream_t st)
-{
-    SlotGuard &g = g_guard[device][idx];
-    if (!g.ev && cudaEventCreateWithFlags (&g.ev, cudaEventDisableTiming) != cudaSuccess) return;
-    cudaEventRecord (g.ev, st);
-    g.last = st; g.used = 1;
-}
-
-struct voxgpu_sched
-{
-    int device;
-    int w, y0, rows;              /* geometry the recorded costs refer to */
-    unsigned cap;                 /* tiles the buffers can hold */
-    unsigned *list[3];
-    unsigned *count;
-    unsigned char *cost[2];
-    int cur;                      /* cost buffer the next launch reads */
-    unsigned t_heavy, t_mid;
+    unsigned *buf;
+    size_t tiles;               /* capacity */
+    unsigned epoch;
 };
 
-extern "C" voxgpu_sched* voxgpu_sched_create (void)
-{
-    voxgpu_sched *sc = (voxgpu_sched*) calloc (1, sizeof *sc);
-    const char *e1 = getenv ("VOXGPU_HEAVY_ITERS"), *e2 = getenv ("VOXGPU_MID_ITERS");
-    sc->t_heavy = e1 ? (unsigned) atoi (e1) : 24u;
-    sc->t_mid = e2 ? (unsigned) atoi (e2) : 8u;
-    sc->device = -1;
-    return sc;
-}
+static void maskbuf_free (MaskBuf &m) { if (m.buf) cudaFree (m.buf); m.buf = NULL; m.tiles = 0; m.epoch = 0; }
 
-static void sched_release (voxgpu_sched *sc)
+/* make room for `mtiles` tiles and start a new epoch; everything is queued on `st` */
+static int maskbuf_begin (MaskBuf &m, size_t mtiles, cudaStream_t st)
 {
-    for (int i=0; i<3; i++) { cudaFree (sc->list[i]); sc->list[i] = NULL; }
-    cudaFree (sc->cost[0]); cudaFree (sc->cost[1]); cudaFree (sc->count);
-    sc->cost[0] = sc->cost[1] = NULL; sc->count = NULL; sc->cap = 0;
-}
-
-extern "C" void voxgpu_sched_destroy (voxgpu_sched *sc)
-{
-    if (!sc) return;
-    sched_release (sc);
-    free (sc);
-}
-
-/* Sort the tiles for this launch from the costs the previous one recorded
-   (all zero after a change of geometry: plain order). */
-static int sched_prepare (voxgpu_sched *sc, int device, int w, int y0, int rows, cudaStream_t st, DevSched *out)
-{
-    const int tiles_x = w >> 3, tiles_y = rows >> 2;
-    const unsigned ntiles = (unsigned) (tiles_x * tiles_y);
-    const bool restart = sc->device != device || sc->w != w || sc->y0 != y0 || sc->rows != rows || !sc->count;
-    if (restart)
+    if (m.tiles < mtiles)
     {
-        if (sc->cap < ntiles || sc->device != device)
-        {
-            sched_release (sc);
-            for (int i=0; i<3; i++) CU (cudaMalloc (&sc->list[i], (size_t) ntiles * sizeof (unsigned)));
-            for (int i=0; i<2; i++) CU (cudaMalloc (&sc->cost[i], ntiles));
-            CU (cudaMalloc (&sc->count, 3 * sizeof (unsigned)));
-            sc->cap = ntiles;
-        }
-        CU (cudaMemsetAsync (sc->count, 0, 3 * sizeof (unsigned), st));
-        CU (cudaMemsetAsync (sc->cost[0], 0, ntiles, st));
-        sc->device = device; sc->w = w; sc->y0 = y0; sc->rows = rows; sc->cur = 0;
+        if (m.buf) { CU (cudaDeviceSynchronize ()); cudaFree (m.buf); m.buf = NULL; m.tiles = 0; }
+        CU (cudaMalloc (&m.buf, (2 * mtiles + MASK_CTL_WORDS) * sizeof (unsigned)));
+        m.tiles = mtiles; m.epoch = 0xffffffffu;    /* forces the clear below */
     }
-    const int p = sc->cur, q = p ^ 1;
-    k_sched_build<<<(ntiles + 255) / 256, 256, 0, st>>> (sc->cost[p], tiles_x, tiles_y, sc->t_heavy, sc->t_mid,
-                                                         sc->list[0], sc->list[1], sc->list[2], sc->count);
-    g_launches++;
-    CU (cudaGetLastError ());
-    out->list[0] = sc->list[0]; out->list[1] = sc->list[1]; out->list[2] = sc->list[2];
-    out->count = sc->count;
-    out->cost_next = sc->cost[q];
-    sc->cur = q;
+    if (++m.epoch == 0u)
+    {
+        m.epoch = 1;
+        CU (cudaMemsetAsync (m.buf, 0, (2 * m.tiles + MASK_CTL_WORDS) * sizeof (unsigned), st));
+    }
     return 0;
 }
+
+/* after a failure between k_mark and the render kernel that would have consumed (and reset) the lists */
+static void maskbuf_reset_lists (MaskBuf &m, cudaStream_t st)
+{
+    if (m.buf) cudaMemsetAsync (m.buf + 2 * m.tiles, 0, MASK_CTL_WORDS * sizeof (unsigned), st);
+}
+
+static DevMask maskbuf_band (const MaskBuf &m, int band, size_t first_tile)
+{
+    DevMask k;
+    k.mark = m.buf; k.list = m.buf + m.tiles + first_tile;
+    k.ctl = m.buf + 2 * m.tiles + 4 * band;
+    k.epoch = m.epoch;
+    return k;
+}
+
+/* --------------------------------------------------- per-device render state */
+
+/* A render launch borrows a SLOT of its device: a pair of self-resetting tile counters and a screen-mask
+   buffer; the quality modes other than BEST also borrow one of a few SCRATCH buffers for the root searches
+   (20 B per pixel of the band: too big to keep one per slot).  Launches rotate through
+   RENDER_SLOTS slots; should a slot come round again while its previous borrower is still queued or
+   running on ANOTHER stream, the new stream waits for it (one event per slot), so sharing is always
+   ordered.  vox_render may be called from any thread (Manual.md:171-175): everything here is guarded by
+   the device's mutex, which is held from slot acquisition until the launch is queued and the slot's
+   event recorded. */
+#define RENDER_SLOTS 64
+struct RenderSlot
+{
+    cudaEvent_t ev;
+    cudaStream_t last;
+    int used;
+    MaskBuf mask;
+};
+
+#define RENDER_SCRATCHES 4
+struct RenderScratch
+{
+    cudaEvent_t ev;
+    cudaStream_t last;
+    int used;
+    void *buf;                  /* 20 B per pixel of a band: hit points, then leaf ids */
+    size_t bytes;
+};
+
+struct RenderDevice
+{
+    std::mutex lock;
+    int ready;
+    unsigned seq;
+    unsigned *counters;         /* 2 per slot */
+    int blocks[6];              /* resident grid of: K1, K1 with hits, K1 lit, K1b, K1b lit, streaming K2 */
+    RenderSlot slot[RENDER_SLOTS];
+    unsigned scratch_seq;
+    RenderScratch scratch[RENDER_SCRATCHES];
+};
+static RenderDevice g_rdev[64];
+
+enum { GRID_K1 = 0, GRID_K1_HITS, GRID_K1_LIT, GRID_K1B, GRID_K1B_LIT, GRID_RAYS_STREAM };
+
+/* call with the device's lock held */
+static int render_device_init (RenderDevice &rd, int device)
+{
+    if (rd.ready) return 0;
+    unsigned *p = NULL;
+    CU (cudaMalloc (&p, RENDER_SLOTS * 2 * sizeof (unsigned)));
+    cudaError_t e = cudaMemset (p, 0, RENDER_SLOTS * 2 * sizeof (unsigned));
+    if (e != cudaSuccess) { cudaFree (p); return fail ("cudaMemset of the tile counters failed: %s", cudaGetErrorString (e)); }
+    int sms = 0, b = 0;
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
+#define RESIDENT(slot_, kernel_) do { b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, kernel_, RENDER_BLOCK, 0); \
+                                      rd.blocks[slot_] = sms * (b > 0 ? b : 1); } while (0)
+    RESIDENT (GRID_K1, (k_render_persistent<false, RENDER_STRIPS, false>));
+    RESIDENT (GRID_K1_HITS, (k_render_persistent<true, RENDER_STRIPS, false>));
+    RESIDENT (GRID_K1_LIT, (k_render_persistent<true, RENDER_STRIPS, true>));
+    RESIDENT (GRID_K1B, (k_render_blocks<true, false, true>));
+    RESIDENT (GRID_K1B_LIT, (k_render_blocks<true, true, true>));
+#undef RESIDENT
+    b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, k_rays_stream<true>, RAYS_BLOCK, 0);
+    rd.blocks[GRID_RAYS_STREAM] = sms * (b > 0 ? b : 1);
+    rd.counters = p;
+    rd.ready = 1;
+    return 0;
+}
+
+/* K2 in its streaming form borrows a slot's pair of self-resetting counters like a render launch does */
+static int rays_stream_launch (const voxgpu_tree *t, uint32_t start, const float *d_o, const float *d_d, size_t n,
+                               int32_t *d_leaf, float *d_pts, int32_t *d_vox, const unsigned *perm, cudaStream_t st)
+{
+    RenderDevice &rd = g_rdev[t->device];
+    std::lock_guard<std::mutex> guard (rd.lock);
+    if (render_device_init (rd, t->device)) return -1;
+    const unsigned idx = rd.seq++ % RENDER_SLOTS;
+    RenderSlot &sl = rd.slot[idx];
+    if (!sl.ev) CU (cudaEventCreateWithFlags (&sl.ev, cudaEventDisableTiming));
+    if (sl.used && sl.last != st) CU (cudaStreamWaitEvent (st, sl.ev, 0));
+    const size_t want = (n + RAYS_BLOCK - 1) / RAYS_BLOCK;
+    int grid = rd.blocks[GRID_RAYS_STREAM];
+    if ((size_t) grid > want) grid = (int) want;
+    if (perm)
+        k_rays_stream<true><<<grid, RAYS_BLOCK, 0, st>>> (tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, (unsigned) n,
+                                                         d_leaf, (float4*) d_pts, d_vox, perm, rd.counters + 2 * idx, g_rays_refill);
+    else
+        k_rays_stream<false><<<grid, RAYS_BLOCK, 0, st>>> (tree_ref (t), start, (const float4*) d_o, (const float4*) d_d, (unsigned) n,
+                                                          d_leaf, (float4*) d_pts, d_vox, NULL, rd.counters + 2 * idx, g_rays_refill);
+    g_launches++;
+    const cudaError_t e = cudaGetLastError ();
+    if (cudaEventRecord (sl.ev, st) == cudaSuccess) { sl.last = st; sl.used = 1; }
+    if (e != cudaSuccess) return fail ("voxgpu_rays_device: launch failed: %s", cudaGetErrorString (e));
+    return 0;
+}
+
+/* ------------------------------------------------------------ k_mark + bounds */
 
 /*
  * Screen mask.  Every voxel lies in the box of one node of the tree's cut (voxgpu_tree.cut); a ray that
  * hits the voxel passes through that box, so its pixel lies in the convex hull of the box's projected
- * corners (see voxgpu_screen_bounds for the argument) and therefore in their bounding rectangle.  One
- * thread per cut node projects its box (fp32 here: the error is ~1e-3 pixel, the rectangle is widened by 2)
- * and marks the 8x4 tiles the rectangle touches.  A tile nobody marked cannot show a voxel: the render
- * kernel clears it without casting its rays -- on a C2 frame half of the primary rays enter the root box
- * but only a fifth hit a voxel, and the ones in between cost 40-50 % of all node fetches.
- * A box not safely in front of the camera, or covering more than 4096 tiles, raises the "no bounds"
- * flag behind the mask instead (the frame is then rendered without the mask).
+ * corners (see voxgpu_screen_bounds for the argument) and therefore in their bounding rectangle.  Eight
+ * lanes per cut node project its box (fp32 here: the error is ~1e-3 pixel, the rectangle is widened by 2)
+ * and mark the 8x4 tiles the rectangle touches with the frame's epoch -- only tiles of rows the render
+ * launches of this mask will draw ([y0, y1), and of those the tile rows r with r % il_world == il_rank).
+ * A tile nobody marked cannot show a voxel: the render kernel clears it without casting its rays --
+ * on a C2 frame half of the primary rays enter the root box but only a fifth hit a voxel, and the ones in
+ * between cost 40-50 % of all node fetches.  A box not safely in front of the camera, or covering more
+ * than 4096 tiles, raises the "no bounds" flag of every band instead (the frame is then rendered without
+ * the mask).  k_list then compacts the marked tiles of every band into that band's list (see
+ * k_render_persistent for what the list is for).
+ * (Tried and dropped: building the lists inside k_mark with atomics -- the first box to reach a tile
+ * appending it -- made k_mark the longest kernel of the frame: 17 000 appends on ONE counter, where the
+ * stores below wait for nobody; and a second list of "heavy" tiles, many boxes along the line of sight,
+ * handed out first: on C2 the number of boxes over a tile does not predict its cost, correlation
+ * 0.02-0.14, profiles/r02_tile_trace.txt.)
  */
+struct MarkBands
+{
+    int y0, y1;                 /* frame rows the launches of this mask draw */
+    int nbands;                 /* [y0, y1) is cut into nbands bands of whole 4-row units: band i starts at unit (units*i)/nbands */
+    int il_world, il_rank;      /* only tile rows r (counted from y0) with r % il_world == il_rank */
+};
+
 __global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned n_cut, DevCamera cam,
-                        int w, int h, unsigned char * __restrict__ mask, int mask_tiles, unsigned char epoch,
-                        int band_y0, int band_y1)
+                        int w, int h, unsigned *buf, unsigned mtiles, unsigned epoch, MarkBands mb)
 {
     /* eight lanes per node, one per corner of its box; min/max over the eight by shuffles */
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,28 +274,56 @@ __global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned 
         anybad |= __shfl_xor_sync (0xffffffffu, anybad, off);
     }
     if (!live) return;
+    unsigned *mark = buf, *ctl = buf + 2 * (size_t) mtiles;
     if (!anybad)
     {
         const float x0 = floorf (lox) - 2.0f, x1 = ceilf (hix) + 3.0f, y0 = floorf (loy) - 2.0f, y1 = ceilf (hiy) + 3.0f;
         if (x1 <= 0.0f || y1 <= 0.0f || x0 >= (float) w || y0 >= (float) h) return;       /* off screen */
         const int tiles_x = w >> 3;
         const int tx0 = max ((int) x0, 0) >> 3, tx1 = (min ((int) x1, w) + 7) >> 3;
-        /* only the rows [band_y0, band_y1) of the frame are drawn by the launch this mask is for */
-        const int ty0 = max ((int) y0, band_y0) >> 2, ty1 = (min ((int) y1, band_y1) + 3) >> 2;
+        const int ty0 = max ((int) y0, mb.y0) >> 2, ty1 = (min ((int) y1, mb.y1) + 3) >> 2;
         if (ty1 <= ty0) return;
         const int nx = tx1 - tx0, n = nx * (ty1 - ty0);
         if (n <= 4096)
         {
-            for (int j = k; j < n; j += 8) mask[(size_t) (ty0 + j / nx) * tiles_x + tx0 + j % nx] = epoch;
+            const int u0 = mb.y0 >> 2;
+            for (int j = k; j < n; j += 8)
+            {
+                const int ty = ty0 + j / nx, tx = tx0 + j % nx;
+                if (mb.il_world > 1 && (ty - u0) % mb.il_world != mb.il_rank) continue;
+                mark[(size_t) ty * tiles_x + tx] = epoch;       /* a plain store: nobody waits for it */
+            }
             return;
         }
     }
-    if (k == 0) mask[mask_tiles] = epoch;   /* no bounds for this frame */
+    if (k == 0) for (int b = 0; b < mb.nbands; b++) ctl[4*b + 1] = epoch;   /* no bounds for this frame */
 }
 
-extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
-                                    const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                                    voxgpu_stream s, voxgpu_sched *sched);
+/* The marked tiles of every band, compacted: one warp looks at 32 tiles of one tile row (one coalesced load),
+   and appends the marked ones to the list of the row's band with ONE atomicAdd (ballot + popc ranks). */
+__global__ void k_list (unsigned *buf, unsigned mtiles, unsigned epoch, int tiles_x, MarkBands mb)
+{
+    const unsigned *mark = buf;
+    unsigned *list = buf + mtiles, *ctl = buf + 2 * (size_t) mtiles;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned groups_x = ((unsigned) tiles_x + 31u) >> 5;
+    const int units = (mb.y1 - mb.y0) >> 2, u0 = mb.y0 >> 2;
+    const int il_world = mb.il_world > 1 ? mb.il_world : 1, il_rank = mb.il_world > 1 ? mb.il_rank : 0;
+    const int r = (int) (warp / groups_x) * il_world + il_rank;           /* tile row inside [y0, y1) */
+    if (r >= units) return;
+    const int ty = u0 + r, tx = (int) ((warp % groups_x) << 5) + lane;
+    const bool marked = tx < tiles_x && mark[(size_t) ty * tiles_x + tx] == epoch;
+    const unsigned m = __ballot_sync (0xffffffffu, marked);
+    if (!m) return;
+    /* band b = the i with (units*i)/nbands <= r < (units*(i+1))/nbands; its list starts at its first tile */
+    const int b = mb.nbands > 1 ? (int) (((long long) (r + 1) * mb.nbands - 1) / units) : 0;
+    const size_t first = (size_t) (u0 + (int) ((long long) units * b / mb.nbands)) * tiles_x;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd (ctl + 4*b, (unsigned) __popc (m));
+    base = __shfl_sync (0xffffffffu, base, 0);
+    if (marked) list[first + base + __popc (m & ((1u << lane) - 1u))] = (unsigned) (ty * tiles_x + tx);
+}
 
 /*
  * Screen-space bounds of the tree's root box for a pinhole camera: a primary ray through pixel
@@ -344,42 +392,10 @@ extern "C" void voxgpu_screen_bounds (const float root_min[3], const float root_
     out[3] = y1 < 0 ? 0 : (y1 > h ? h : (int) y1);
 }
 
-extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
-                              const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                              voxgpu_stream s)
-{
-    return voxgpu_render_sched (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, NULL);
-}
-
-/* Per-device ring of screen-mask buffers for launches that bring no mask of their own, one per render
-   slot (slot_acquire).  A buffer is never cleared between uses: "marked" is the slot's epoch value,
-   bumped per use, and the buffer is zeroed only when the epoch wraps or the slot grows. */
-#define MASK_SLOTS COUNTER_SLOTS
-struct MaskSlot { unsigned char *buf; size_t cap; unsigned epoch; };
-static MaskSlot g_mask_slots[64][MASK_SLOTS];
-
-static unsigned char* mask_slot (int device, unsigned idx, size_t bytes, cudaStream_t st, unsigned *epoch)
-{
-    MaskSlot &m = g_mask_slots[device][idx];
-    if (m.cap < bytes)
-    {
-        if (m.buf) { cudaDeviceSynchronize (); cudaFree (m.buf); m.buf = NULL; m.cap = 0; }
-        if (cudaMalloc (&m.buf, bytes) != cudaSuccess) return NULL;
-        m.cap = bytes; m.epoch = 255;              /* forces the clear below */
-    }
-    if (++m.epoch > 255u)
-    {
-        m.epoch = 1;
-        if (cudaMemsetAsync (m.buf, 0, m.cap, st) != cudaSuccess) return NULL;
-    }
-    *epoch = m.epoch;
-    return m.buf;
-}
-
 static int mask_usable (const voxgpu_tree *t, const voxgpu_camera *c)
 {
     return g_cull && g_mask && t->n_cut > 1 && (c->kind == VOXGPU_CAMERA_SIMPLE || c->kind == VOXGPU_CAMERA_DOOM) &&
-           c->mul > 0.0f && g_variant >= 1 && g_variant <= 2;
+           c->mul > 0.0f;
 }
 
 static DevCamera dev_camera (const voxgpu_camera *c)
@@ -394,182 +410,178 @@ static DevCamera dev_camera (const voxgpu_camera *c)
     return dc;
 }
 
-/* ext_mask / ext_epoch: a screen mask the caller has already marked for this frame (the presenter marks
-   one per frame and shares it between the bands); NULL: make one for this launch */
+/* queue k_mark for the rows `mb` of a w x h frame into `m` (maskbuf_begin has been called) */
+static int mark_launch (const voxgpu_tree *t, const voxgpu_camera *c, int w, int h, const MaskBuf &m, const MarkBands &mb, cudaStream_t st)
+{
+    k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, st>>> (tree_ref (t), t->cut, t->n_cut, dev_camera (c), w, h, m.buf,
+                                                       (unsigned) m.tiles, m.epoch, mb);
+    const int il = mb.il_world > 1 ? mb.il_world : 1;
+    const unsigned rows = (unsigned) ((((mb.y1 - mb.y0) >> 2) + il - 1) / il);
+    const unsigned warps = rows * ((unsigned) ((w >> 3) + 31) >> 5);
+    k_list<<<(warps + 3) / 4, 128, 0, st>>> (m.buf, (unsigned) m.tiles, m.epoch, w >> 3, mb);
+    g_launches += 2;
+    CU (cudaGetLastError ());
+    return 0;
+}
+
+/* ------------------------------------------------------------- voxgpu_render */
+
+/* ext_mask: a screen mask the caller has already marked for this frame and this band (the presenter marks one
+   per frame and shares it between the bands); NULL: make one for this launch */
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, voxgpu_sched *sched, const unsigned char *ext_mask, unsigned ext_epoch);
+                        voxgpu_stream s, const DevMask *ext_mask);
 
-extern "C" int voxgpu_render_sched (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
-                                    const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                                    voxgpu_stream s, voxgpu_sched *sched)
+extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
+                              const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
+                              voxgpu_stream s)
 {
-    return render_impl (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, sched, NULL, 0);
+    return render_impl (t, c, f, d_tex, d_pixels, d_leaf, d_pts, s, NULL);
 }
 
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, voxgpu_sched *sched, const unsigned char *ext_mask, unsigned ext_epoch)
+                        voxgpu_stream s, const DevMask *ext_mask)
 {
-    if (check_tree (t, 0, "voxgpu_render")) return -1;
+    /* ---- every argument is checked before anything is borrowed or queued ---- */
     if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
+    if (check_tree (t, f->start_node, "voxgpu_render")) return -1;
     if ((f->w & 0xf) || (f->h & 0x3) || f->w <= 0 || f->h <= 0)
         return fail ("voxgpu_render: bad geometry %dx%d (renderer.c:97-100)", f->w, f->h);
     if (f->y0 < 0 || f->y1 > f->h || f->y0 >= f->y1 || (f->y0 & 3) || (f->y1 & 3))
         return fail ("voxgpu_render: bad row band [%d,%d)", f->y0, f->y1);
     if (c->kind == VOXGPU_CAMERA_TABLE && !c->dir_table) return fail ("voxgpu_render: TABLE camera without table");
+    const unsigned mode = f->quality & 3u, merge = f->quality & 12u;
+    if (mode > 2u || merge > 8u || (merge && mode != 2u))
+        return fail ("voxgpu_render: invalid quality %u (renderer.c:179-195)", f->quality);
+    const int il_world = f->interleave_world > 1 ? f->interleave_world : 1;
+    const int il_rank = f->interleave_world > 1 ? f->interleave_rank : 0;
+    if (il_rank < 0 || il_rank >= il_world) return fail ("voxgpu_render: interleave rank %d of %d", il_rank, il_world);
+    if (il_world > 1 && mode != 0u) return fail ("voxgpu_render: interleaved tile rows need quality BEST");
+    if (mode != 0u && (((size_t) d_pixels & 15) || (f->pitch_pixels & 3)))
+        return fail ("voxgpu_render: quality modes other than BEST need 16-byte aligned rows");
+    const bool lit = f->lights != NULL;
+    if (lit && f->lights->device != t->device)
+        return fail ("voxgpu_render: lights live on device %d, tree on %d", f->lights->device, t->device);
 
-    DevCamera dc;
-    dc.kind = c->kind;
-    dc.px = c->position[0]; dc.py = c->position[1]; dc.pz = c->position[2];
-    dc.mul = c->mul; dc.xsub = c->xsub; dc.ysub = c->ysub;
-    dc.qw = c->rotation[0]; dc.qi = c->rotation[1]; dc.qj = c->rotation[2]; dc.qk = c->rotation[3];
-    dc.sinphi = c->sinphi; dc.cosphi = c->cosphi; dc.k = c->k;
-    dc.table = (const float4*) c->dir_table;
+    const DevCamera dc = dev_camera (c);
     DevFrame df;
     df.w = f->w; df.y0 = f->y0; df.rows = f->y1 - f->y0; df.pitch = f->pitch_pixels;
     df.amask = f->fmt.amask;
     df.rloss = f->fmt.rloss; df.gloss = f->fmt.gloss; df.bloss = f->fmt.bloss;
     df.rshift = f->fmt.rshift; df.gshift = f->fmt.gshift; df.bshift = f->fmt.bshift;
     memset (&df.lt, 0, sizeof df.lt);
+    if (lit) df.lt = f->lights->ref;
     {
         int cull[4] = { 0, f->w, 0, f->h };
         if (g_cull) voxgpu_screen_bounds (t->root_min, t->root_max, c, f->w, f->h, cull);
         df.cx0 = cull[0]; df.cx1 = cull[1]; df.cy0 = cull[2]; df.cy1 = cull[3];
     }
-    df.il_world = f->interleave_world > 1 ? f->interleave_world : 1;
-    df.il_rank = f->interleave_world > 1 ? f->interleave_rank : 0;
-    if (df.il_rank < 0 || df.il_rank >= df.il_world) return fail ("voxgpu_render: interleave rank %d of %d", df.il_rank, df.il_world);
-    if (df.il_world > 1 && ((f->quality & 3u) != 0u || g_variant == 0 || g_variant >= 3))
-        return fail ("voxgpu_render: interleaved tile rows need quality BEST and the default kernel variant");
-    const bool lit = f->lights != NULL;
-    if (lit)
-    {
-        if (f->lights->device != t->device) return fail ("voxgpu_render: lights live on device %d, tree on %d", f->lights->device, t->device);
-        df.lt = f->lights->ref;
-    }
+    df.il_world = il_world; df.il_rank = il_rank;
 
-    const unsigned slot = slot_acquire (t->device, (cudaStream_t) s);
-    /* screen mask for this launch: mark from the tree's cut into the slot's buffer */
-    unsigned char *mask = NULL;
-    df.mask = NULL; df.mask_tiles = 0; df.mask_epoch = 1;
-    if (ext_mask)
-    {
-        df.mask = ext_mask; df.mask_tiles = (f->w >> 3) * (f->h >> 2); df.mask_epoch = ext_epoch;
-    }
-    else if (mask_usable (t, c) && !(f->interleave_world > 1))
-    {
-        /* (not for a frame interleaved over N GPUs: every rank would mark the WHOLE mask for 1/N of the tiles --
-           measured on C5 at N = 8: 1.69 ms per 8K frame with the mask, 0.68 ms without) */
-        const int mtiles = (f->w >> 3) * (f->h >> 2);
-        unsigned epoch = 1;
-        mask = mask_slot (t->device, slot, (size_t) mtiles + 4, (cudaStream_t) s, &epoch);
-        if (!mask) return fail ("voxgpu_render: cannot allocate the screen mask");
-        k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, (cudaStream_t) s>>> (tree_ref (t), t->cut, t->n_cut, dc, f->w, f->h, mask, mtiles, (unsigned char) epoch, f->y0, f->y1);
-        g_launches++;
-        df.mask = mask; df.mask_tiles = mtiles; df.mask_epoch = epoch;
-    }
+    cudaStream_t st = (cudaStream_t) s;
+    RenderDevice &rd = g_rdev[t->device];
+    std::lock_guard<std::mutex> guard (rd.lock);
+    if (render_device_init (rd, t->device)) return -1;
 
-    const int ntiles = (df.w >> 3) * (df.rows >> 2);
-    const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
-    if ((f->quality & 3u) != 0u)
+    /* borrow a slot; its previous borrower on another stream goes first */
+    const unsigned idx = rd.seq++ % RENDER_SLOTS;
+    RenderSlot &sl = rd.slot[idx];
+    if (!sl.ev) CU (cudaEventCreateWithFlags (&sl.ev, cudaEventDisableTiming));
+    if (sl.used && sl.last != st) CU (cudaStreamWaitEvent (st, sl.ev, 0));
+    unsigned *counters = rd.counters + 2 * idx;
+    int rc = 0;
+    bool marked_here = false;
+    RenderScratch *scratch = NULL;
+    /* whatever happens below, the slot's event is recorded behind what has been queued */
+#define LEAVE(code_) do { rc = (code_); goto leave; } while (0)
+
     {
-        /* FAST / ADAPTIVE (+ ray merge): the block-sequential kernel */
-        if ((f->quality & 3u) > 2u || (f->quality & 12u) > 8u || ((f->quality & 12u) && (f->quality & 3u) != 2u))
-            return fail ("voxgpu_render: invalid quality %u (renderer.c:179-195)", f->quality);
-        if (((size_t) d_pixels & 15) || (df.pitch & 3))
-            return fail ("voxgpu_render: quality modes other than BEST need 16-byte aligned rows");
-        unsigned *counters = counter_slot (t->device, slot);
-        if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
-        const int warps = (((df.w >> 2) + 7) >> 3) * (((df.rows >> 2) + 3) >> 2);
-        int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
-        const int cap = g_render_blocks[t->device][lit ? 6 : 2];
-        if (grid > cap) grid = cap;
-        cudaStream_t st = (cudaStream_t) s;
-        const bool hits = d_leaf || d_pts;
-        static const bool onepass = getenv ("VOXGPU_BLOCKS_ONEPASS") && atoi (getenv ("VOXGPU_BLOCKS_ONEPASS"));
-        int *pre_leaf = NULL;
-        float4 *pre_pts = NULL;
-        if (!onepass)
+        /* screen mask for this launch: mark from the tree's cut into the slot's buffer */
+        DevMask mk;
+        memset (&mk, 0, sizeof mk);
+        if (ext_mask) mk = *ext_mask;
+        else if (mask_usable (t, c))
         {
-            /* launch 1: every root search of the band, pixel-parallel (K1 as for BEST), into stream-ordered scratch */
-            const size_t npix = (size_t) df.w * df.rows;
-            CU (cudaMallocAsync (&pre_leaf, npix * sizeof (int), st));
-            CU (cudaMallocAsync (&pre_pts, npix * sizeof (float4), st));
-            unsigned *c1 = counters;      /* the two launches run one after the other on this stream; the counters reset themselves */
-            int g1 = g_render_blocks[t->device][1];
+            const size_t mtiles = (size_t) (f->w >> 3) * (f->h >> 2);
+            if (maskbuf_begin (sl.mask, mtiles, st)) LEAVE (-1);
+            MarkBands mb;
+            mb.y0 = f->y0; mb.y1 = f->y1; mb.nbands = 1; mb.il_world = il_world; mb.il_rank = il_rank;
+            if (mark_launch (t, c, f->w, f->h, sl.mask, mb, st)) LEAVE (-1);
+            marked_here = true;
+            mk = maskbuf_band (sl.mask, 0, (size_t) (f->y0 >> 2) * (f->w >> 3));
+        }
+
+        const int ntiles = (df.w >> 3) * (df.rows >> 2);
+        const int blocks = (ntiles + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
+        const bool hits = d_leaf || d_pts;
+        float4 *pts = (float4*) d_pts;
+        const TreeRef tr = tree_ref (t);
+        const unsigned start = f->start_node;
+        if (mode != 0u)
+        {
+            /* FAST / ADAPTIVE (+ ray merge).  Launch 1: every root search of the band, pixel-parallel (K1 as for
+               BEST, unlit), into the slot's scratch; launch 2: the block walk, looking those results up. */
+            const size_t npix = (size_t) df.w * df.rows, need = npix * (sizeof (int) + sizeof (float4));
+            RenderScratch &sc = rd.scratch[rd.scratch_seq++ % RENDER_SCRATCHES];
+            if (!sc.ev && cudaEventCreateWithFlags (&sc.ev, cudaEventDisableTiming) != cudaSuccess) { fail ("voxgpu_render: cudaEventCreate failed"); LEAVE (-1); }
+            if (sc.bytes < need)
+            {
+                if (sc.buf) { cudaError_t e = cudaDeviceSynchronize (); cudaFree (sc.buf); sc.buf = NULL; sc.bytes = 0;
+                              if (e != cudaSuccess) { fail ("voxgpu_render: %s", cudaGetErrorString (e)); LEAVE (-1); } }
+                cudaError_t e = cudaMalloc (&sc.buf, need);
+                if (e != cudaSuccess) { fail ("voxgpu_render: scratch of %zu bytes: %s", need, cudaGetErrorString (e)); LEAVE (-1); }
+                sc.bytes = need;
+            }
+            if (sc.used && sc.last != st && cudaStreamWaitEvent (st, sc.ev, 0) != cudaSuccess) { fail ("voxgpu_render: cudaStreamWaitEvent failed"); LEAVE (-1); }
+            scratch = &sc;
+            float4 *pre_pts = (float4*) sc.buf;
+            int *pre_leaf = (int*) ((char*) sc.buf + npix * sizeof (float4));
+            int g1 = rd.blocks[GRID_K1_HITS];
             if (g1 > blocks) g1 = blocks;
-            DevSched none;
-            memset (&none, 0, sizeof none);
             DevFrame plain = df;
             memset (&plain.lt, 0, sizeof plain.lt);
-            k_render_persistent<true, RENDER_STRIPS, false><<<g1, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, plain, d_tex, d_pixels, pre_leaf, pre_pts, c1, NULL, none);
+            k_render_persistent<true, RENDER_STRIPS, false><<<g1, RENDER_BLOCK, 0, st>>> (tr, start, dc, plain, mk, d_tex, d_pixels, pre_leaf, pre_pts, counters, NULL);
             g_launches++;
-            /* launch 2: the walk, looking those results up */
+            marked_here = false;            /* the lists are consumed */
+            const int warps = (((df.w >> 2) + 7) >> 3) * (((df.rows >> 2) + 3) >> 2);
+            int grid = (warps + RENDER_BLOCK/32 - 1) / (RENDER_BLOCK/32);
+            const int cap = rd.blocks[lit ? GRID_K1B_LIT : GRID_K1B];
+            if (grid > cap) grid = cap;
+            /* the two launches run one after the other on this stream; the counters reset themselves */
             if (lit)
-                k_render_blocks<true, true, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, pre_leaf, pre_pts);
+                k_render_blocks<true, true, true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, f->quality, d_tex, d_pixels, d_leaf, pts, counters, pre_leaf, pre_pts);
             else if (hits)
-                k_render_blocks<true, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, pre_leaf, pre_pts);
+                k_render_blocks<true, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, f->quality, d_tex, d_pixels, d_leaf, pts, counters, pre_leaf, pre_pts);
             else
-                k_render_blocks<false, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters, pre_leaf, pre_pts);
-            CU (cudaGetLastError ());
-            CU (cudaFreeAsync (pre_leaf, st));
-            CU (cudaFreeAsync (pre_pts, st));
-        }
-        else if (lit)
-            k_render_blocks<true, true, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, NULL, NULL);
-        else if (hits)
-            k_render_blocks<true, false, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, d_leaf, (float4*) d_pts, counters, NULL, NULL);
-        else
-            k_render_blocks<false, false, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters, NULL, NULL);
-    }
-    else if (g_variant == 0 && !lit)
-    {
-        if (d_leaf || d_pts)
-            k_render<true><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, (float4*) d_pts);
-        else
-            k_render<false><<<blocks, RENDER_BLOCK, 0, (cudaStream_t) s>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL);
-    }
-    else
-    {
-        unsigned *counters = counter_slot (t->device, slot);
-        if (!counters) return fail ("voxgpu_render: cannot allocate tile counters");
-        const bool hits = d_leaf || d_pts;
-        int grid = g_render_blocks[t->device][hits ? 1 : 0];
-        if (grid > blocks) grid = blocks;
-        cudaStream_t st = (cudaStream_t) s;
-        float4 *pts = (float4*) d_pts;
-        DevSched sch;
-        memset (&sch, 0, sizeof sch);
-        if (sched && g_variant == 1 && sched->t_heavy && df.il_world == 1 &&
-            sched_prepare (sched, t->device, df.w, df.y0, df.rows, st, &sch)) return -1;
-        if (lit)
-        {   /* light manager attached: the default kernel, shading through the flattened M-tree */
-            grid = g_render_blocks[t->device][5];
-            if (grid > blocks) grid = blocks;
-            k_render_persistent<true, RENDER_STRIPS, true><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
-        }
-        else if (g_variant >= 3)
-        {   /* per-lane refill; g_variant - 2 = refill threshold when >= 3 ... */
-            const int rmin = g_refill_min;
-            grid = g_render_blocks[t->device][hits ? 4 : 3];
-            if (grid > blocks) grid = blocks;
-            if (hits) k_render_stream<true, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, rmin);
-            else      k_render_stream<false, RENDER_STRIPS><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, rmin);
-        }
-        else if (g_variant == 2)
-        {   /* raster tile order, kept for A/B measurements */
-            if (hits) k_render_persistent<true, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
-            else      k_render_persistent<false, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
+                k_render_blocks<false, false, true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, f->quality, d_tex, d_pixels, NULL, NULL, counters, pre_leaf, pre_pts);
         }
         else
         {
-            if (hits) k_render_persistent<true, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, d_leaf, pts, counters, g_trace, sch);
-            else      k_render_persistent<false, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tree_ref (t), dc, df, d_tex, d_pixels, NULL, NULL, counters, g_trace, sch);
+            int grid = rd.blocks[lit ? GRID_K1_LIT : (hits ? GRID_K1_HITS : GRID_K1)];
+            if (grid > blocks) grid = blocks;
+            if (lit)      /* light manager attached: shading through the flattened M-tree */
+                k_render_persistent<true, RENDER_STRIPS, true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
+            else if (g_variant == 2)
+            {   /* raster tile order, kept for A/B measurements */
+                if (hits) k_render_persistent<true, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
+                else      k_render_persistent<false, 1u, false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, NULL, NULL, counters, g_trace);
+            }
+            else
+            {
+                if (hits) k_render_persistent<true, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
+                else      k_render_persistent<false, RENDER_STRIPS, false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, NULL, NULL, counters, g_trace);
+            }
+            marked_here = false;
         }
+        g_launches++;
+        cudaError_t e = cudaGetLastError ();
+        if (e != cudaSuccess) { fail ("voxgpu_render: launch failed: %s", cudaGetErrorString (e)); LEAVE (-1); }
     }
-    g_launches++;
-    CU (cudaGetLastError ());
-    slot_release (t->device, slot, (cudaStream_t) s);
-    return 0;
+leave:
+#undef LEAVE
+    if (marked_here) maskbuf_reset_lists (sl.mask, st);     /* k_mark ran, its consumer did not */
+    if (scratch && cudaEventRecord (scratch->ev, st) == cudaSuccess) { scratch->last = st; scratch->used = 1; }
+    if (cudaEventRecord (sl.ev, st) == cudaSuccess) { sl.last = st; sl.used = 1; }
+    return rc;
 }

@@ -72,6 +72,9 @@ struct TreeRef
 #ifndef VOXGPU_SMEM_TOP
 #define VOXGPU_SMEM_TOP 0          /* nodes staged per CTA by the render kernel: 73 = levels 0-2, 585 = levels 0-3 */
 #endif
+#ifndef VOXGPU_EARLY_CTR
+#define VOXGPU_EARLY_CTR 1         /* fetch the split centre together with the node record */
+#endif
 #ifndef VOXGPU_PREFETCH
 #define VOXGPU_PREFETCH 0          /* prefetch.global.L1 of the child a lane descends into */
 #endif
@@ -399,8 +402,6 @@ __device__ __forceinline__ bool ball_tree (const TreeRef &tr, unsigned start, co
     return false;
 }
 
-#endif
-
 /* ======================================================================
  * Production traversal.  Same search, same fp32 results as ray_tree<> above
  * (which stays as the readable, instrumented form that mirrors the
@@ -555,6 +556,57 @@ __device__ __forceinline__ unsigned subspace_fast (const V3 c, const V3 p, bool 
 
 #define VOXGPU_FULL 0xffffffffu
 #define VOXGPU_DEAD 0xffffffffu
+
+/*
+ * The stack of pending calls of one lane.  Slots [0, VOXGPU_SMEM_STACK) live in shared memory, laid
+ * out [slot][thread] as float4: whatever slot each lane of a warp is at, lane l touches banks 4l..4l+3,
+ * so a 128-bit access is conflict-free (4 wavefronts, the minimum) -- in local memory the same access
+ * with 32 different stack depths costs up to 32 x 4 sector accesses in L1 (the r01 profile had the stack
+ * at 5.9 times the L1 sectors of the node fetches).  Deeper slots spill to per-thread local memory.
+ * Shared memory is carved out of the same SRAM as L1, so the number of slots is a trade against the L1
+ * hit rate of the node records: see DESIGN.md for the measured choice.  0 = everything in local memory.
+ */
+#ifndef VOXGPU_SMEM_STACK
+#define VOXGPU_SMEM_STACK 0
+#endif
+#define VOXGPU_STACK_THREADS 128    /* block size of every kernel that searches (K1, K1b, K2) */
+
+struct RayStack
+{
+    float4 *loc;            /* VOXGPU_RAY_STACK entries of per-thread scratch */
+#if VOXGPU_SMEM_STACK
+    float4 *sm;             /* this thread's column of the CTA's shared slots: slot i at sm[i * VOXGPU_STACK_THREADS] */
+#endif
+    __device__ __forceinline__ void put (int i, const float4 v) const
+    {
+#if VOXGPU_SMEM_STACK
+        if (i < VOXGPU_SMEM_STACK) sm[i * VOXGPU_STACK_THREADS] = v; else loc[i - VOXGPU_SMEM_STACK] = v;
+#else
+        loc[i] = v;
+#endif
+    }
+    __device__ __forceinline__ float4 get (int i) const
+    {
+#if VOXGPU_SMEM_STACK
+        if (i < VOXGPU_SMEM_STACK) return sm[i * VOXGPU_STACK_THREADS];
+        return loc[i - VOXGPU_SMEM_STACK];
+#else
+        return loc[i];
+#endif
+    }
+};
+
+/* in a kernel: `VOXGPU_DECLARE_STACK (stack);` declares the local (and shared) storage and a RayStack over it */
+#if VOXGPU_SMEM_STACK
+#define VOXGPU_DECLARE_STACK(name)                                                              \
+    __shared__ float4 name##_shared[VOXGPU_SMEM_STACK * VOXGPU_STACK_THREADS];                  \
+    float4 name##_local[VOXGPU_RAY_STACK];                                                      \
+    RayStack name; name.loc = name##_local; name.sm = name##_shared + threadIdx.x
+#else
+#define VOXGPU_DECLARE_STACK(name)                                                              \
+    float4 name##_local[VOXGPU_RAY_STACK];                                                      \
+    RayStack name; name.loc = name##_local
+#endif
 #ifndef VOXGPU_COOP_MAX_LANES
 #define VOXGPU_COOP_MAX_LANES 8      /* more lanes than this at a leaf: everyone loops over its own voxels
                                         (C2, tools/ab_variants.sh: 8 -> 12.54, 12 -> 12.48, 16 -> 12.40 Grays/s) */
@@ -591,7 +643,7 @@ __device__ __forceinline__ void lane_search_begin (LaneSearch &s, unsigned start
  * the warp, followed by the cooperative leaf tests and the pop of the next pending call.
  * WARP-SYNCHRONOUS: all 32 lanes must call it together.
  */
-__device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK &k, LaneSearch &s, float4 *stack, const int lane)
+__device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK &k, LaneSearch &s, const RayStack &stack, const int lane)
 {
     /* what a lane does after the node visit of this iteration */
     enum { IDLE = 0, GO = 1, POP = 2, LEAF = 3 };
@@ -609,6 +661,12 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
 #else
         load_rec (tr.rec + s.cur, q0, q1);
 #endif
+#if VOXGPU_EARLY_CTR
+        /* the split centre is fetched with the record, not after the box test has passed: one round trip to
+           L2 per node visit instead of two on the critical path of the longest rays (a wasted 16-byte load
+           for leaves and for boxes the ray misses) */
+        const float4 qc = __ldg (tr.ctr + s.cur);
+#endif
         const unsigned meta = __float_as_uint (q0.w);
         const unsigned link = __float_as_uint (q1.w);
         const unsigned kind = meta & 3u;
@@ -622,6 +680,8 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
             {
 #if VOXGPU_SMEM_TOP
                 const V3 c = v3 (top ? tr.top_ctr[s.cur] : __ldg (tr.ctr + s.cur));
+#elif VOXGPU_EARLY_CTR
+                const V3 c = v3 (qc);
 #else
                 const V3 c = v3 (__ldg (tr.ctr + s.cur));
 #endif
@@ -659,12 +719,12 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
                     const bool e1 = v1 && ((mask >> s1) & 1u);
                     const bool e2 = v2 && ((mask >> s2) & 1u);
                     /* the call tried first must be popped first: slot = number of later calls */
-                    if (e0) stack[s.sp + (int)(e1 && b01) + (int)(e2 && b02)] =
-                        make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0)));
-                    if (e1) stack[s.sp + (int)(e0 && !b01) + (int)(e2 && b12)] =
-                        make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1)));
-                    if (e2) stack[s.sp + (int)(e0 && !b02) + (int)(e1 && !b12)] =
-                        make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2)));
+                    if (e0) stack.put (s.sp + (int)(e1 && b01) + (int)(e2 && b02),
+                                       make_float4 (p0.x, p0.y, p0.z, __uint_as_float (child_id (link, mask, s0))));
+                    if (e1) stack.put (s.sp + (int)(e0 && !b01) + (int)(e2 && b12),
+                                       make_float4 (p1.x, p1.y, p1.z, __uint_as_float (child_id (link, mask, s1))));
+                    if (e2) stack.put (s.sp + (int)(e0 && !b02) + (int)(e1 && !b12),
+                                       make_float4 (p2.x, p2.y, p2.z, __uint_as_float (child_id (link, mask, s2))));
                     s.sp += (int) e0 + (int) e1 + (int) e2;
                 }
                 /* search.c:83-97: the child the entry point lies in goes first */
@@ -674,7 +734,7 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
             {
                 /* search.c:31-37 */
                 s.leaf = (int) s.cur;
-                stack[0] = make_float4 (entry.x, entry.y, entry.z, __int_as_float (-1));
+                stack.put (0, make_float4 (entry.x, entry.y, entry.z, __int_as_float (-1)));
                 s.cur = VOXGPU_DEAD; st = IDLE;
             }
             else
@@ -774,7 +834,7 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
             if (best < inf)
             {
                 s.leaf = (int) s.cur;
-                stack[0] = make_float4 (best_p.x, best_p.y, best_p.z, __uint_as_float (s.lf_link + (unsigned) best_i));
+                stack.put (0, make_float4 (best_p.x, best_p.y, best_p.z, __uint_as_float (s.lf_link + (unsigned) best_i)));
                 s.cur = VOXGPU_DEAD;
             }
             else st = POP;
@@ -787,7 +847,7 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
         if (s.sp == 0) s.cur = VOXGPU_DEAD;
         else
         {
-            const float4 e = stack[--s.sp];
+            const float4 e = stack.get (--s.sp);
             s.org.x = e.x; s.org.y = e.y; s.org.z = e.z;
             s.cur = __float_as_uint (e.w);
         }
@@ -795,13 +855,13 @@ __device__ __forceinline__ void warp_search_step (const TreeRef &tr, const RayK 
 }
 
 /* the result of a finished lane (s.cur == VOXGPU_DEAD) */
-__device__ __forceinline__ void lane_search_result (const LaneSearch &s, const float4 *stack, RayResult &out)
+__device__ __forceinline__ void lane_search_result (const LaneSearch &s, const RayStack &stack, RayResult &out)
 {
     out.leaf = s.leaf;
     out.voxel = -1;
     if (s.leaf >= 0)
     {
-        const float4 h = stack[0];
+        const float4 h = stack.get (0);
         out.point.x = h.x; out.point.y = h.y; out.point.z = h.z;
         out.voxel = __float_as_int (h.w);
     }
@@ -810,11 +870,10 @@ __device__ __forceinline__ void lane_search_result (const LaneSearch &s, const f
 /*
  * vox_ray_tree_intersection (search.c:8-153) for the 32 rays of a warp.
  * WARP-SYNCHRONOUS: all 32 lanes must call it together; `has_ray` says whether
- * this lane has a ray at all.  `stack` is VOXGPU_RAY_STACK float4 entries of
- * per-thread scratch.  Returns the number of iterations the warp needed.
+ * this lane has a ray at all.  `stack`: VOXGPU_DECLARE_STACK.  Returns the number of iterations the warp needed.
  */
 __device__ __forceinline__ int ray_tree_warp (const TreeRef &tr, unsigned start, const V3 origin, const V3 dir,
-                                              bool has_ray, float4 *stack, RayResult &out)
+                                              bool has_ray, const RayStack &stack, RayResult &out)
 {
     const RayK k = ray_constants (dir);
     const int lane = threadIdx.x & 31;
@@ -829,3 +888,5 @@ __device__ __forceinline__ int ray_tree_warp (const TreeRef &tr, unsigned start,
     lane_search_result (s, stack, out);
     return iterations;
 }
+
+#endif /* VOXGPU_TRAVERSE_CUH */

@@ -20,6 +20,8 @@
 #include <math.h>
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <condition_variable>
 
 #include "voxgpu.h"
 #include "traverse.cuh"
@@ -145,6 +147,15 @@ extern "C" void* voxgpu_ipc_open (const unsigned char handle[VOXGPU_IPC_HANDLE_B
     return p;
 }
 extern "C" int voxgpu_ipc_close (void *dptr) { CU (cudaIpcCloseMemHandle (dptr)); return 0; }
+/* One process, several devices: let kernels of the CURRENT device store into memory of `peer` (the same
+   NVLink path as the IPC mapping above, without a second process). */
+extern "C" int voxgpu_enable_peer (int peer)
+{
+    cudaError_t e = cudaDeviceEnablePeerAccess (peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError (); return 0; }
+    if (e != cudaSuccess) return fail ("cudaDeviceEnablePeerAccess (%d): %s", peer, cudaGetErrorString (e));
+    return 0;
+}
 
 /* ------------------------------------------------------------------- timer */
 
@@ -169,7 +180,9 @@ extern "C" float voxgpu_timer_elapsed_ms (voxgpu_timer *t)
 }
 
 #include "tree.inl"
+#include "sort.inl"
 #include "queries.inl"
+#include "volume.inl"
 #include "render_kernels.inl"
 #include "render_launch.inl"
 #include "present.inl"

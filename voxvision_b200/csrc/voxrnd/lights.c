@@ -13,14 +13,16 @@
 #include "private.h"
 #include "mtree-node.h"
 
+#define VOX_LIGHT_DEVICES 64
+
 struct vox_light_manager
 {
     vox_dot ambient_light;
     struct vox_mtree_node *bound_lights;
     unsigned long version;            /* bumped by every change */
-    voxgpu_lights *dev;               /* snapshot on device `dev_id`, made from `dev_version` */
-    int dev_id;
-    unsigned long dev_version;
+    /* snapshots by CUDA ordinal, each made from `dev_version[d]` (a context may draw on several devices) */
+    voxgpu_lights *dev[VOX_LIGHT_DEVICES];
+    unsigned long dev_version[VOX_LIGHT_DEVICES];
 };
 
 /* lights.c:81-89 */
@@ -36,7 +38,6 @@ struct vox_light_manager* vox_make_light_manager (void)
     if (!lm) return NULL;
     vox_dot_set (lm->ambient_light, 1, 1, 1);
     lm->version = 1;
-    lm->dev_id = -1;
     return lm;
 }
 
@@ -44,7 +45,10 @@ void vox_destroy_light_manager (struct vox_light_manager *lm)
 {
     if (!lm) return;
     vox_mtree_destroy (lm->bound_lights);
-    voxgpu_lights_free (lm->dev);
+    int cur = voxgpu_get_device ();
+    for (int d=0; d<VOX_LIGHT_DEVICES; d++)
+        if (lm->dev[d]) { voxgpu_set_device (d); voxgpu_lights_free (lm->dev[d]); }
+    if (cur >= 0) voxgpu_set_device (cur);
     free (lm);
 }
 
@@ -168,10 +172,11 @@ void vox_light_manager_flatten (const struct vox_light_manager *lm, uint32_t *n_
 const voxgpu_lights* vox_light_manager_device (struct vox_light_manager *lm)
 {
     int dev = voxgpu_get_device ();
-    if (lm->dev && lm->dev_id == dev && lm->dev_version == lm->version) return lm->dev;
+    if (dev < 0 || dev >= VOX_LIGHT_DEVICES) { vox_set_error ("bad CUDA device %d", dev); return NULL; }
+    if (lm->dev[dev] && lm->dev_version[dev] == lm->version) return lm->dev[dev];
     voxgpu_synchronize (NULL);                       /* frames in flight may still read the old snapshot */
-    voxgpu_lights_free (lm->dev);
-    lm->dev = NULL;
+    voxgpu_lights_free (lm->dev[dev]);
+    lm->dev[dev] = NULL;
 
     uint32_t nn = 0, ns = 0;
     vox_light_manager_flatten (lm, &nn, &ns, NULL, NULL, NULL, NULL);
@@ -184,10 +189,9 @@ const voxgpu_lights* vox_light_manager_device (struct vox_light_manager *lm)
     memcpy (f.ambient, lm->ambient_light, sizeof f.ambient);
     f.n_nodes = nn; f.n_spheres = ns;
     f.node_bounds = bounds; f.node_link = link; f.sphere_geom = geom; f.sphere_light = light;
-    lm->dev = voxgpu_lights_upload (&f);
+    lm->dev[dev] = voxgpu_lights_upload (&f);
     free (bounds); free (geom); free (light); free (link);
-    if (!lm->dev) { vox_set_error ("light upload failed: %s", voxgpu_last_error ()); return NULL; }
-    lm->dev_id = dev;
-    lm->dev_version = lm->version;
-    return lm->dev;
+    if (!lm->dev[dev]) { vox_set_error ("light upload failed: %s", voxgpu_last_error ()); return NULL; }
+    lm->dev_version[dev] = lm->version;
+    return lm->dev[dev];
 }

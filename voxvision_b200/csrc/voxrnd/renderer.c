@@ -29,34 +29,97 @@ static struct vox_rnd_ctx_full* allocate_context (void)
     ctx->texture_dirty = 1;
     ctx->quality = VOX_QUALITY_ADAPTIVE;
     ctx->device = -1;
+    ctx->want_devices = 1;
+    const char *env = getenv ("VOXVISION_DEVICES");
+    if (env) ctx->want_devices = (!strcmp (env, "all") || atoi (env) <= 0) ? 0 : atoi (env);
     return ctx;
 }
 
-/* Device-side resources; only possible (and only needed) with a GPU present. */
+/* Drop everything that lives on a device (the context stays usable: the next vox_render sets it up again). */
+static void context_device_release (struct vox_rnd_ctx_full *ctx)
+{
+    int cur = voxgpu_get_device ();
+    if (ctx->stream) voxgpu_synchronize (ctx->stream);
+    voxgpu_multi_destroy (ctx->multi);
+    ctx->multi = NULL;
+    if (ctx->device >= 0) voxgpu_set_device (ctx->device);
+    voxgpu_present_destroy (ctx->present);
+    ctx->present = NULL;
+    voxgpu_free (ctx->d_dir_table);
+    ctx->d_dir_table = NULL;
+    voxgpu_stream_destroy (ctx->stream);
+    ctx->stream = NULL;
+    for (int i=0; i<VOX_CTX_MAX_DEVICES; i++)
+    {
+        if (!ctx->d_texture[i]) continue;
+        voxgpu_set_device (ctx->devices[i]);
+        voxgpu_free (ctx->d_texture[i]);
+        ctx->d_texture[i] = NULL;
+    }
+    if (cur >= 0) voxgpu_set_device (cur);
+    ctx->device = -1;
+    ctx->ndev = 0;
+    ctx->texture_dirty = 1;
+}
+
+/* Device-side resources; only possible (and only needed) with a GPU present.  Restartable: a step that
+   succeeded is not repeated when a later one failed and the next vox_render tries again. */
 static int context_device_init (struct vox_rnd_ctx_full *ctx)
 {
     if (ctx->device >= 0) return 1;
-    if (voxgpu_device_count () <= 0)
+    const int visible = voxgpu_device_count ();
+    if (visible <= 0)
     {
         vox_set_error ("no CUDA device available (%s); voxvision-b200 has no CPU renderer", voxgpu_last_error ());
         return 0;
     }
     SDL_Surface *s = ctx->pub.surface;
     size_t bytes = (size_t) s->pitch * s->h;
-    if (!vox_surface_is_pinned (s))
+    if (!ctx->registered && !vox_surface_is_pinned (s))
     {
-        /* a caller-provided surface: page-lock and map its pixels in place */
+        /* a caller-provided surface: page-lock and map its pixels in place (for every device) */
         if (voxgpu_host_register (s->pixels, bytes))
         { vox_set_error ("cannot map surface pixels: %s", voxgpu_last_error ()); return 0; }
         ctx->registered = 1;
     }
-    ctx->d_texture = voxgpu_malloc (VOX_TEXTURE_SIZE);
-    ctx->stream = voxgpu_stream_create ();
-    ctx->present = voxgpu_present_create (s->w, s->h, 0);
-    if (!ctx->d_texture || !ctx->stream || !ctx->present)
-    { vox_set_error ("context device setup failed: %s", voxgpu_last_error ()); return 0; }
-    ctx->device = voxgpu_get_device ();
+    const int primary = voxgpu_get_device ();
+    if (primary < 0) { vox_set_error ("context device setup failed: %s", voxgpu_last_error ()); return 0; }
+    /* devices[0] = the current device, then the others in ordinal order */
+    int want = ctx->want_devices <= 0 ? visible : ctx->want_devices;
+    if (want > visible) want = visible;
+    if (want > VOX_CTX_MAX_DEVICES) want = VOX_CTX_MAX_DEVICES;
+    if (s->pitch != s->w * 4) want = 1;           /* shares of a frame are copied as blocks of four whole rows */
+    int n = 0;
+    ctx->devices[n++] = primary;
+    for (int d=0; d<visible && n<want; d++) if (d != primary) ctx->devices[n++] = d;
+
+    int ok = 1;
+    for (int i=0; i<n && ok; i++)
+    {
+        if (ctx->d_texture[i]) continue;
+        ok = voxgpu_set_device (ctx->devices[i]) == 0 && (ctx->d_texture[i] = voxgpu_malloc (VOX_TEXTURE_SIZE)) != NULL;
+    }
+    voxgpu_set_device (primary);
+    if (ok && !ctx->stream) ok = (ctx->stream = voxgpu_stream_create ()) != NULL;
+    if (ok && !ctx->present) ok = (ctx->present = voxgpu_present_create (s->w, s->h, 0)) != NULL;
+    if (ok && n > 1 && !ctx->multi) ok = (ctx->multi = voxgpu_multi_create (s->w, s->h, n, ctx->devices)) != NULL;
+    if (!ok) { vox_set_error ("context device setup failed: %s", voxgpu_last_error ()); return 0; }
+    ctx->ndev = n;
+    ctx->device = primary;
+    ctx->texture_dirty = 1;
     return 1;
+}
+
+int vox_context_set_devices (struct vox_rnd_ctx *pub, int n)
+{
+    struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
+    const int visible = voxgpu_device_count ();
+    if (n < 0) n = 1;
+    if (n != ctx->want_devices && ctx->device >= 0) context_device_release (ctx);
+    ctx->want_devices = n;
+    if (visible <= 0) return 0;
+    int use = n == 0 ? visible : (n < visible ? n : visible);
+    return use > VOX_CTX_MAX_DEVICES ? VOX_CTX_MAX_DEVICES : use;
 }
 
 struct vox_rnd_ctx* vox_make_context_from_surface (SDL_Surface *surface)
@@ -87,14 +150,10 @@ void vox_destroy_context (struct vox_rnd_ctx *pub)
     /* renderer.c:151-161 */
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
     if (!ctx) return;
-    if (ctx->stream) voxgpu_synchronize (ctx->stream);
-    voxgpu_present_destroy (ctx->present);
+    context_device_release (ctx);
     if (ctx->registered) voxgpu_host_unregister (pub->surface->pixels);
     if (ctx->owns_surface) vox_free_surface (pub->surface);
-    voxgpu_free (ctx->d_texture);
-    voxgpu_free (ctx->d_dir_table);
     voxgpu_host_free (ctx->dir_table);
-    voxgpu_stream_destroy (ctx->stream);
     free (ctx->texture);
     free (ctx);
 }
@@ -145,7 +204,7 @@ float vox_context_last_kernel_ms (struct vox_rnd_ctx *pub)
 {
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
     if (!ctx->timed) return -1.0f;
-    return voxgpu_present_last_ms (ctx->present);
+    return ctx->timed == 2 ? voxgpu_multi_last_ms (ctx->multi) : voxgpu_present_last_ms (ctx->present);
 }
 
 /* A camera without `describe`: evaluate its host screen2world for every pixel. */
@@ -184,25 +243,23 @@ void vox_render (struct vox_rnd_ctx *pub)
     if (!pub->scene)
     {
         /* every ray misses a NULL tree (search.c:22): the frame is all zeros */
+        vox_redraw (pub);                               /* a frame still on its way would land on top of it */
         memset (s->pixels, 0, (size_t) s->pitch * s->h);
         return;
     }
     if (!context_device_init (ctx)) return;
-    voxgpu_tree *tree = vox_tree_device_handle (pub->scene);
-    if (!tree) return;
+    if (voxgpu_get_device () != ctx->device && voxgpu_set_device (ctx->device))
+    { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
 
-    if (ctx->texture_dirty)
-    {
-        if (voxgpu_memcpy_h2d (ctx->d_texture, ctx->texture, VOX_TEXTURE_SIZE, ctx->stream) ||
-            voxgpu_synchronize (ctx->stream))
-        { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
-        ctx->texture_dirty = 0;
-    }
+    /* any node is a scene (renderer.c:297 searches inside returned leaves): the searches start there */
+    struct vox_tree_info info;
+    vox_tree_get_info (pub->scene, &info);
 
     voxgpu_camera cam;
     memset (&cam, 0, sizeof cam);
     struct vox_camera_desc desc;
-    if (pub->camera->iface->describe && pub->camera->iface->describe (pub->camera, &desc))
+    int described = pub->camera->iface->describe && pub->camera->iface->describe (pub->camera, &desc);
+    if (described)
     {
         cam.kind = desc.kind == VOX_CAMERA_DESC_DOOM ? VOXGPU_CAMERA_DOOM : VOXGPU_CAMERA_SIMPLE;
         memcpy (cam.position, desc.position, sizeof cam.position);
@@ -210,7 +267,23 @@ void vox_render (struct vox_rnd_ctx *pub)
         cam.mul = desc.mul; cam.xsub = desc.xsub; cam.ysub = desc.ysub;
         cam.sinphi = desc.sinphi; cam.cosphi = desc.cosphi; cam.k = desc.k;
     }
-    else
+    /* a frame is split over the devices when there are several, the mode is BEST and the camera is a POD */
+    const int split = ctx->multi && ctx->ndev > 1 && (ctx->quality & VOX_QUALITY_MODE_MASK) == VOX_QUALITY_BEST && described;
+    const int ndev = split ? ctx->ndev : 1;
+
+    if (ctx->texture_dirty)
+    {
+        /* (every device gets it, whether or not this frame is split) */
+        int bad = 0;
+        for (int i=0; i<ctx->ndev && !bad; i++)
+            bad = voxgpu_set_device (ctx->devices[i]) || voxgpu_memcpy_h2d (ctx->d_texture[i], ctx->texture, VOX_TEXTURE_SIZE, NULL) ||
+                  voxgpu_synchronize (NULL);
+        voxgpu_set_device (ctx->device);
+        if (bad) { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
+        ctx->texture_dirty = 0;
+    }
+
+    if (!described)
     {
         vox_dot pos;
         pub->camera->iface->get_position (pub->camera, pos);
@@ -226,15 +299,35 @@ void vox_render (struct vox_rnd_ctx *pub)
     fr.fmt.amask = s->format->Amask;
     fr.fmt.rloss = s->format->Rloss; fr.fmt.gloss = s->format->Gloss; fr.fmt.bloss = s->format->Bloss;
     fr.fmt.rshift = s->format->Rshift; fr.fmt.gshift = s->format->Gshift; fr.fmt.bshift = s->format->Bshift;
+    fr.start_node = info.node_id;
 
-    if (pub->light_manager)
+    /* the replicas of the tree (uploaded on first use, again after an edit) and of the lights
+       (renderer.c:41-49: the kernel shades through a flattened copy of the manager's M-tree) */
+    const voxgpu_tree *trees[VOX_CTX_MAX_DEVICES];
+    const voxgpu_lights *lights[VOX_CTX_MAX_DEVICES];
+    int ok = 1;
+    for (int i=0; i<ndev && ok; i++)
     {
-        /* renderer.c:41-49: the kernel shades through a flattened copy of the manager's M-tree */
-        fr.lights = vox_light_manager_device (pub->light_manager);
-        if (!fr.lights) return;
+        if (ndev > 1 && voxgpu_set_device (ctx->devices[i])) { vox_set_error ("vox_render: %s", voxgpu_last_error ()); ok = 0; break; }
+        trees[i] = vox_tree_device_handle (pub->scene);
+        lights[i] = pub->light_manager ? vox_light_manager_device (pub->light_manager) : NULL;
+        ok = trees[i] && (!pub->light_manager || lights[i]);
     }
+    if (ndev > 1) voxgpu_set_device (ctx->device);
+    if (!ok) return;
 
-    if (voxgpu_present_render (ctx->present, tree, &cam, &fr, ctx->d_texture, s->pixels, (size_t) s->pitch))
+    if (split)
+    {
+        if (ctx->present) voxgpu_present_wait (ctx->present);   /* a frame of another mode still on its way */
+        if (voxgpu_multi_render (ctx->multi, trees, &cam, &fr, (const uint8_t *const *) ctx->d_texture,
+                                 pub->light_manager ? lights : NULL, s->pixels, (size_t) s->pitch))
+        { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
+        ctx->timed = 2;
+        return;
+    }
+    if (ctx->multi) voxgpu_multi_wait (ctx->multi);
+    fr.lights = lights[0];
+    if (voxgpu_present_render (ctx->present, trees[0], &cam, &fr, ctx->d_texture[0], s->pixels, (size_t) s->pitch))
     { vox_set_error ("vox_render: %s", voxgpu_last_error ()); return; }
     ctx->timed = 1;
 }
@@ -244,6 +337,8 @@ void vox_redraw (struct vox_rnd_ctx *pub)
     /* renderer.c:321-327: after this call surface->pixels holds the frame.
        There is no window to update. */
     struct vox_rnd_ctx_full *ctx = (struct vox_rnd_ctx_full*) pub;
+    if (ctx->multi && voxgpu_multi_wait (ctx->multi))
+        vox_set_error ("vox_redraw: %s", voxgpu_last_error ());
     if (ctx->present && voxgpu_present_wait (ctx->present))
         vox_set_error ("vox_redraw: %s", voxgpu_last_error ());
 }

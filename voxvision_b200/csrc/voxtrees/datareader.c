@@ -12,11 +12,6 @@
 #include <errno.h>
 #include "store.h"
 
-static int sample_above (unsigned int sample, void *user)
-{
-    return sample > *(const unsigned int*) user;
-}
-
 struct vox_node* vox_read_raw_data_fn (const char *filename, unsigned int dim[],
                                        unsigned int samplesize, vox_sample_test test, void *user,
                                        const char **error)
@@ -75,11 +70,75 @@ done:
 #undef FAIL
 }
 
+struct range { unsigned int min; unsigned long long max; };
+
+static int sample_in_range (unsigned int sample, void *user)
+{
+    const struct range *r = user;
+    return sample >= r->min && (unsigned long long) sample < r->max;     /* modules/voxtrees.c:321-323 */
+}
+
+/* The range predicate evaluated on the device: upload, threshold, compact (libvoxgpu, volume.inl), then
+   vox_make_tree on the resulting list -- the list the host loop above would have made, in the same order. */
+static struct vox_node* read_raw_gpu (const char *filename, unsigned int dim[], unsigned int samplesize,
+                                      const struct range *r, const char **error)
+{
+#define FAIL(msg) do { if (error) *error = (msg); goto done; } while (0)
+    struct vox_node *tree = NULL;
+    unsigned char *raw = NULL;
+    float *dots = NULL;
+    size_t kept = 0;
+    FILE *f = fopen (filename, "rb");
+    if (!f) { if (error) *error = strerror (errno); return NULL; }
+    if (samplesize < 1 || samplesize > 4) FAIL ("Unsupported sample size");
+    size_t n = (size_t) dim[0] * dim[1] * dim[2];
+    struct stat sb;
+    if (fstat (fileno (f), &sb) == -1) FAIL (strerror (errno));
+    if ((off_t) (n * samplesize) != sb.st_size) FAIL ("Wrong size of dataset");      /* datareader.c:39-42 */
+    raw = malloc (n * samplesize + 1);
+    if (!raw) FAIL (strerror (errno));
+    if (fread (raw, samplesize, n, f) != n) FAIL ("Short read");
+    if (voxgpu_volume_extract (raw, dim, samplesize, r->min, r->max, vox_voxel, &dots, &kept))
+    {
+        vox_set_error ("vox_read_raw_data: %s", voxgpu_last_error ());
+        FAIL (vox_last_error ());
+    }
+    tree = vox_make_tree ((vox_dot*) dots, kept);
+    if (!tree && kept && error) *error = vox_last_error ();
+done:
+    voxgpu_host_free (dots);
+    free (raw);
+    fclose (f);
+    return tree;
+#undef FAIL
+}
+
+static struct vox_node* read_raw_range (const char *filename, unsigned int dim[], unsigned int samplesize,
+                                        struct range r, const char **error)
+{
+    const char *force = getenv ("VOXTREES_LOADER");
+    int gpu = force ? !strcmp (force, "gpu") : voxgpu_device_count () > 0;
+    if (force && strcmp (force, "gpu") && strcmp (force, "host"))
+    { if (error) *error = "VOXTREES_LOADER must be host or gpu"; return NULL; }
+    if (gpu) return read_raw_gpu (filename, dim, samplesize, &r, error);
+    return vox_read_raw_data_fn (filename, dim, samplesize, sample_in_range, &r, error);
+}
+
 struct vox_node* vox_read_raw_data_threshold (const char *filename, unsigned int dim[],
                                               unsigned int samplesize, unsigned int threshold,
                                               const char **error)
 {
-    return vox_read_raw_data_fn (filename, dim, samplesize, sample_above, &threshold, error);
+    /* sample > threshold */
+    struct range r = { threshold == 0xffffffffu ? threshold : threshold + 1, threshold == 0xffffffffu ? 0 : 1ull << 32 };
+    return read_raw_range (filename, dim, samplesize, r, error);
+}
+
+struct vox_node* vox_read_raw_data_range (const char *filename, unsigned int dim[],
+                                          unsigned int samplesize, unsigned int min, unsigned int max,
+                                          const char **error)
+{
+    struct range r = { min, max };
+    return read_raw_range (filename, dim, samplesize, r, error);
 }
 
 static int is_regular_file (const char *path)
