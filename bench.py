@@ -224,7 +224,7 @@ def algorithmic_bytes_per_frame(ds, orc_mod, sample_frames, threads):
 
 class OrbitBenchResult(C.Structure):
     _fields_ = [("seconds", C.c_double), ("checksum", C.c_ulonglong), ("frames", C.c_long), ("devices", C.c_int),
-                ("error", C.c_char * 256)]
+                ("device_ms_mean", C.c_double), ("error", C.c_char * 256)]
 
 
 class Env:
@@ -245,6 +245,10 @@ class Env:
             torch.cuda.set_device(self.local_rank)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist, self.torch = dist, torch
+            # a HOST-side barrier for the legs in which rank 0 alone drives several GPUs: a rank waiting in an NCCL
+            # collective spins in a kernel on its GPU, and rank 0's work on that GPU would be time-sliced against it
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+            self.host_pg = dist.new_group(backend="gloo")
         vv.set_device(self.local_rank)
         self.g = api.libs.gpu
         self.orbit = C.CDLL(os.path.join(api.LIB_DIR, "liborbitbench.so"))
@@ -258,6 +262,10 @@ class Env:
             self.torch.cuda.synchronize()
         else:
             self.g.voxgpu_synchronize(None)
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.host_pg)
 
     def max_over_ranks(self, x):
         if self.world == 1:
@@ -427,18 +435,26 @@ def leg_e2e(E, args, tree, poses):
             if rc:
                 raise E.vv.VoxError("orbit_bench_run: " + res.error.decode())
             secs = res.seconds
-        secs = E.max_over_ranks(secs)
+        if all_ranks:
+            secs = E.max_over_ranks(secs)
+        else:
+            E.host_barrier()            # the idle ranks wait on the host, their GPUs stay free for rank 0
         E.sync_all()
         ranks = world if all_ranks else 1
+        run.device_ms = float(res.device_ms_mean)
         return ranks * steps * nframes * RAYS_PER_FRAME / secs / 1e6, int(res.devices)
 
     out = {}
     ring, _ = run(E2E_CONTEXTS, 1, 0)
     one, _ = run(1, 1, 0)
+    one_device_ms = run.device_ms
     ada_ring, _ = run(E2E_CONTEXTS, 1, 2)
     ada_one, _ = run(1, 1, 2)
     out.update({"value": round(ring, 2), "unit": "Mrays/s", "steps": steps, "contexts_in_flight": E2E_CONTEXTS,
                 "single_context": round(one, 2),
+                "single_context_ms": {"wall_per_frame": round(RAYS_PER_FRAME / one / 1e3 * world, 4), "device_per_frame": round(one_device_ms, 4),
+                                      "what": "wall: vox_render + vox_redraw + the host's look at the frame; device: first launch of the frame to "
+                                              "its last byte in host memory (CUDA events, a separate untimed pass)"},
                 "adaptive": {"value": round(ada_ring, 2), "single_context": round(ada_one, 2),
                              "what": "the same legs in the reference's DEFAULT quality (ADAPTIVE, renderer.c:78): "
                                      "K1 root searches + the block-sequential walk, two launches per band"}})
@@ -557,6 +573,8 @@ def leg_c5(E, args):
     E.sync_all()
 
     out = None
+    if rank != 0:
+        E.host_barrier()                # rank 0's checks below use its own GPU only; wait for them on the host all the same
     if rank == 0:
         # the same frames on ONE GPU, in the same run: the base of the strong-scaling figure
         own = vv.DeviceBuffer(frame_bytes)
@@ -622,6 +640,7 @@ def leg_c5(E, args):
                             "achieved": round(bytes_per_ray * value * 1e6 / 1e9 / world, 2), "peak": peak, "unit": "GB/s per GPU",
                             "frac": round(bytes_per_ray * value * 1e6 / 1e9 / world / peak, 5),
                             "l2": "the 2.6 GB device tree does not fit the 126 MB L2: this config streams from HBM"}}
+        E.host_barrier()
     E.sync_all()
     tree.destroy()
     return out

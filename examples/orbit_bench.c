@@ -24,6 +24,8 @@ struct orbit_bench_result
     unsigned long long checksum;    /* xor of the centre pixels read: the frames were looked at */
     long frames;                    /* frames rendered in the timed passes */
     int devices;                    /* what vox_context_set_devices answered */
+    double device_ms_mean;          /* contexts == 1: mean vox_context_last_kernel_ms over one extra, untimed pass
+                                       (first launch of a frame -> last byte of it in host memory, CUDA events) */
     char error[256];
 };
 
@@ -85,6 +87,23 @@ int orbit_bench_run (struct vox_node *tree, int w, int h, int nframes, const flo
         if (pass) { out->checksum ^= acc; out->frames += nframes; }
     }
     out->seconds = now () - t0;
+    if (contexts == 1)
+    {
+        double sum = 0;
+        for (int f = 0; f < nframes; f++)
+        {
+            vox_dot pos, look;
+            vox_dot_set (pos, poses[6*f], poses[6*f+1], poses[6*f+2]);
+            vox_dot_set (look, poses[6*f+3], poses[6*f+4], poses[6*f+5]);
+            cam[0]->iface->set_property_dot (cam[0], "position", pos);
+            cam[0]->iface->look_at (cam[0], look);
+            vox_context_set_camera (ctx[0], cam[0]);
+            vox_render (ctx[0]);
+            vox_redraw (ctx[0]);
+            sum += vox_context_last_kernel_ms (ctx[0]);
+        }
+        out->device_ms_mean = sum / nframes;
+    }
     rc = 0;
 done:
     for (int i=0; i<contexts; i++)

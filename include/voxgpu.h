@@ -276,8 +276,8 @@ VOXGPU_EXPORT int voxgpu_multi_wait (voxgpu_multi *m);
 /** Slowest device's time from its launch to the arrival of its share in host memory, ms (waits). */
 VOXGPU_EXPORT float voxgpu_multi_last_ms (voxgpu_multi *m);
 
-/** Development knob: 1 = strip-interleaved tile order in the dark-tile / unmasked phase of the render
-    kernel (default), 2 = raster order.  Kept for A/B measurements; results are identical. */
+/** Development knob: 1 = strip-interleaved tile order where a launch has no screen mask (default), 2 = raster
+    order.  Kept for A/B measurements; results are identical. */
 VOXGPU_EXPORT void voxgpu_set_variant (int variant);
 /** Screen-space culling of 8x4 tiles that cannot show a voxel.  1 (default): the bounds of the tree's
     root box AND a per-launch screen mask marked from the boxes of a cut through the tree (k_mark);

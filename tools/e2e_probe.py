@@ -1,30 +1,37 @@
 #!/usr/bin/env python
-"""Where does an end-to-end frame go?  wall time per vox_render+vox_redraw vs the presenter's device time."""
-import os, sys, time
+"""One-context end-to-end time per C2 frame (vox_render + vox_redraw from C, examples/orbit_bench.c) for several band
+counts of the presenter ($VOXGPU_BANDS is read when a context is first rendered), in BEST and ADAPTIVE.
+
+    python tools/e2e_probe.py [bands ...]         default: 1 2 3 4 6 8
+"""
+import ctypes as C
+import os
+import sys
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import voxvision_b200 as vv
+from voxvision_b200 import api
 from tools import datasets as ds
-W, H, FOV = 1920, 1080, 1.2
+import bench
+
+W, H, FRAMES = 1920, 1080, 360
+orbit = C.CDLL(os.path.join(api.LIB_DIR, "liborbitbench.so"))
+orbit.orbit_bench_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                  C.c_uint, C.c_int, C.POINTER(bench.OrbitBenchResult)]
+vv.set_device(0)
 tree = vv.Tree.build(ds.volume_voxels("skull"))
-ctx = vv.Context(W, H); ctx.set_scene(tree); ctx.set_quality(vv.QUALITY_BEST)
-cam = vv.Camera("simple-camera")
-poses = [ds.orbit_pose(f) for f in range(360)]
-ds.setup_camera(cam, *poses[0], FOV, W, H); ctx.set_camera(cam)
-def loop(setcam=True, n=360):
-    dev = []
-    t0 = time.perf_counter()
-    tr = trd = 0.0
-    for f in range(n):
-        if setcam:
-            pos, look = poses[f]
-            cam.set_position(pos); cam.look_at(look); ctx.set_camera(cam)
-        a = time.perf_counter(); ctx.render(); b = time.perf_counter(); ctx.redraw(); c = time.perf_counter()
-        tr += b - a; trd += c - b
-        dev.append(ctx.kernel_ms())
-    wall = (time.perf_counter() - t0) / n * 1e3
-    return wall, tr / n * 1e3, trd / n * 1e3, float(np.mean(dev))
-loop(); loop()
-for sc in (True, False):
-    w, r, rd, d = loop(sc)
-    print(f"setcam={sc}: wall {w:.4f} ms/frame (render call {r:.4f}, redraw call {rd:.4f}), presenter device time {d:.4f} ms")
+poses = np.ascontiguousarray([list(p) + list(l) for p, l in (ds.orbit_pose(f, FRAMES) for f in range(FRAMES))], np.float32)
+for bands in [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4, 6, 8]:
+    os.environ["VOXGPU_BANDS"] = str(bands)
+    line = [f"bands {bands}:"]
+    for qname, q in (("BEST", 0), ("ADAPTIVE", 2)):
+        for contexts in (1, 6):
+            res = bench.OrbitBenchResult()
+            rc = orbit.orbit_bench_run(tree.h, W, H, FRAMES, poses.ctypes.data, 1.2, contexts, 1, q, 2, C.byref(res))
+            assert rc == 0, res.error
+            wall = res.seconds / res.frames * 1e3
+            line.append(f"{qname} x{contexts}: wall {wall:.4f} ms/frame ({W*H/wall/1e3:.0f} Mrays/s)" +
+                        (f" device {res.device_ms_mean:.4f}" if contexts == 1 else ""))
+    print(" | ".join(line), flush=True)

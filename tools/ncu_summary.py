@@ -62,7 +62,7 @@ def full(path, cmd):
     rd = list(csv.reader(io.StringIO(out[out.find('"ID"'):])))
     names, units, data = rd[0], rd[1], rd[2:]
     print(cmd)
-    traffic = []
+    traffic, insts = [], []
     for n, row in enumerate(data):
         rec = dict(zip(names, row))
         unit = dict(zip(names, units))
@@ -79,12 +79,15 @@ def full(path, cmd):
             rd_b = float(rec["dram__bytes_read.sum"].replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(unit["dram__bytes_read.sum"], 1)
             wr_b = float(rec["dram__bytes_write.sum"].replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(unit["dram__bytes_write.sum"], 1)
             traffic.append(int(rd_b + wr_b))
+            insts.append(int(float(rec["smsp__inst_executed.sum"].replace(",", ""))))
         except Exception:
             pass
     if traffic:
         with open(os.path.join(ROOT, "profiles", "k_render_traffic.json"), "w") as f:
             json.dump({"kernel": "k_render_persistent", "source": os.path.basename(path) + " (ncu --set full), see the full summary under profiles/",
-                       "dram_bytes_per_launch": int(sum(traffic) / len(traffic)), "per_launch": traffic}, f, indent=1)
+                       "dram_bytes_per_launch": int(sum(traffic) / len(traffic)), "per_launch": traffic,
+                       "warp_instructions_per_launch": int(sum(insts) / len(insts)) if insts else None,
+                       "warp_instructions": insts}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -60,7 +60,6 @@ extern "C" void voxgpu_lights_free (voxgpu_lights *l)
 
 /* ------------------------------------------------------- screen-mask buffers */
 
-#define MASK_MAX_BANDS 16
 #define MASK_CTL_WORDS (4 * MASK_MAX_BANDS)
 
 /* One frame's screen mask (see DevMask): mark[mtiles] | list[mtiles] | ctl[MASK_CTL_WORDS].
@@ -113,10 +112,11 @@ static DevMask maskbuf_band (const MaskBuf &m, int band, size_t first_tile)
    (20 B per pixel of the band: too big to keep one per slot).  Launches rotate through
    RENDER_SLOTS slots; should a slot come round again while its previous borrower is still queued or
    running on ANOTHER stream, the new stream waits for it (one event per slot), so sharing is always
-   ordered.  vox_render may be called from any thread (Manual.md:171-175): everything here is guarded by
+   ordered.  (16 slots: a slot's mask buffer is 8 B per 8x4 tile of the frame -- 8 MB for an 8K frame -- and
+   is allocated when a slot first sees a frame that size.)  vox_render may be called from any thread (Manual.md:171-175): everything here is guarded by
    the device's mutex, which is held from slot acquisition until the launch is queued and the slot's
    event recorded. */
-#define RENDER_SLOTS 64
+#define RENDER_SLOTS 16
 struct RenderSlot
 {
     cudaEvent_t ev;
@@ -426,11 +426,21 @@ static int mark_launch (const voxgpu_tree *t, const voxgpu_camera *c, int w, int
 
 /* ------------------------------------------------------------- voxgpu_render */
 
+/* The presenter's whole-frame launch (k_render_frame): the frame's mask buffer, already marked and listed for
+   the bands of `bd` */
+struct FrameBands
+{
+    DevBands bd;
+    unsigned *mbuf;
+    unsigned mtiles, epoch;
+};
+
 /* ext_mask: a screen mask the caller has already marked for this frame and this band (the presenter marks one
-   per frame and shares it between the bands); NULL: make one for this launch */
+   per frame and shares it between the bands); NULL: make one for this launch.  fb: draw the whole frame with
+   k_render_frame instead (BEST, no per-pixel outputs). */
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, const DevMask *ext_mask);
+                        voxgpu_stream s, const DevMask *ext_mask, const FrameBands *fb = NULL);
 
 extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                               const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
@@ -441,7 +451,7 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
 
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, const DevMask *ext_mask)
+                        voxgpu_stream s, const DevMask *ext_mask, const FrameBands *fb)
 {
     /* ---- every argument is checked before anything is borrowed or queued ---- */
     if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
@@ -501,6 +511,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         DevMask mk;
         memset (&mk, 0, sizeof mk);
         if (ext_mask) mk = *ext_mask;
+        else if (fb) {}
         else if (mask_usable (t, c))
         {
             const size_t mtiles = (size_t) (f->w >> 3) * (f->h >> 2);
@@ -518,7 +529,15 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         float4 *pts = (float4*) d_pts;
         const TreeRef tr = tree_ref (t);
         const unsigned start = f->start_node;
-        if (mode != 0u)
+        if (fb)
+        {
+            if (mode != 0u || hits || il_world > 1 || f->y0 != 0 || f->y1 != f->h) { fail ("voxgpu_render: a whole-frame launch draws BEST frames only"); LEAVE (-1); }
+            int grid = rd.blocks[lit ? GRID_K1_LIT : GRID_K1];
+            if (grid > blocks) grid = blocks;
+            if (lit) k_render_frame<true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, fb->mbuf, fb->mtiles, fb->epoch, fb->bd, d_tex, d_pixels, counters);
+            else     k_render_frame<false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, fb->mbuf, fb->mtiles, fb->epoch, fb->bd, d_tex, d_pixels, counters);
+        }
+        else if (mode != 0u)
         {
             /* FAST / ADAPTIVE (+ ray merge).  Launch 1: every root search of the band, pixel-parallel (K1 as for
                BEST, unlit), into the slot's scratch; launch 2: the block walk, looking those results up. */

@@ -67,6 +67,7 @@ static struct enode* enode_new (uint32_t flags)
 static struct enode* enode_stub (const struct vox_tree_store *st, uint64_t id)
 {
     struct enode *n = enode_new (st->flags[id]);
+    if (!n) return NULL;
     memcpy (n->bb_min, st->bb_min + 3*id, sizeof n->bb_min);
     memcpy (n->bb_max, st->bb_max + 3*id, sizeof n->bb_max);
     n->dots_num = st->dots_num[id];
@@ -86,6 +87,7 @@ static void realize (const struct vox_edit *e, struct enode *n)
     {
         uint32_t cap = n->dots_num > VOX_MAX_DOTS ? n->dots_num : VOX_MAX_DOTS;
         n->dots = malloc (cap * sizeof *n->dots);
+        if (!n->dots) { n->dots_num = 0; vox_set_error ("out of memory while editing a tree"); return; }
         memcpy (n->dots, st->dots + 3*st->dots_off[id], (size_t) n->dots_num * 3 * sizeof (float));
         return;
     }
@@ -258,6 +260,7 @@ static struct enode* from_pool (struct pool *pool, uint32_t idx, const vox_dot *
 {
     const struct bnode *b = pool_at (pool, idx);
     struct enode *n = enode_new (b->flags);
+    if (!n) return NULL;
     memcpy (n->bb_min, b->bb_min, sizeof n->bb_min);
     memcpy (n->bb_max, b->bb_max, sizeof n->bb_max);
     n->dots_num = b->dots_num;
@@ -266,6 +269,7 @@ static struct enode* from_pool (struct pool *pool, uint32_t idx, const vox_dot *
     {
         uint32_t cap = b->dots_num > VOX_MAX_DOTS ? b->dots_num : VOX_MAX_DOTS;
         n->dots = malloc (cap * sizeof *n->dots);
+        if (!n->dots) { n->dots_num = 0; return n; }
         for (uint32_t k=0; k<b->dots_num; k++) memcpy (n->dots[k], set[b->set_off + k], 3*sizeof (float));
         return n;
     }
@@ -280,6 +284,7 @@ static struct enode* subtree_of (vox_dot *set, size_t n, const float voxel[3])
 {
     if (!n) return NULL;
     struct pool *pool = calloc (1, sizeof *pool);
+    if (!pool) return NULL;
     uint32_t root = vox_build (pool, set, 0, n, voxel);
     struct enode *res = (root != NO_NODE && !pool->failed) ? from_pool (pool, root, (const vox_dot*) set) : NULL;
     vox_pool_free (pool);
@@ -290,9 +295,11 @@ static struct enode* subtree_of (vox_dot *set, size_t n, const float voxel[3])
 static struct vox_edit* edit_from_store (const struct vox_tree_store *st)
 {
     struct vox_edit *e = calloc (1, sizeof *e);
+    if (!e) return NULL;
     memcpy (e->voxel, st->voxel, sizeof e->voxel);
     e->st = st;
     e->root = enode_stub (st, 0);
+    if (!e->root) { free (e); return NULL; }
     return e;
 }
 
@@ -719,6 +726,7 @@ static struct vox_tree_store* editable (struct vox_node **tree_ptr, const char *
     { vox_set_error ("%s: not the root of a live tree", who); return NULL; }
     struct vox_tree_store *st = tree->store;
     if (!st->edit) st->edit = edit_from_store (st);
+    if (!st->edit) { vox_set_error ("%s: out of memory", who); return NULL; }
     return st;
 }
 
@@ -794,6 +802,7 @@ struct vox_node* vox_rebuild_tree (const struct vox_node *tree)
     struct vox_tree_store *st = tree->store;
     struct vox_edit *e = st->edit, *tmp = NULL;
     if (!e) e = tmp = edit_from_store (st);
+    if (!e) { vox_set_error ("vox_rebuild_tree: out of memory"); return NULL; }
     size_t n = e->root ? e->root->dots_num : 0;
     vox_dot *set = vox_alloc (sizeof (vox_dot) * (n ? n : 1));
     struct vox_node *res = NULL;

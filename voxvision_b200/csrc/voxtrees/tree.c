@@ -297,7 +297,10 @@ uint32_t vox_build (struct pool *pool, vox_dot *base, size_t off, size_t n, cons
 void vox_pool_free (struct pool *pool)
 {
     if (!pool) return;
-    for (uint32_t c=0; c<POOL_MAX_CHUNKS; c++) free (pool->chunk[c]);
+    /* chunks are handed out in order: nothing lives beyond the one `used` reached */
+    uint32_t last = pool->used >> POOL_SHIFT;
+    if (last >= POOL_MAX_CHUNKS) last = POOL_MAX_CHUNKS - 1;
+    for (uint32_t c=0; c<=last; c++) free (pool->chunk[c]);
     free (pool);
 }
 
