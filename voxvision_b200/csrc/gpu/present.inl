@@ -29,7 +29,6 @@ struct voxgpu_present
     int device, w, h, bands;
     uint32_t *fb;                         /* device framebuffer, w*h */
     cudaStream_t stream[PRESENT_MAX_BANDS];
-    cudaStream_t cstream[PRESENT_MAX_BANDS];  /* copy streams of the one-kernel form: each waits for its band's flag */
     cudaEvent_t done[PRESENT_MAX_BANDS];
     cudaEvent_t start;
     int in_flight;                        /* a frame has been queued and not yet waited for */
@@ -54,7 +53,6 @@ extern "C" void voxgpu_present_destroy (voxgpu_present *p)
     for (int i=0; i<p->bands; i++)
     {
         if (p->stream[i]) { cudaStreamSynchronize (p->stream[i]); cudaStreamDestroy (p->stream[i]); }
-        if (p->cstream[i]) { cudaStreamSynchronize (p->cstream[i]); cudaStreamDestroy (p->cstream[i]); }
         if (p->done[i]) cudaEventDestroy (p->done[i]);
     }
     if (p->start) cudaEventDestroy (p->start);
@@ -94,7 +92,6 @@ extern "C" voxgpu_present* voxgpu_present_create (int w, int h, int bands)
         int prio = greatest + i;            /* numerically lower = served first */
         if (prio > least) prio = least;
         if ((e = cudaStreamCreateWithPriority (&p->stream[i], cudaStreamNonBlocking, prio)) != cudaSuccess ||
-            (e = cudaStreamCreateWithFlags (&p->cstream[i], cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate (&p->done[i])) != cudaSuccess) goto bad;
     }
     return p;
@@ -105,88 +102,6 @@ bad:
 }
 
 extern "C" int voxgpu_present_bands (const voxgpu_present *p) { return p ? p->bands : 0; }
-
-/* cuStreamWaitValue32, fetched through the runtime (no link against libcuda); NULL if this driver has none */
-typedef CUresult (*wait_value_fn) (CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-static wait_value_fn wait_value (void)
-{
-    static std::once_flag once;
-    static wait_value_fn fn = NULL;
-    std::call_once (once, [] {
-        if (getenv ("VOXGPU_NO_BAND_FLAGS") && atoi (getenv ("VOXGPU_NO_BAND_FLAGS"))) return;
-        void *p = NULL;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint ("cuStreamWaitValue32", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
-            fn = (wait_value_fn) p;
-        else cudaGetLastError ();
-    });
-    return fn;
-}
-
-/* The one-kernel form of a banded frame (see k_render_frame): mark + list, ONE render kernel on stream[0], and
-   per band a copy stream that waits for the band's flag and then moves the band into the surface. */
-static int present_render_flagged (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
-                                   const uint8_t *d_tex, void *host_pixels, size_t host_pitch_bytes, int nbands)
-{
-    const int units = p->h / 4, tiles_x = p->w >> 3;
-    const size_t mtiles = (size_t) tiles_x * units;
-    wait_value_fn waitv = wait_value ();
-    CU (cudaEventRecord (p->start, p->stream[0]));
-    if (maskbuf_begin (p->mask, mtiles, p->stream[0])) return -1;
-    MarkBands mb;
-    mb.y0 = 0; mb.y1 = p->h; mb.nbands = nbands; mb.il_world = 1; mb.il_rank = 0;
-    if (mark_launch (t, c, p->w, p->h, p->mask, mb, p->stream[0])) return -1;
-    FrameBands fb;
-    memset (&fb, 0, sizeof fb);
-    fb.mbuf = p->mask.buf; fb.mtiles = (unsigned) mtiles; fb.epoch = p->mask.epoch;
-    fb.bd.n = nbands;
-    for (int b = 0; b <= nbands; b++) fb.bd.row0[b] = (int) ((long long) units * b / nbands);
-    /* bands that cannot see the tree's root box are only cleared: they go first, and cross PCIe while the others render */
-    int cull[4] = { 0, p->w, 0, p->h }, n = 0;
-    if (g_cull) voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
-    for (int pass = 0; pass < 2; pass++)
-        for (int b = 0; b < nbands; b++)
-        {
-            const bool dark = fb.bd.row0[b + 1] * 4 <= cull[2] || fb.bd.row0[b] * 4 >= cull[3];
-            if (dark == (pass == 0)) fb.bd.order[n++] = b;
-        }
-    voxgpu_frame whole = *f;
-    whole.y0 = 0; whole.y1 = p->h; whole.pitch_pixels = p->w;
-    if (render_impl (t, c, &whole, d_tex, p->fb, NULL, NULL, (voxgpu_stream) p->stream[0], NULL, &fb))
-    {
-        maskbuf_reset_lists (p->mask, p->stream[0]);
-        return -1;
-    }
-    int rc = 0, queued = 0;
-    unsigned *ctl = p->mask.buf + 2 * p->mask.tiles;
-    for (int i = 0; i < nbands; i++)
-    {
-        const int b = fb.bd.order[i];
-        const int y0 = fb.bd.row0[b] * 4, y1 = fb.bd.row0[b + 1] * 4;
-        cudaStream_t cs = p->cstream[b];
-        cudaError_t e = cudaSuccess;
-        if (waitv ((CUstream) cs, (CUdeviceptr) (ctl + 4*b + 3), (cuuint32_t) fb.epoch, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-        {
-            /* cannot wait on the flag: this band goes after the whole kernel */
-            cudaGetLastError ();
-            e = cudaEventRecord (p->marked, p->stream[0]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent (cs, p->marked, 0);
-        }
-        const uint32_t *src = p->fb + (size_t) y0 * p->w;
-        char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
-        if (e == cudaSuccess)
-            e = host_pitch_bytes == (size_t) p->w * 4
-                ? cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, cs)
-                : cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0, cudaMemcpyDeviceToHost, cs);
-        if (e != cudaSuccess && !rc) rc = fail ("voxgpu_present_render: copy to the surface failed: %s", cudaGetErrorString (e));
-        cudaEventRecord (p->done[i], cs);
-        queued++;
-    }
-    p->used_bands = queued;
-    p->in_flight = 1;
-    g_presents_in_flight++;
-    return rc;
-}
 
 extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c,
                                       const voxgpu_frame *f, const uint8_t *d_tex,
@@ -208,8 +123,6 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     if (p->in_flight && voxgpu_present_wait (p)) return -1;   /* the previous frame owns fb and the events */
     const int others = g_presents_in_flight.load ();
     const int nbands = il_world > 1 ? 1 : ((!p->fixed_bands && others > 0) ? 1 : p->bands);
-    if (nbands > 1 && (f->quality & 3u) == 0u && t && mask_usable (t, c) && wait_value ())
-        return present_render_flagged (p, t, c, f, d_tex, host_pixels, host_pitch_bytes, nbands);
     CU (cudaEventRecord (p->start, p->stream[0]));
     /* one screen mask per frame, marked on the first band's stream, shared by all bands */
     bool masked = false;

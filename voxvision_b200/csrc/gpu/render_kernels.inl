@@ -4,7 +4,6 @@
 
 #define RENDER_BLOCK 128
 #define RENDER_STRIPS 64u
-#define MASK_MAX_BANDS 16
 
 struct DevCamera
 {
@@ -154,8 +153,7 @@ struct DevMask
     const unsigned *mark;       /* NULL: no mask for this launch */
     const unsigned *list;       /* this band's marked tiles (frame tile indices) */
     unsigned *ctl;              /* this band's control words: [0] marked tiles (zeroed again by the render kernel),
-                                   [1] == epoch: a box gave no bounds, draw everything; k_render_frame also uses
-                                   [2] finished tickets of the band (zeroed again) and [3] == epoch: the band is complete */
+                                   [1] == epoch: a box gave no bounds, draw everything */
     unsigned epoch;
 };
 
@@ -338,130 +336,6 @@ k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, Dev
         {
             counters[0] = 0; counters[1] = 0;
             if (mk.mark) mk.ctl[0] = 0;                         /* for the next k_mark into this buffer */
-            __threadfence ();
-        }
-    }
-}
-
-/*
- * K1 for a WHOLE frame that leaves the device band by band (what vox_render uses for a lone context).
- * The frame is cut into horizontal bands, each of which is DMA-copied into the host surface as soon as it is
- * complete.  r01 launched one persistent kernel per band on prioritised streams, each followed by its copy;
- * but a persistent kernel fills the GPU, so the band kernels ran one after the other and the frame paid the
- * tail of every one of them (4 bands: 0.28 ms of kernels for 0.21 ms of work).  Here ONE kernel draws the
- * frame: the tickets run through the bands in `order` -- per band its marked tiles, then its groups of dark
- * tiles -- and every finished ticket is counted in its band; the warp that completes a band raises the
- * band's flag (release: pixel stores, __threadfence, count; the last one fences again and writes the
- * epoch).  The copy streams wait for the flags with cuStreamWaitValue32 (present.inl), so a band crosses
- * PCIe while the kernel is still working on the others, and the frame pays one tail.
- * Needs the frame's screen mask buffer (for the lists and for the control words); a box without bounds
- * (ctl[1] == epoch) turns every band into "all tiles, in order".
- */
-struct DevBands
-{
-    int n;
-    int order[MASK_MAX_BANDS];          /* bands in ticket order */
-    int row0[MASK_MAX_BANDS + 1];       /* band b = tile rows [row0[b], row0[b+1]) */
-};
-
-template <bool LIT>
-__global__ void __launch_bounds__(RENDER_BLOCK, VOXGPU_RENDER_MIN_BLOCKS)
-k_render_frame (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, unsigned *mbuf, unsigned mtiles, unsigned epoch, DevBands bd,
-                const unsigned char * __restrict__ tex, unsigned * __restrict__ pixels, unsigned *counters)
-{
-    __shared__ unsigned s_end[MASK_MAX_BANDS], s_marked[MASK_MAX_BANDS];
-    const int tiles_x = fr.w >> 3;
-    const int lane = threadIdx.x & 31;
-    const unsigned total_warps = gridDim.x * (RENDER_BLOCK/32);
-    const unsigned *mark = mbuf, *list = mbuf + mtiles;
-    unsigned *ctl = mbuf + 2 * (size_t) mtiles;
-    const bool masked = ctl[1] != epoch;
-    const unsigned groups_x = ((unsigned) tiles_x + 31u) >> 5;
-    VOXGPU_DECLARE_STACK (stack);
-    V3 origin; origin.x = cam.px; origin.y = cam.py; origin.z = cam.pz;
-    if (threadIdx.x == 0)
-    {
-        unsigned acc = 0;
-        for (int i = 0; i < bd.n; i++)
-        {
-            const int b = bd.order[i];
-            const unsigned rows = (unsigned) (bd.row0[b + 1] - bd.row0[b]);
-            const unsigned m = masked ? ctl[4*b] : rows * (unsigned) tiles_x;
-            s_marked[i] = m;
-            acc += m + (masked ? groups_x * rows : 0u);
-            s_end[i] = acc;
-        }
-    }
-    __syncthreads ();
-    const unsigned tickets = s_end[bd.n - 1];
-
-    for (;;)
-    {
-        unsigned ticket = 0;
-        if (lane == 0) ticket = atomicAdd (&counters[0], 1u);
-        ticket = __shfl_sync (0xffffffffu, ticket, 0);
-        if (ticket >= tickets) break;
-        int i = 0;
-        while (ticket >= s_end[i]) i++;
-        const int b = bd.order[i];
-        const unsigned first = i ? s_end[i - 1] : 0u, local = ticket - first;
-        if (local < s_marked[i])
-        {
-            const unsigned gt = masked ? list[(size_t) bd.row0[b] * tiles_x + local] : (unsigned) bd.row0[b] * (unsigned) tiles_x + local;
-            const int tx = (int) (gt % (unsigned) tiles_x), ty = (int) (gt / (unsigned) tiles_x);
-            const int sx = (tx << 3) + (lane & 7), sy = (ty << 2) + (lane >> 3);
-            const int tx0 = tx << 3, ty0 = ty << 2;
-            unsigned color = 0;
-            /* (without a mask: tiles outside the root box's screen bounds are only cleared) */
-            if (masked || !(tx0 >= fr.cx1 || tx0 + 8 <= fr.cx0 || ty0 >= fr.cy1 || ty0 + 4 <= fr.cy0))
-            {
-                const V3 dir = screen2world (cam, sx, sy, fr.w);
-                RayResult r;
-                ray_tree_warp (tr, start, origin, dir, true, stack, r);
-                if (r.leaf >= 0) color = shade<LIT> (tr, fr, tex, r.point);
-            }
-            pixels[(size_t) sy * fr.pitch + sx] = color;
-        }
-        else
-        {
-            const unsigned t = local - s_marked[i];
-            const int gx = (int) ((t % groups_x) << 5) + lane;
-            const int gy = bd.row0[b] + (int) (t / groups_x);
-            if (gx < tiles_x && mark[(size_t) gy * tiles_x + gx] != epoch)
-            {
-                #pragma unroll
-                for (int r = 0; r < 4; r++)
-                {
-                    unsigned *row = pixels + (size_t) ((gy << 2) + r) * fr.pitch + (gx << 3);
-                    if ((((size_t) row) & 15) == 0)
-                    {
-                        ((uint4*) row)[0] = make_uint4 (0u, 0u, 0u, 0u);
-                        ((uint4*) row)[1] = make_uint4 (0u, 0u, 0u, 0u);
-                    }
-                    else for (int c = 0; c < 8; c++) row[c] = 0u;
-                }
-            }
-        }
-        /* this ticket's pixels are out: count it in its band; whoever completes the band raises its flag */
-        __threadfence ();
-        __syncwarp ();
-        if (lane == 0)
-        {
-            const unsigned done = atomicAdd (ctl + 4*b + 2, 1u);
-            if (done + 1 == s_end[i] - first)
-            {
-                __threadfence ();
-                *(volatile unsigned*) (ctl + 4*b + 3) = epoch;
-            }
-        }
-    }
-    if (lane == 0)
-    {
-        const unsigned done = atomicAdd (&counters[1], 1u);
-        if (done + 1 == total_warps)
-        {
-            counters[0] = 0; counters[1] = 0;
-            for (int b = 0; b < bd.n; b++) { ctl[4*b] = 0; ctl[4*b + 2] = 0; }   /* for the next frame into this buffer */
             __threadfence ();
         }
     }

@@ -60,6 +60,7 @@ extern "C" void voxgpu_lights_free (voxgpu_lights *l)
 
 /* ------------------------------------------------------- screen-mask buffers */
 
+#define MASK_MAX_BANDS 16
 #define MASK_CTL_WORDS (4 * MASK_MAX_BANDS)
 
 /* One frame's screen mask (see DevMask): mark[mtiles] | list[mtiles] | ctl[MASK_CTL_WORDS].
@@ -426,21 +427,11 @@ static int mark_launch (const voxgpu_tree *t, const voxgpu_camera *c, int w, int
 
 /* ------------------------------------------------------------- voxgpu_render */
 
-/* The presenter's whole-frame launch (k_render_frame): the frame's mask buffer, already marked and listed for
-   the bands of `bd` */
-struct FrameBands
-{
-    DevBands bd;
-    unsigned *mbuf;
-    unsigned mtiles, epoch;
-};
-
 /* ext_mask: a screen mask the caller has already marked for this frame and this band (the presenter marks one
-   per frame and shares it between the bands); NULL: make one for this launch.  fb: draw the whole frame with
-   k_render_frame instead (BEST, no per-pixel outputs). */
+   per frame and shares it between the bands); NULL: make one for this launch */
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, const DevMask *ext_mask, const FrameBands *fb = NULL);
+                        voxgpu_stream s, const DevMask *ext_mask);
 
 extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                               const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
@@ -451,7 +442,7 @@ extern "C" int voxgpu_render (const voxgpu_tree *t, const voxgpu_camera *c, cons
 
 static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxgpu_frame *f,
                         const uint8_t *d_tex, uint32_t *d_pixels, int32_t *d_leaf, float *d_pts,
-                        voxgpu_stream s, const DevMask *ext_mask, const FrameBands *fb)
+                        voxgpu_stream s, const DevMask *ext_mask)
 {
     /* ---- every argument is checked before anything is borrowed or queued ---- */
     if (!c || !f || !d_tex || !d_pixels) return fail ("voxgpu_render: NULL argument");
@@ -511,7 +502,6 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         DevMask mk;
         memset (&mk, 0, sizeof mk);
         if (ext_mask) mk = *ext_mask;
-        else if (fb) {}
         else if (mask_usable (t, c))
         {
             const size_t mtiles = (size_t) (f->w >> 3) * (f->h >> 2);
@@ -529,15 +519,7 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         float4 *pts = (float4*) d_pts;
         const TreeRef tr = tree_ref (t);
         const unsigned start = f->start_node;
-        if (fb)
-        {
-            if (mode != 0u || hits || il_world > 1 || f->y0 != 0 || f->y1 != f->h) { fail ("voxgpu_render: a whole-frame launch draws BEST frames only"); LEAVE (-1); }
-            int grid = rd.blocks[lit ? GRID_K1_LIT : GRID_K1];
-            if (grid > blocks) grid = blocks;
-            if (lit) k_render_frame<true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, fb->mbuf, fb->mtiles, fb->epoch, fb->bd, d_tex, d_pixels, counters);
-            else     k_render_frame<false><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, fb->mbuf, fb->mtiles, fb->epoch, fb->bd, d_tex, d_pixels, counters);
-        }
-        else if (mode != 0u)
+        if (mode != 0u)
         {
             /* FAST / ADAPTIVE (+ ray merge).  Launch 1: every root search of the band, pixel-parallel (K1 as for
                BEST, unlit), into the slot's scratch; launch 2: the block walk, looking those results up. */

@@ -13,7 +13,6 @@
  * Compile with -fmad=false (see traverse.cuh for why).
  */
 #include <cuda_runtime.h>
-#include <cuda.h>          /* types of cuStreamWaitValue32 only: the entry point comes from the runtime, libcuda is not linked */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
