@@ -442,6 +442,8 @@ def leg_e2e(E, args, tree, poses):
         E.sync_all()
         ranks = world if all_ranks else 1
         run.device_ms = float(res.device_ms_mean)
+        if secs <= 0.0:                 # a rank that sat this leg out
+            return 0.0, 0
         return ranks * steps * nframes * RAYS_PER_FRAME / secs / 1e6, int(res.devices)
 
     out = {}
@@ -452,7 +454,7 @@ def leg_e2e(E, args, tree, poses):
     ada_one, _ = run(1, 1, 2)
     out.update({"value": round(ring, 2), "unit": "Mrays/s", "steps": steps, "contexts_in_flight": E2E_CONTEXTS,
                 "single_context": round(one, 2),
-                "single_context_ms": {"wall_per_frame": round(RAYS_PER_FRAME / one / 1e3 * world, 4), "device_per_frame": round(one_device_ms, 4),
+                "single_context_ms": {"wall_per_frame": round(RAYS_PER_FRAME / max(one, 1e-9) / 1e3 * world, 4), "device_per_frame": round(one_device_ms, 4),
                                       "what": "wall: vox_render + vox_redraw + the host's look at the frame; device: first launch of the frame to "
                                               "its last byte in host memory (CUDA events, a separate untimed pass)"},
                 "adaptive": {"value": round(ada_ring, 2), "single_context": round(ada_one, 2),

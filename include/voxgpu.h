@@ -279,6 +279,12 @@ VOXGPU_EXPORT float voxgpu_multi_last_ms (voxgpu_multi *m);
 /** Development knob: 1 = strip-interleaved tile order where a launch has no screen mask (default), 2 = raster
     order.  Kept for A/B measurements; results are identical. */
 VOXGPU_EXPORT void voxgpu_set_variant (int variant);
+/** Tile cost feedback: every traversed 8x4 tile of a BEST frame records the node visits of its slowest lane in a map
+    kept with the device tree; the next frame of the same geometry hands out first the marked tiles in whose 3x3
+    neighbourhood that map holds at least `heavy_min` visits (default 48; 0 = off; $VOXGPU_TILE_FEEDBACK sets the
+    start-up value).  A pure scheduling hint for frame sequences: results do not depend on it. */
+VOXGPU_EXPORT void voxgpu_set_tile_feedback (int heavy_min);
+
 /** Screen-space culling of 8x4 tiles that cannot show a voxel.  1 (default): the bounds of the tree's
     root box AND a per-launch screen mask marked from the boxes of a cut through the tree (k_mark);
     2: the root-box bounds only; 0: none ($VOXGPU_NO_CULL=1, $VOXGPU_NO_MASK=1 set the start-up value).

@@ -127,6 +127,36 @@ def test_masked_ticket_phases_leave_no_pixel_behind(gpu, skull, ds):
             assert np.array_equal(band[0], want[0][y0:y1]) and np.array_equal(band[1], want[1][y0:y1])
 
 
+def test_tile_cost_feedback_changes_nothing(gpu, golden, skull, ds):
+    """voxgpu_set_tile_feedback: the order in which a frame's tiles are handed out follows the cost the previous
+    frame recorded; pixels, leaf ids and hit points do not -- for a sequence of frames, a change of geometry in
+    between (the map is re-made), every tile heavy (threshold 1), the default, and feedback off."""
+    meta, _ = golden
+    t = gpu.Tree.build(skull)
+    ctx = gpu.Context(1920, 1080)
+    tex, fmt = ctx.texture(), ctx.pixfmt()
+    g = gpu.api.libs.gpu
+    frames = sorted(int(k) for k in meta["c2"])
+    try:
+        for thr in (1, 48, 0):
+            g.voxgpu_set_tile_feedback(thr)
+            for rep in range(2):
+                for f in frames[:4] if rep else frames:
+                    cam = ds.setup_camera(gpu.Camera(), *ds.orbit_pose(f), 1.2, 1920, 1080)
+                    pix, leaf, pts = render_device(gpu, t, cam, 1920, 1080, tex, fmt)
+                    want = meta["c2"][str(f)]
+                    assert sha(pix) == want["pix_sha"] and sha(leaf) == want["leaf_sha"] and sha(pts[leaf >= 0]) == want["hit_sha"], (thr, f)
+                cam = ds.setup_camera(gpu.Camera(), *ds.orbit_pose(77), 1.2, 640, 360)
+                small = render_device(gpu, t, cam, 640, 360, tex, fmt, want_hits=False)[0]
+                g.voxgpu_set_cull(0)
+                plain = render_device(gpu, t, cam, 640, 360, tex, fmt, want_hits=False)[0]
+                g.voxgpu_set_cull(1)
+                assert np.array_equal(small, plain)
+    finally:
+        g.voxgpu_set_tile_feedback(48)
+        g.voxgpu_set_cull(1)
+
+
 def test_render_errors_leave_the_device_usable(gpu, skull, ds):
     """Arguments are validated before anything is queued; a rejected call must not disturb later ones."""
     t = gpu.Tree.build(skull)

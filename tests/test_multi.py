@@ -98,3 +98,30 @@ def test_world_size_2_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_band_of_a_tile_row_is_the_inverse_of_the_band_cuts():
+    """The presenter cuts a frame of `units` 4-row tile rows into n bands at (units*i)//n (present.inl); k_list
+    (render_launch.inl) finds the band of tile row r as ((r+1)*n - 1)//units.  The two must agree for every
+    geometry, or a band's list would receive tiles of its neighbour."""
+    for units in list(range(1, 40)) + [135, 270, 1080, 1081]:
+        for n in range(1, min(units, 16) + 1):
+            cuts = [units * i // n for i in range(n + 1)]
+            assert cuts[0] == 0 and cuts[-1] == units
+            for r in range(units):
+                b = ((r + 1) * n - 1) // units
+                assert cuts[b] <= r < cuts[b + 1], (units, n, r, b)
+
+
+def test_interleaved_shares_partition_the_tile_rows():
+    """voxgpu_frame.interleave_*: rank k of n draws the tile rows r with r % n == k; the number of rows the
+    kernel computes for itself, (rows - k + n - 1)//n, is the size of that share, and the shares tile the frame."""
+    for rows in (1, 2, 7, 135, 270, 1080):
+        for n in (1, 2, 3, 4, 8, 16):
+            seen = []
+            for k in range(n):
+                own = (rows - k + n - 1) // n if k < rows else 0
+                share = list(range(k, rows, n))
+                assert own == len(share)
+                seen += share
+            assert sorted(seen) == list(range(rows))

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A/B of the installed libvoxgpu.so (tools/ab_build.sh swaps build-time variants in): golden parity of the
 eight C2 frames, lone-launch time, throughput with 4 frames in flight, and optionally C3 (K2) and C5 (8K frame of
-the 100 M-voxel volume, HBM-bound).  Render variants: voxgpu_set_variant values (1 = default).
+the 100 M-voxel volume, HBM-bound).  Render variants: `V[:F]` = voxgpu_set_variant (V) (1 = default) with the
+tile cost feedback threshold F (voxgpu_set_tile_feedback; 0 = off; default: the library's).
 
     python tools/ab.py [--c3] [--c5] [variant ...]        default variants: 1
 """
@@ -44,7 +45,10 @@ streams = [C.c_void_p(g.voxgpu_stream_create()) for _ in range(4)]
 tag = os.environ.get("AB_TAG", "installed")
 
 for spec in specs:
-    g.voxgpu_set_variant(int(spec))
+    v, _, fbk = spec.partition(":")
+    g.voxgpu_set_variant(int(v))
+    if fbk:
+        g.voxgpu_set_tile_feedback(int(fbk))
     ok, lone = 0, []
     for f in frames:
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
@@ -60,6 +64,13 @@ for spec in specs:
         good = good and sha(d_pix[0].download(np.uint32, (H, W))) == want["pix_sha"]
         ok += good
         lone.append(sorted(ms)[5])
+    # lone launches along the orbit, 4 degrees apart, each frame once (what bench.py's roofline times)
+    seq = []
+    for rep in range(2):
+        seq = []
+        for gc in orbit[::2]:
+            t.start(); g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix[0].ptr, None, None, None); t.stop()
+            seq.append(t.elapsed_ms())
     flight = []
     for rep in range(3):
         for st in streams[1:]:
@@ -71,7 +82,7 @@ for spec in specs:
             g.voxgpu_stream_join(streams[0], st)
         t.stop(streams[0])
         flight.append(t.elapsed_ms() / len(orbit))
-    print(f"AB {tag} render {spec}: parity {ok}/8 | lone launch {np.mean(lone):.4f} ms ({W*H/np.mean(lone)/1e3:.0f} Mrays/s) | "
+    print(f"AB {tag} render {spec}: parity {ok}/8 | lone launch, same frame again {np.mean(lone):.4f} ms | along the orbit {np.mean(seq):.4f} ms ({W*H/np.mean(seq)/1e3:.0f} Mrays/s) | "
           f"4 in flight {min(flight):.4f} ms/frame ({W*H/min(flight)/1e3:.0f} Mrays/s)", flush=True)
 g.voxgpu_set_variant(1)
 

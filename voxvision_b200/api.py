@@ -176,6 +176,7 @@ class _Libs:
         g.voxgpu_balls_device.argtypes = [_vp, _vp, _vp, sz, _vp, _vp]
         g.voxgpu_render.argtypes = [_vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, _vp, _vp, _vp]
         g.voxgpu_set_cull.argtypes = [_i]
+        g.voxgpu_set_tile_feedback.argtypes = [_i]
         g.voxgpu_set_variant.argtypes = [_i]
         g.voxgpu_set_rays_sort.argtypes = [_i]
         g.voxgpu_set_rays_refill.argtypes = [_i]

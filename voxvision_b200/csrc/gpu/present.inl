@@ -126,13 +126,19 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     CU (cudaEventRecord (p->start, p->stream[0]));
     /* one screen mask per frame, marked on the first band's stream, shared by all bands */
     bool masked = false;
+    unsigned char *cost = NULL;
     if (t && mask_usable (t, c))
     {
         const size_t mtiles = (size_t) (p->w >> 3) * (p->h >> 2);
         if (maskbuf_begin (p->mask, mtiles, p->stream[0])) return -1;
         MarkBands mb;
         mb.y0 = 0; mb.y1 = p->h; mb.nbands = nbands; mb.il_world = il_world; mb.il_rank = il_rank;
-        if (mark_launch (t, c, p->w, p->h, p->mask, mb, p->stream[0])) return -1;
+        {
+            /* (the cost map belongs to the tree: made under the device's render lock) */
+            std::lock_guard<std::mutex> guard (g_rdev[t->device].lock);
+            cost = (f->quality & 3u) == 0u && !f->start_node ? cost_map (t, p->w, p->h, p->stream[0]) : NULL;
+        }
+        if (mark_launch (t, c, p->w, p->h, p->mask, mb, p->stream[0], cost)) return -1;
         masked = true;
     }
     CU (cudaEventRecord (p->marked, p->stream[0]));
@@ -148,7 +154,7 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
         uint32_t *src = p->fb + (size_t) y0 * p->w;
         DevMask mk;
-        if (masked) mk = maskbuf_band (p->mask, i, (size_t) (y0 >> 2) * (p->w >> 3));
+        if (masked) mk = maskbuf_band (p->mask, i, (size_t) (y0 >> 2) * (p->w >> 3), cost);
         if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], masked ? &mk : NULL)) { rc = -1; break; }
         char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
         cudaError_t e;

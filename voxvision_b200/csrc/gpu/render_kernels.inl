@@ -4,6 +4,10 @@
 
 #define RENDER_BLOCK 128
 #define RENDER_STRIPS 64u
+/* tile cost feedback: node visits from which a tile counts as expensive (0 = feedback off); see DESIGN.md for the measurement */
+#ifndef VOXGPU_TILE_FEEDBACK_DEFAULT
+#define VOXGPU_TILE_FEEDBACK_DEFAULT 48
+#endif
 
 struct DevCamera
 {
@@ -152,8 +156,10 @@ struct DevMask
 {
     const unsigned *mark;       /* NULL: no mask for this launch */
     const unsigned *list;       /* this band's marked tiles (frame tile indices) */
-    unsigned *ctl;              /* this band's control words: [0] marked tiles (zeroed again by the render kernel),
-                                   [1] == epoch: a box gave no bounds, draw everything */
+    const unsigned *heavy;      /* those of them the last frame found expensive (tile cost feedback): handed out first */
+    unsigned *ctl;              /* this band's control words: [0] listed tiles, [2] heavy tiles (both zeroed again by the
+                                   render kernel), [1] == epoch: a box gave no bounds, draw everything */
+    unsigned char *cost;        /* per tile of the frame: node visits of its slowest lane, written for the next frame; or NULL */
     unsigned epoch;
 };
 
@@ -167,8 +173,10 @@ struct DevMask
  * GPU and every warp pulls tickets from a global counter until the frame is done.  The counter resets
  * itself: the last warp to leave zeroes it, so no memset precedes the launch.
  *
- * TICKET ORDER.  With a screen mask the tickets run through two phases: (M) the band's marked tiles, one
- * per ticket; (D) the band's tile rows in groups of 32 tiles per ticket, one tile per lane, where the
+ * TICKET ORDER.  With a screen mask the tickets run through the band's marked tiles, one per ticket -- (H) first
+ * those in whose 3x3 neighbourhood the previous frame of this tree and geometry met an expensive tile (tile
+ * cost feedback: every traversed tile records the node visits of its slowest lane), (M) then the others --
+ * and then (D) through the band's tile rows in groups of 32 tiles per ticket, one tile per lane, where the
  * marked tiles are skipped (done already) and the dark ones are cleared.  The r01 profile showed a lone
  * launch with its SMs busy only 75-80 % of the elapsed time: the longest tiles of a frame (60-80 node
  * visits of dependent loads and arithmetic, ~0.1 ms) were handed out wherever the raster order put them,
@@ -229,12 +237,12 @@ k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, Dev
        horizontal strips of the band, so that stores and traversal overlap for the whole kernel instead of
        coming in bursts (the empty top and bottom of a frame only store). */
     const unsigned per_strip = (ntiles + STRIPS - 1) / STRIPS;
-    unsigned n_listed = 0;
+    unsigned n_listed = 0, n_heavy = 0;
     bool masked = false;
     if (mk.mark)
     {
         masked = mk.ctl[1] != mk.epoch;
-        if (masked) n_listed = mk.ctl[0];
+        if (masked) { n_heavy = mk.ctl[2]; n_listed = n_heavy + mk.ctl[0]; }
     }
     const unsigned groups_x = ((unsigned) tiles_x + 31u) >> 5;          /* phase D: 32 tiles of a row per ticket */
     const unsigned tickets = masked ? n_listed + groups_x * (unsigned) own_rows : per_strip * STRIPS;
@@ -250,7 +258,7 @@ k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, Dev
         int tx, ty;                     /* the tile, in tiles of the whole frame */
         if (ticket < n_listed)
         {
-            const unsigned gt = mk.list[ticket];
+            const unsigned gt = ticket < n_heavy ? mk.heavy[ticket] : mk.list[ticket - n_heavy];
             tx = (int) (gt % (unsigned) tiles_x); ty = (int) (gt / (unsigned) tiles_x);
         }
         else if (masked)
@@ -320,6 +328,7 @@ k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, Dev
             if (points && r.leaf >= 0) points[pos] = make_float4 (r.point.x, r.point.y, r.point.z, 0.0f);
         }
         __syncwarp ();
+        if (mk.cost && lane == 0) mk.cost[(size_t) ty * tiles_x + tx] = (unsigned char) min (iterations, 255);
         if (trace && lane == 0)
         {
             /* development trace (voxgpu_set_trace): when and where each tile ran, per tile of the FRAME */
@@ -335,7 +344,7 @@ k_render_persistent (TreeRef tr, unsigned start, DevCamera cam, DevFrame fr, Dev
         if (done + 1 == total_warps)
         {
             counters[0] = 0; counters[1] = 0;
-            if (mk.mark) mk.ctl[0] = 0;                         /* for the next k_mark into this buffer */
+            if (mk.mark) { mk.ctl[0] = 0; mk.ctl[2] = 0; }      /* for the next k_list into this buffer */
             __threadfence ();
         }
     }

@@ -63,7 +63,7 @@ extern "C" void voxgpu_lights_free (voxgpu_lights *l)
 #define MASK_MAX_BANDS 16
 #define MASK_CTL_WORDS (4 * MASK_MAX_BANDS)
 
-/* One frame's screen mask (see DevMask): mark[mtiles] | list[mtiles] | ctl[MASK_CTL_WORDS].
+/* One frame's screen mask (see DevMask): mark[mtiles] | list[mtiles] | heavy[mtiles] | ctl[MASK_CTL_WORDS].
    Zeroed when allocated and when the epoch wraps; otherwise never cleared. */
 struct MaskBuf
 {
@@ -80,13 +80,13 @@ static int maskbuf_begin (MaskBuf &m, size_t mtiles, cudaStream_t st)
     if (m.tiles < mtiles)
     {
         if (m.buf) { CU (cudaDeviceSynchronize ()); cudaFree (m.buf); m.buf = NULL; m.tiles = 0; }
-        CU (cudaMalloc (&m.buf, (2 * mtiles + MASK_CTL_WORDS) * sizeof (unsigned)));
+        CU (cudaMalloc (&m.buf, (3 * mtiles + MASK_CTL_WORDS) * sizeof (unsigned)));
         m.tiles = mtiles; m.epoch = 0xffffffffu;    /* forces the clear below */
     }
     if (++m.epoch == 0u)
     {
         m.epoch = 1;
-        CU (cudaMemsetAsync (m.buf, 0, (2 * m.tiles + MASK_CTL_WORDS) * sizeof (unsigned), st));
+        CU (cudaMemsetAsync (m.buf, 0, (3 * m.tiles + MASK_CTL_WORDS) * sizeof (unsigned), st));
     }
     return 0;
 }
@@ -94,15 +94,16 @@ static int maskbuf_begin (MaskBuf &m, size_t mtiles, cudaStream_t st)
 /* after a failure between k_mark and the render kernel that would have consumed (and reset) the lists */
 static void maskbuf_reset_lists (MaskBuf &m, cudaStream_t st)
 {
-    if (m.buf) cudaMemsetAsync (m.buf + 2 * m.tiles, 0, MASK_CTL_WORDS * sizeof (unsigned), st);
+    if (m.buf) cudaMemsetAsync (m.buf + 3 * m.tiles, 0, MASK_CTL_WORDS * sizeof (unsigned), st);
 }
 
-static DevMask maskbuf_band (const MaskBuf &m, int band, size_t first_tile)
+static DevMask maskbuf_band (const MaskBuf &m, int band, size_t first_tile, unsigned char *cost)
 {
     DevMask k;
-    k.mark = m.buf; k.list = m.buf + m.tiles + first_tile;
-    k.ctl = m.buf + 2 * m.tiles + 4 * band;
+    k.mark = m.buf; k.list = m.buf + m.tiles + first_tile; k.heavy = m.buf + 2 * m.tiles + first_tile;
+    k.ctl = m.buf + 3 * m.tiles + 4 * band;
     k.epoch = m.epoch;
+    k.cost = cost;
     return k;
 }
 
@@ -275,7 +276,7 @@ __global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned 
         anybad |= __shfl_xor_sync (0xffffffffu, anybad, off);
     }
     if (!live) return;
-    unsigned *mark = buf, *ctl = buf + 2 * (size_t) mtiles;
+    unsigned *mark = buf, *ctl = buf + 3 * (size_t) mtiles;
     if (!anybad)
     {
         const float x0 = floorf (lox) - 2.0f, x1 = ceilf (hix) + 3.0f, y0 = floorf (loy) - 2.0f, y1 = ceilf (hiy) + 3.0f;
@@ -301,11 +302,15 @@ __global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned 
 }
 
 /* The marked tiles of every band, compacted: one warp looks at 32 tiles of one tile row (one coalesced load),
-   and appends the marked ones to the list of the row's band with ONE atomicAdd (ballot + popc ranks). */
-__global__ void k_list (unsigned *buf, unsigned mtiles, unsigned epoch, int tiles_x, MarkBands mb)
+   and appends the marked ones to the lists of the row's band with ONE atomicAdd per list (ballot + popc ranks).
+   Tile cost feedback: a marked tile goes to the band's HEAVY list if the previous frame met a tile of at least
+   `heavy_min` node visits in its 3x3 neighbourhood (which tile of a silhouette is the expensive one changes with
+   the slightest camera move; that its neighbourhood is does not). */
+__global__ void k_list (unsigned *buf, unsigned mtiles, unsigned epoch, int tiles_x, int tiles_y, MarkBands mb,
+                        const unsigned char * __restrict__ cost, unsigned heavy_min)
 {
     const unsigned *mark = buf;
-    unsigned *list = buf + mtiles, *ctl = buf + 2 * (size_t) mtiles;
+    unsigned *list = buf + mtiles, *heavy = buf + 2 * (size_t) mtiles, *ctl = buf + 3 * (size_t) mtiles;
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned groups_x = ((unsigned) tiles_x + 31u) >> 5;
@@ -315,15 +320,34 @@ __global__ void k_list (unsigned *buf, unsigned mtiles, unsigned epoch, int tile
     if (r >= units) return;
     const int ty = u0 + r, tx = (int) ((warp % groups_x) << 5) + lane;
     const bool marked = tx < tiles_x && mark[(size_t) ty * tiles_x + tx] == epoch;
-    const unsigned m = __ballot_sync (0xffffffffu, marked);
-    if (!m) return;
-    /* band b = the i with (units*i)/nbands <= r < (units*(i+1))/nbands; its list starts at its first tile */
+    bool hv = false;
+    if (marked && cost)
+    {
+        unsigned m = 0;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++)
+            {
+                const int x = tx + dx, y = ty + dy;
+                if (x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) m = max (m, (unsigned) cost[(size_t) y * tiles_x + x]);
+            }
+        hv = m >= heavy_min;
+    }
+    const unsigned mh = __ballot_sync (0xffffffffu, marked && hv), mn = __ballot_sync (0xffffffffu, marked && !hv);
+    if (!(mh | mn)) return;
+    /* band b = the i with (units*i)/nbands <= r < (units*(i+1))/nbands; its lists start at its first tile */
     const int b = mb.nbands > 1 ? (int) (((long long) (r + 1) * mb.nbands - 1) / units) : 0;
     const size_t first = (size_t) (u0 + (int) ((long long) units * b / mb.nbands)) * tiles_x;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd (ctl + 4*b, (unsigned) __popc (m));
-    base = __shfl_sync (0xffffffffu, base, 0);
-    if (marked) list[first + base + __popc (m & ((1u << lane) - 1u))] = (unsigned) (ty * tiles_x + tx);
+    unsigned base_n = 0, base_h = 0;
+    if (lane == 0)
+    {
+        if (mn) base_n = atomicAdd (ctl + 4*b, (unsigned) __popc (mn));
+        if (mh) base_h = atomicAdd (ctl + 4*b + 2, (unsigned) __popc (mh));
+    }
+    base_n = __shfl_sync (0xffffffffu, base_n, 0);
+    base_h = __shfl_sync (0xffffffffu, base_h, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (marked && !hv) list[first + base_n + __popc (mn & below)] = (unsigned) (ty * tiles_x + tx);
+    if (marked && hv) heavy[first + base_h + __popc (mh & below)] = (unsigned) (ty * tiles_x + tx);
 }
 
 /*
@@ -411,15 +435,34 @@ static DevCamera dev_camera (const voxgpu_camera *c)
     return dc;
 }
 
-/* queue k_mark for the rows `mb` of a w x h frame into `m` (maskbuf_begin has been called) */
-static int mark_launch (const voxgpu_tree *t, const voxgpu_camera *c, int w, int h, const MaskBuf &m, const MarkBands &mb, cudaStream_t st)
+/* Tile cost feedback: the cost map of (tree, frame geometry), made on first use.  Call with the device's render
+   lock held.  NULL: feedback is off, or no memory for it (it is only a hint). */
+static int g_feedback = getenv ("VOXGPU_TILE_FEEDBACK") ? atoi (getenv ("VOXGPU_TILE_FEEDBACK")) : VOXGPU_TILE_FEEDBACK_DEFAULT;
+extern "C" void voxgpu_set_tile_feedback (int heavy_min) { g_feedback = heavy_min < 0 ? 0 : (heavy_min > 255 ? 255 : heavy_min); }
+
+static unsigned char* cost_map (const voxgpu_tree *ct, int w, int h, cudaStream_t st)
+{
+    if (!g_feedback) return NULL;
+    voxgpu_tree *t = (voxgpu_tree*) ct;
+    const int tx = w >> 3, ty = h >> 2;
+    if (t->cost && t->cost_tiles_x == tx && t->cost_tiles_y == ty) return t->cost;
+    if (t->cost) { if (cudaDeviceSynchronize () != cudaSuccess) return NULL; cudaFree (t->cost); t->cost = NULL; }
+    if (cudaMalloc (&t->cost, (size_t) tx * ty) != cudaSuccess) { cudaGetLastError (); t->cost = NULL; return NULL; }
+    if (cudaMemsetAsync (t->cost, 0, (size_t) tx * ty, st) != cudaSuccess) { cudaFree (t->cost); t->cost = NULL; return NULL; }
+    t->cost_tiles_x = tx; t->cost_tiles_y = ty;
+    return t->cost;
+}
+
+/* queue k_mark + k_list for the rows `mb` of a w x h frame into `m` (maskbuf_begin has been called) */
+static int mark_launch (const voxgpu_tree *t, const voxgpu_camera *c, int w, int h, const MaskBuf &m, const MarkBands &mb, cudaStream_t st,
+                        const unsigned char *cost)
 {
     k_mark<<<(t->n_cut * 8 + 127) / 128, 128, 0, st>>> (tree_ref (t), t->cut, t->n_cut, dev_camera (c), w, h, m.buf,
                                                        (unsigned) m.tiles, m.epoch, mb);
     const int il = mb.il_world > 1 ? mb.il_world : 1;
     const unsigned rows = (unsigned) ((((mb.y1 - mb.y0) >> 2) + il - 1) / il);
     const unsigned warps = rows * ((unsigned) ((w >> 3) + 31) >> 5);
-    k_list<<<(warps + 3) / 4, 128, 0, st>>> (m.buf, (unsigned) m.tiles, m.epoch, w >> 3, mb);
+    k_list<<<(warps + 3) / 4, 128, 0, st>>> (m.buf, (unsigned) m.tiles, m.epoch, w >> 3, h >> 2, mb, cost, (unsigned) g_feedback);
     g_launches += 2;
     CU (cudaGetLastError ());
     return 0;
@@ -508,9 +551,10 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
             if (maskbuf_begin (sl.mask, mtiles, st)) LEAVE (-1);
             MarkBands mb;
             mb.y0 = f->y0; mb.y1 = f->y1; mb.nbands = 1; mb.il_world = il_world; mb.il_rank = il_rank;
-            if (mark_launch (t, c, f->w, f->h, sl.mask, mb, st)) LEAVE (-1);
+            unsigned char *cost = mode == 0u && !f->start_node ? cost_map (t, f->w, f->h, st) : NULL;
+            if (mark_launch (t, c, f->w, f->h, sl.mask, mb, st, cost)) LEAVE (-1);
             marked_here = true;
-            mk = maskbuf_band (sl.mask, 0, (size_t) (f->y0 >> 2) * (f->w >> 3));
+            mk = maskbuf_band (sl.mask, 0, (size_t) (f->y0 >> 2) * (f->w >> 3), cost);
         }
 
         const int ntiles = (df.w >> 3) * (df.rows >> 2);

@@ -16,6 +16,11 @@ struct voxgpu_tree
        above it, so that every voxel lies in the box of exactly one node of the cut */
     unsigned *cut;
     unsigned n_cut, cut_level;
+    /* tile cost feedback (render_launch.inl): node visits of the slowest lane of every 8x4 tile in the last BEST
+       frame of this geometry, a hint for the ticket order of the next one; made on first use, under the
+       device's render lock */
+    unsigned char *cost;
+    int cost_tiles_x, cost_tiles_y;
 };
 #define VOXGPU_CUT_MAX 131072u
 
@@ -146,7 +151,7 @@ extern "C" void voxgpu_tree_free (voxgpu_tree *t)
     int cur = -1;
     cudaGetDevice (&cur);
     if (cur != t->device) cudaSetDevice (t->device);
-    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut);
+    cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut); cudaFree (t->cost);
     if (cur != t->device && cur >= 0) cudaSetDevice (cur);
     free (t);
 }
