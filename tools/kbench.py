@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Kernel A/B harness: render the eight golden C2 frames, check them against the golden digests, and print
-CUDA-event times of LONE launches (the figure bench.py's roofline is computed from) for each heavy-tile
-threshold given (voxgpu_set_heavy_threshold; 0 = no heavy class).
+CUDA-event times of LONE launches (the figure bench.py's roofline is computed from) for each tile cost feedback
+threshold given (voxgpu_set_tile_feedback; 0 = feedback off).
 
-    python tools/kbench.py [threshold ...]           default: 0
+    python tools/kbench.py [threshold ...]           default: the library's
     KBENCH_CULL=0|1|2                                voxgpu_set_cull for all runs (default 1)
 """
 import ctypes as C
@@ -22,7 +22,7 @@ from tools import datasets as ds
 W, H = 1920, 1080
 sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 gold = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "golden.json")))
-thresholds = [int(a) for a in sys.argv[1:]] or [0]
+thresholds = [int(a) for a in sys.argv[1:]] or [-1]
 g = api.libs.gpu
 g.voxgpu_set_cull(int(os.environ.get("KBENCH_CULL", "1")))
 tree = vv.Tree.build(ds.volume_voxels("skull"))
@@ -47,6 +47,8 @@ def timed(gc, target, reps=15):
 
 
 for thr in thresholds:
+    if thr >= 0:
+        g.voxgpu_set_tile_feedback(thr)
     tot = 0.0
     for f in frames:
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
@@ -60,7 +62,7 @@ for thr in thresholds:
         md = timed(gc, d_pix.ptr)
         ok.append(sha(d_pix.download(np.uint32, (H, W))) == want["pix_sha"])
         tot += md[len(md) // 2]
-        print(f"heavy_t {thr:3d} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
+        print(f"feedback {thr:3d} frame {f:3d} parity {'OK' if all(ok) else ok} hits {int(m.sum())} "
               f"lone launch min {md[0]:.4f} med {md[len(md)//2]:.4f} max {md[-1]:.4f} ms", flush=True)
     n = len(frames)
-    print(f"heavy_t {thr}: mean of per-frame medians {tot/n:.4f} ms -> {W*H/(tot/n)/1e3:.0f} Mrays/s", flush=True)
+    print(f"feedback {thr}: mean of per-frame medians {tot/n:.4f} ms -> {W*H/(tot/n)/1e3:.0f} Mrays/s", flush=True)

@@ -71,7 +71,8 @@ def box_counts(gc):
     return cnt.reshape(-1), len(cut)
 
 
-for thr in [int(a) for a in sys.argv[1:]] or [0]:
+for thr in [int(a) for a in sys.argv[1:]] or [48]:
+    g.voxgpu_set_tile_feedback(thr)
     for f in (0, 90):
         ds.setup_camera(cam, *ds.orbit_pose(f), 1.2, W, H)
         gc = cam.gpu_camera()
@@ -89,7 +90,7 @@ for thr in [int(a) for a in sys.argv[1:]] or [0]:
         dur = (t1 - t0) / 1e3
         total = t1.max() / 1e3
         it = (tr[ran, 2] & np.uint64(0xffffffff)).astype(np.int64)
-        print(f"heavy_t {thr} frame {f}: traversal span {total:.1f} us, traversed tiles {int(ran.sum())} of {ntiles}, tile us: median {np.median(dur):.2f} "
+        print(f"feedback {thr} frame {f}: traversal span {total:.1f} us, traversed tiles {int(ran.sum())} of {ntiles}, tile us: median {np.median(dur):.2f} "
               f"p90 {np.percentile(dur, 90):.1f} p99 {np.percentile(dur, 99):.1f} max {dur.max():.1f}; sum {dur.sum()/1e3:.1f} ms")
         edges = np.linspace(0, t1.max(), 41)
         busy = [np.clip(np.minimum(t1, b) - np.maximum(t0, a), 0, None).sum() / (b - a) for a, b in zip(edges[:-1], edges[1:])]
@@ -99,7 +100,7 @@ for thr in [int(a) for a in sys.argv[1:]] or [0]:
         idx = np.flatnonzero(ran)
         for i in late:
             print(f"   late tile (x {idx[i] % TX}, y {idx[i] // TX}): start {t0[i]/1e3:.1f} end {t1[i]/1e3:.1f} us dur {dur[i]:.1f} iters {it[i]}")
-        if thr == 0:
+        if thr == 48:
             cnt, ncut = box_counts(gc)
             c = cnt[ran]
             print(f"   cut boxes per traversed tile ({ncut} boxes): median {int(np.median(c))} p90 {int(np.percentile(c, 90))} p99 {int(np.percentile(c, 99))} max {c.max()}; "
