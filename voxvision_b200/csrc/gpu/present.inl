@@ -143,19 +143,40 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     }
     CU (cudaEventRecord (p->marked, p->stream[0]));
     int rc = 0, queued = 0;
-    for (int i=0; i<nbands && !rc; i++)
+    /* Band k of the frame is queued on the stream of its RANK: the bands with the fewest rows inside the root
+       box's screen bounds go first (highest priority) -- they are cleared rather than traversed, done at once,
+       and cross PCIe while the others render -- so that what is left exposed at the end is the copy of one band
+       and not the kernel of a nearly empty one behind it ($VOXGPU_BAND_ORDER=0: top to bottom). */
+    int order[PRESENT_MAX_BANDS];
+    for (int i=0; i<nbands; i++) order[i] = i;
+    static const int by_weight = !(getenv ("VOXGPU_BAND_ORDER") && !atoi (getenv ("VOXGPU_BAND_ORDER")));
+    if (by_weight && nbands > 1 && t && g_cull)
     {
+        int cull[4] = { 0, p->w, 0, p->h }, weight[PRESENT_MAX_BANDS];
+        voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
+        for (int i=0; i<nbands; i++)
+        {
+            const int y0 = (int) ((long long) units * i / nbands) * 4, y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
+            const int lo = y0 > cull[2] ? y0 : cull[2], hi = y1 < cull[3] ? y1 : cull[3];
+            weight[i] = hi > lo ? hi - lo : 0;
+        }
+        for (int i=1; i<nbands; i++)            /* insertion sort, stable: equal weights stay top to bottom */
+            for (int j=i; j>0 && weight[order[j]] < weight[order[j-1]]; j--) { const int x = order[j]; order[j] = order[j-1]; order[j-1] = x; }
+    }
+    for (int k=0; k<nbands && !rc; k++)
+    {
+        const int i = order[k];                 /* band i of the frame, on the stream / events of rank k */
         /* the later bands wait for the mask (and with it the start mark: the elapsed time covers all of them) */
-        if (i && cudaStreamWaitEvent (p->stream[i], p->marked, 0) != cudaSuccess) { rc = fail ("voxgpu_present_render: cudaStreamWaitEvent failed"); break; }
+        if (k && cudaStreamWaitEvent (p->stream[k], p->marked, 0) != cudaSuccess) { rc = fail ("voxgpu_present_render: cudaStreamWaitEvent failed"); break; }
         const int y0 = (int) ((long long) units * i / nbands) * 4;
         const int y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
-        if (y1 <= y0) { cudaEventRecord (p->done[i], p->stream[i]); queued++; continue; }
+        if (y1 <= y0) { cudaEventRecord (p->done[k], p->stream[k]); queued++; continue; }
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
         uint32_t *src = p->fb + (size_t) y0 * p->w;
         DevMask mk;
         if (masked) mk = maskbuf_band (p->mask, i, (size_t) (y0 >> 2) * (p->w >> 3), cost);
-        if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[i], masked ? &mk : NULL)) { rc = -1; break; }
+        if (render_impl (t, c, &band, d_tex, src, NULL, NULL, (voxgpu_stream) p->stream[k], masked ? &mk : NULL)) { rc = -1; break; }
         char *dst = (char*) host_pixels + (size_t) y0 * host_pitch_bytes;
         cudaError_t e;
         if (il_world > 1)
@@ -164,15 +185,15 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
             const int own = il_rank < units ? (units - il_rank + il_world - 1) / il_world : 0;
             const size_t row4 = (size_t) p->w * 16;
             e = own ? cudaMemcpy2DAsync (dst + (size_t) il_rank * row4, row4 * il_world, (const char*) src + (size_t) il_rank * row4,
-                                         row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[i]) : cudaSuccess;
+                                         row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[k]) : cudaSuccess;
         }
         else if (host_pitch_bytes == (size_t) p->w * 4)
-            e = cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[i]);
+            e = cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[k]);
         else
             e = cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0,
-                                   cudaMemcpyDeviceToHost, p->stream[i]);
+                                   cudaMemcpyDeviceToHost, p->stream[k]);
         if (e != cudaSuccess) { rc = fail ("voxgpu_present_render: copy to the surface failed: %s", cudaGetErrorString (e)); }
-        cudaEventRecord (p->done[i], p->stream[i]);
+        cudaEventRecord (p->done[k], p->stream[k]);
         queued++;
     }
     if (rc && masked && queued < nbands) maskbuf_reset_lists (p->mask, p->stream[0]);   /* lists nobody will consume */
