@@ -246,6 +246,18 @@ def test_raw_volume_range_loader(vv, tmp_path, monkeypatch):
         vv.Tree.from_raw_file(path, dim, 2, sample_range=(0, 5))
 
 
+def test_set_devices_contract_without_a_device(vv):
+    """vox_context_set_devices answers how many devices will draw: 0 when there is none; the context stays usable."""
+    if vv.gpu_available():
+        pytest.skip("a CUDA device is present")
+    ctx = vv.Context(64, 16)
+    for n in (0, 1, 8, -3):
+        assert ctx.set_devices(n) == 0
+    ctx.set_scene(vv.Tree.build(CROSS)); ctx.set_camera(vv.Camera())
+    ctx.render()
+    assert "no CUDA device" in vv.last_error()
+
+
 def test_no_gpu_means_loud_failure(vv):
     """The product has no CPU search path: without a device every query raises."""
     if vv.gpu_available():
