@@ -240,7 +240,10 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
  * horizontal bands (0 = default, or $VOXGPU_BANDS), each on its own prioritised
  * stream and each followed by a DMA copy into `host_pixels`, which must be
  * page-locked (voxgpu_host_alloc / voxgpu_host_register).  _render returns as
- * soon as the work is queued; _wait returns once every band has landed.
+ * soon as the work is queued (and the margin of the surface outside the root
+ * box's screen bounds, which no voxel can reach, is zeroed by the calling
+ * thread: only the visible rectangle is rendered and copied); _wait returns
+ * once every band has landed.
  * frame->y0/y1/pitch_pixels are ignored (the whole frame is drawn) -- or, with
  * frame->interleave_world = N > 1, this device's share of a frame that N devices
  * split: the tile rows r with r % N == interleave_rank, one launch, one strided
@@ -255,6 +258,9 @@ VOXGPU_EXPORT int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t
 VOXGPU_EXPORT int voxgpu_present_wait (voxgpu_present *p);
 /** Device time from the first band's launch to the last band's arrival in host memory, ms (waits). */
 VOXGPU_EXPORT float voxgpu_present_last_ms (voxgpu_present *p);
+/** Bytes of frames all presenters of this process have queued for device-to-host copies so far (only the visible
+    rectangle of a frame crosses PCIe; the margin is zeroed on the host). */
+VOXGPU_EXPORT unsigned long long voxgpu_present_bytes_copied (void);
 /** The device framebuffer the last frame was rendered into (w*h pixels, pitch w). */
 VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p);
 

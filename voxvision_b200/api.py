@@ -188,6 +188,7 @@ class _Libs:
         g.voxgpu_present_render.argtypes = [_vp, _vp, C.POINTER(GpuCamera), C.POINTER(GpuFrame), _vp, _vp, sz]
         g.voxgpu_present_wait.argtypes = [_vp]
         g.voxgpu_launch_count.restype = C.c_ulonglong
+        g.voxgpu_present_bytes_copied.restype = C.c_ulonglong
         g.voxgpu_timer_create.restype = _vp
         g.voxgpu_timer_destroy.argtypes = [_vp]
         g.voxgpu_timer_start.argtypes = [_vp, _vp]

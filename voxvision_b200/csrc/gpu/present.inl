@@ -43,6 +43,9 @@ struct voxgpu_present
    frame's kernels; splitting such frames into bands only adds launches (measured on C2:
    6 contexts x 1 band 12.0 Grays/s, x 2 bands 11.4; one context: 4 bands 6.0, 1 band 5.0). */
 static std::atomic<int> g_presents_in_flight (0);
+/* bytes of frames queued for the copy engines by all presenters of the process (bench.py's e2e.d2h_bytes_per_step) */
+static std::atomic<unsigned long long> g_present_bytes (0);
+extern "C" unsigned long long voxgpu_present_bytes_copied (void) { return g_present_bytes.load (); }
 
 extern "C" void voxgpu_present_destroy (voxgpu_present *p)
 {
@@ -103,6 +106,35 @@ bad:
 
 extern "C" int voxgpu_present_bands (const voxgpu_present *p) { return p ? p->bands : 0; }
 
+/* Zero every pixel of a w x h surface outside [x0,x1) x [y0,y1) (an empty rectangle: the whole surface).  A
+   memset of several MB is bound by one core's store bandwidth, so a few threads share the rows (the num_threads
+   clause, not $OMP_NUM_THREADS, which launchers like torchrun set to 1). */
+static void host_clear_margin (void *pixels, size_t pitch, int w, int h, int x0, int x1, int y0, int y1)
+{
+    static const int threads = [] {
+        if (getenv ("VOXGPU_CLEAR_THREADS")) return atoi (getenv ("VOXGPU_CLEAR_THREADS"));
+        /* up to 4, but leave the box to its other GPUs' processes: half of the cores, shared by the visible devices */
+        int gpus = 1;
+        if (cudaGetDeviceCount (&gpus) != cudaSuccess || gpus < 1) { cudaGetLastError (); gpus = 1; }
+        const int n = omp_get_num_procs () / (2 * gpus);
+        return n < 1 ? 1 : (n > 4 ? 4 : n);
+    } ();
+    char *base = (char*) pixels;
+    if (x1 <= x0 || y1 <= y0) { x0 = x1 = 0; y0 = y1 = 0; }
+    const size_t left = (size_t) x0 * 4, right_off = (size_t) x1 * 4, right = (size_t) (w - x1) * 4, row = (size_t) w * 4;
+    #pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1) if (threads > 1)
+    for (int y = 0; y < h; y++)
+    {
+        char *r = base + (size_t) y * pitch;
+        if (y < y0 || y >= y1) memset (r, 0, row);
+        else
+        {
+            if (left) memset (r, 0, left);
+            if (right) memset (r + right_off, 0, right);
+        }
+    }
+}
+
 extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c,
                                       const voxgpu_frame *f, const uint8_t *d_tex,
                                       void *host_pixels, size_t host_pitch_bytes)
@@ -119,11 +151,40 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     if (il_world > 1 && host_pitch_bytes != (size_t) p->w * 4)
         return fail ("voxgpu_present_render: a share of an interleaved frame needs pitch == 4*w");
 
-    const int units = p->h / 4;             /* bands are multiples of 4 rows (renderer.c:97-100) */
     if (p->in_flight && voxgpu_present_wait (p)) return -1;   /* the previous frame owns fb and the events */
     const int others = g_presents_in_flight.load ();
-    const int nbands = il_world > 1 ? 1 : ((!p->fixed_bands && others > 0) ? 1 : p->bands);
+    int nbands = il_world > 1 ? 1 : ((!p->fixed_bands && others > 0) ? 1 : p->bands);
+
+    /* THE VISIBLE RECTANGLE.  Pixels outside the root box's screen bounds (voxgpu_screen_bounds: conservative,
+       host arithmetic) are zero whatever the tree holds.  They are neither drawn nor sent over PCIe: the device
+       renders and copies the tile-aligned rectangle [vx0,vx1) x [vy0,vy1) only, and the calling thread (with a few
+       helpers) zeroes the margin of the surface while the GPU works -- the reference clears its squares on the
+       host every frame too (renderer.c:324).  On a C2 frame the rectangle holds half of the pixels, and the PCIe
+       link is what bounds vox_render + vox_redraw.  ($VOXGPU_HOST_CLEAR=0: the whole frame comes from the device.) */
+    int vx0 = 0, vx1 = p->w, vy0 = 0, vy1 = p->h;
+    static const int host_clear = !(getenv ("VOXGPU_HOST_CLEAR") && !atoi (getenv ("VOXGPU_HOST_CLEAR")));
+    if (host_clear && t && g_cull)
+    {
+        int cull[4] = { 0, p->w, 0, p->h };
+        voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
+        vx0 = cull[0] & ~7; vx1 = (cull[1] + 7) & ~7; vy0 = cull[2] & ~3; vy1 = (cull[3] + 3) & ~3;
+        if (vx1 > p->w) vx1 = p->w;
+        if (vy1 > p->h) vy1 = p->h;
+        /* one GPU's share of a split frame is copied in blocks of four whole rows: only the rows are cut, and the
+           caller of all shares (voxgpu_multi_render) zeroes the margin once */
+        if (il_world > 1) { vx0 = 0; vx1 = p->w; }
+    }
+    const bool nothing = vx1 <= vx0 || vy1 <= vy0;
+    const int v_units = nothing ? 0 : (vy1 - vy0) / 4, v_u0 = vy0 / 4;
+    if (nbands > v_units) nbands = v_units > 0 ? v_units : 1;
     CU (cudaEventRecord (p->start, p->stream[0]));
+    if (nothing)
+    {
+        /* the camera cannot see the tree at all: the frame is the margin */
+        if (il_world == 1) host_clear_margin (host_pixels, host_pitch_bytes, p->w, p->h, 0, 0, 0, 0);
+        p->used_bands = 0;
+        return 0;
+    }
     /* one screen mask per frame, marked on the first band's stream, shared by all bands */
     bool masked = false;
     unsigned char *cost = NULL;
@@ -132,7 +193,7 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         const size_t mtiles = (size_t) (p->w >> 3) * (p->h >> 2);
         if (maskbuf_begin (p->mask, mtiles, p->stream[0])) return -1;
         MarkBands mb;
-        mb.y0 = 0; mb.y1 = p->h; mb.nbands = nbands; mb.il_world = il_world; mb.il_rank = il_rank;
+        mb.y0 = vy0; mb.y1 = vy1; mb.nbands = nbands; mb.il_world = il_world; mb.il_rank = il_rank;
         {
             /* (the cost map belongs to the tree: made under the device's render lock) */
             std::lock_guard<std::mutex> guard (g_rdev[t->device].lock);
@@ -143,10 +204,11 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     }
     CU (cudaEventRecord (p->marked, p->stream[0]));
     int rc = 0, queued = 0;
-    /* Band k of the frame is queued on the stream of its RANK: the bands with the fewest rows inside the root
-       box's screen bounds go first (highest priority) -- they are cleared rather than traversed, done at once,
-       and cross PCIe while the others render -- so that what is left exposed at the end is the copy of one band
-       and not the kernel of a nearly empty one behind it ($VOXGPU_BAND_ORDER=0: top to bottom). */
+    /* Band k of the rectangle is queued on the stream of its RANK.  When the whole frame comes from the device
+       (no host clearing) the bands with the fewest rows inside the root box's screen bounds go first (highest
+       priority): they are cleared rather than traversed, done at once, and cross PCIe while the others render, so
+       that what is left exposed at the end is the copy of one band and not the kernel of a nearly empty one
+       behind it ($VOXGPU_BAND_ORDER=0: top to bottom).  Inside the visible rectangle all rows count the same. */
     int order[PRESENT_MAX_BANDS];
     for (int i=0; i<nbands; i++) order[i] = i;
     static const int by_weight = !(getenv ("VOXGPU_BAND_ORDER") && !atoi (getenv ("VOXGPU_BAND_ORDER")));
@@ -156,7 +218,7 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
         for (int i=0; i<nbands; i++)
         {
-            const int y0 = (int) ((long long) units * i / nbands) * 4, y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
+            const int y0 = (v_u0 + (int) ((long long) v_units * i / nbands)) * 4, y1 = (v_u0 + (int) ((long long) v_units * (i + 1) / nbands)) * 4;
             const int lo = y0 > cull[2] ? y0 : cull[2], hi = y1 < cull[3] ? y1 : cull[3];
             weight[i] = hi > lo ? hi - lo : 0;
         }
@@ -168,8 +230,8 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         const int i = order[k];                 /* band i of the frame, on the stream / events of rank k */
         /* the later bands wait for the mask (and with it the start mark: the elapsed time covers all of them) */
         if (k && cudaStreamWaitEvent (p->stream[k], p->marked, 0) != cudaSuccess) { rc = fail ("voxgpu_present_render: cudaStreamWaitEvent failed"); break; }
-        const int y0 = (int) ((long long) units * i / nbands) * 4;
-        const int y1 = (int) ((long long) units * (i + 1) / nbands) * 4;
+        const int y0 = (v_u0 + (int) ((long long) v_units * i / nbands)) * 4;
+        const int y1 = (v_u0 + (int) ((long long) v_units * (i + 1) / nbands)) * 4;
         if (y1 <= y0) { cudaEventRecord (p->done[k], p->stream[k]); queued++; continue; }
         voxgpu_frame band = *f;
         band.y0 = y0; band.y1 = y1; band.pitch_pixels = p->w;
@@ -181,22 +243,28 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         cudaError_t e;
         if (il_world > 1)
         {
-            /* this GPU's share: tile rows rank, rank + world, ...  Four rows are contiguous on both sides */
-            const int own = il_rank < units ? (units - il_rank + il_world - 1) / il_world : 0;
+            /* this GPU's share: tile rows rank, rank + world, ... of the band.  Four rows are contiguous on both sides */
+            const int b_units = (y1 - y0) / 4;
+            const int own = il_rank < b_units ? (b_units - il_rank + il_world - 1) / il_world : 0;
             const size_t row4 = (size_t) p->w * 16;
             e = own ? cudaMemcpy2DAsync (dst + (size_t) il_rank * row4, row4 * il_world, (const char*) src + (size_t) il_rank * row4,
                                          row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[k]) : cudaSuccess;
         }
-        else if (host_pitch_bytes == (size_t) p->w * 4)
+        else if (host_pitch_bytes == (size_t) p->w * 4 && vx0 == 0 && vx1 == p->w)
             e = cudaMemcpyAsync (dst, src, (size_t) (y1 - y0) * p->w * 4, cudaMemcpyDeviceToHost, p->stream[k]);
-        else
-            e = cudaMemcpy2DAsync (dst, host_pitch_bytes, src, (size_t) p->w * 4, (size_t) p->w * 4, y1 - y0,
+        else        /* the columns of the visible rectangle only */
+            e = cudaMemcpy2DAsync (dst + (size_t) vx0 * 4, host_pitch_bytes, src + vx0, (size_t) p->w * 4, (size_t) (vx1 - vx0) * 4, y1 - y0,
                                    cudaMemcpyDeviceToHost, p->stream[k]);
         if (e != cudaSuccess) { rc = fail ("voxgpu_present_render: copy to the surface failed: %s", cudaGetErrorString (e)); }
+        else g_present_bytes += il_world > 1 ? (unsigned long long) p->w * 16 * (il_rank < (y1 - y0) / 4 ? ((y1 - y0) / 4 - il_rank + il_world - 1) / il_world : 0)
+                                             : (unsigned long long) (vx1 - vx0) * 4 * (y1 - y0);
         cudaEventRecord (p->done[k], p->stream[k]);
         queued++;
     }
     if (rc && masked && queued < nbands) maskbuf_reset_lists (p->mask, p->stream[0]);   /* lists nobody will consume */
+    /* the margin, while the device works on the rectangle */
+    if (il_world == 1 && (vx0 > 0 || vx1 < p->w || vy0 > 0 || vy1 < p->h))
+        host_clear_margin (host_pixels, host_pitch_bytes, p->w, p->h, vx0, vx1, vy0, vy1);
     p->used_bands = queued;
     if (queued)
     {
@@ -397,6 +465,20 @@ extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *
         j.tree = trees[i]; j.d_tex = d_tex[i]; j.lights = lights ? lights[i] : NULL;
         j.cam = *c; j.frame = *f; j.host_pixels = host_pixels; j.pitch = host_pitch_bytes;
         multi_post (&mu->wk[i], seq);
+    }
+    /* the rows no device draws (outside the root box's screen bounds: see voxgpu_present_render), while the workers queue */
+    {
+        static const int host_clear = !(getenv ("VOXGPU_HOST_CLEAR") && !atoi (getenv ("VOXGPU_HOST_CLEAR")));
+        if (host_clear && g_cull && trees[0])
+        {
+            int cull[4] = { 0, mu->w, 0, mu->h };
+            voxgpu_screen_bounds (trees[0]->root_min, trees[0]->root_max, c, mu->w, mu->h, cull);
+            int vy0 = cull[2] & ~3, vy1 = (cull[3] + 3) & ~3;
+            if (vy1 > mu->h) vy1 = mu->h;
+            const bool nothing = ((cull[1] + 7) & ~7) <= (cull[0] & ~7) || vy1 <= vy0;
+            if (nothing) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, 0, 0, 0, 0);
+            else if (vy0 > 0 || vy1 < mu->h) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, 0, mu->w, vy0, vy1);
+        }
     }
     int rc = 0;
     for (int i=0; i<mu->n; i++)

@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <math.h>
+#include <omp.h>
 #include <atomic>
 #include <mutex>
 #include <thread>
