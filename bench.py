@@ -14,8 +14,9 @@ rays).  Prints ONE JSON line (rank 0).
   e2e        C2 through the reference-facing API, called from C (examples/orbit_bench.c:
              vox_context_set_camera -> vox_render -> vox_redraw per frame, one pixel of every
              finished frame read by the host): per frame the camera goes host->device and the
-             8.3 MB frame device->host.  `value`: a ring of contexts (a swap chain of
-             page-locked surfaces) per rank; `single_context`: the reference demo's loop,
+             frame device->host (its visible rectangle over PCIe, the margin zeroed on the host).
+             `value`: a ring of contexts (a swap chain of page-locked surfaces) per rank, the best
+             of the depths 1 / 2 / 6 measured; `single_context`: the reference demo's loop,
              ONE context -- at N > 1 one process splitting every frame over all N GPUs
              (vox_context_set_devices); `adaptive`: the reference's default quality;
              `d2h_ceiling`: what plain DMA copies of frame-sized buffers reach on this box.
@@ -454,23 +455,32 @@ def leg_e2e(E, args, tree, poses):
     d2h_per_step = (int(E.g.voxgpu_present_bytes_copied()) - bytes0) // (steps + 1)
     one, _ = run(1, 1, 0)
     one_device_ms = run.device_ms
+    pair, _ = run(2, 1, 0)
     ada_ring, _ = run(E2E_CONTEXTS, 1, 2)
     ada_one, _ = run(1, 1, 2)
-    out.update({"value": round(ring, 2), "unit": "Mrays/s", "steps": steps, "contexts_in_flight": E2E_CONTEXTS,
+    # The depth of the swap chain is the caller's choice.  On one GPU six surfaces keep the PCIe link busy; with eight
+    # ranks on one host, 48 surfaces of 8.3 MB fall out of the CPUs' caches and the host's memory becomes the limit, and
+    # ONE surface per rank (which stays cached) is the better caller.  `value` is the best of the depths measured.
+    by_depth = {E2E_CONTEXTS: ring, 2: pair, 1: one}
+    best_depth = max(by_depth, key=by_depth.get)
+    out.update({"value": round(by_depth[best_depth], 2), "unit": "Mrays/s", "steps": steps, "contexts_in_flight": best_depth,
+                "by_contexts_in_flight": {str(k): round(v, 2) for k, v in sorted(by_depth.items())},
                 "single_context": round(one, 2),
                 "single_context_ms": {"wall_per_frame": round(RAYS_PER_FRAME / max(one, 1e-9) / 1e3 * world, 4), "device_per_frame": round(one_device_ms, 4),
                                       "what": "wall: vox_render + vox_redraw + the host's look at the frame; device: first launch of the frame to "
                                               "its last byte in host memory (CUDA events, a separate untimed pass)"},
-                "adaptive": {"value": round(ada_ring, 2), "single_context": round(ada_one, 2),
+                "adaptive": {"value": round(max(ada_ring, ada_one), 2), "ring": round(ada_ring, 2), "single_context": round(ada_one, 2),
                              "what": "the same legs in the reference's DEFAULT quality (ADAPTIVE, renderer.c:78): "
                                      "K1 root searches + the block-sequential walk, two launches per band"}})
     if world > 1:
         # one PROCESS, all N GPUs: rank 0 alone, the other ranks wait at the barrier with idle GPUs
         out["single_context_per_rank"] = out["single_context"]
         split_one, used = run(1, 0, 0, all_ranks=False)
+        split_pair, _ = run(2, 0, 0, all_ranks=False)
         split_ring, _ = run(E2E_CONTEXTS, 0, 0, all_ranks=False)
         out["single_context"] = round(split_one, 2)
-        out["in_process"] = {"devices": used, "single_context": round(split_one, 2), "ring": round(split_ring, 2),
+        out["in_process"] = {"devices": used, "single_context": round(split_one, 2), "two_contexts": round(split_pair, 2),
+                             "ring": round(split_ring, 2),
                              "what": "ONE process (rank 0; the other ranks idle) drives all GPUs behind vox_render: every frame's tile "
                                      "rows dealt to the devices (vox_context_set_devices), each device DMA-copies its rows into the "
                                      "surface over its own PCIe link"}
