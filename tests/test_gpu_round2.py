@@ -127,6 +127,48 @@ def test_masked_ticket_phases_leave_no_pixel_behind(gpu, skull, ds):
             assert np.array_equal(band[0], want[0][y0:y1]) and np.array_equal(band[1], want[1][y0:y1])
 
 
+@pytest.mark.parametrize("camera", ["simple-camera", "doom-camera"])
+def test_visible_rectangle_frames_equal_the_oracle(gpu, checker, skull, ds, camera):
+    """vox_render draws and copies only the part of the frame inside the root box's screen bounds and zeroes the
+    margin on the host (present.inl).  Random poses -- far, near, inside the volume, rolled, looking away, the box
+    partly off screen, narrow and wide fov -- through vox_render / vox_redraw into a POISONED surface, in BEST and in
+    the reference's default quality, on one context reused for all poses (so every frame meets the leftovers of a
+    frame with a different rectangle): every pixel must equal the oracle's frame."""
+    t, otree = gpu.Tree.build(skull), checker.tree(skull)
+    w, h = 320, 160
+    ctx = gpu.Context(w, h)
+    ctx.set_scene(t)
+    rng = np.random.default_rng(23)
+    kind = 0 if camera == "simple-camera" else 1
+    g = gpu.api.libs.gpu
+    shrunk = 0
+    for trial in range(30):
+        dist = [600.0, 330.0, 200.0, 140.0, 60.0, 0.0][trial % 6]
+        v = rng.normal(size=3)
+        pos = 128 + dist * v / np.linalg.norm(v) + rng.normal(size=3) * 3
+        look = 128 + rng.normal(size=3) * (40 if trial % 4 else 400)
+        fov = [0.3, 1.2, 2.5][trial % 3]
+        cam, ocam = gpu.Camera(camera), checker.camera(kind)
+        rot = [float(x) for x in rng.normal(size=3) * (0.5 if trial % 2 else 0.0)]
+        for c_ in (cam, ocam):
+            ds.setup_camera(c_, pos, look, fov, w, h)
+            c_.rotate(rot)
+        q = gpu.QUALITY_BEST if trial % 3 else gpu.QUALITY_ADAPTIVE
+        assert ctx.set_quality(q)
+        ctx.set_camera(cam)
+        ctx.pixels()[:] = 0xdeadbeef
+        before = int(g.voxgpu_present_bytes_copied())
+        ctx.render()
+        ctx.redraw()
+        assert gpu.last_error() == ""
+        copied = int(g.voxgpu_present_bytes_copied()) - before
+        assert copied <= w * h * 4
+        shrunk += copied < w * h * 4
+        opix = otree.render(ocam, w, h, q, ctx.texture(), threads=THREADS, want_hits=False)
+        assert np.array_equal(ctx.pixels(), opix), (trial, copied)
+    assert shrunk > 8           # the rectangle did shrink the copy in a good part of the poses
+
+
 def test_tile_cost_feedback_changes_nothing(gpu, golden, skull, ds):
     """voxgpu_set_tile_feedback: the order in which a frame's tiles are handed out follows the cost the previous
     frame recorded; pixels, leaf ids and hit points do not -- for a sequence of frames, a change of geometry in
