@@ -2,7 +2,7 @@
 """Minimal driver for ncu / A-B: 7680x4320 frames of the C5 volume (union of 4096 balls in 1024^3, ~106 M voxels,
 2.6 GB device tree: streams from HBM) through K1.
 
-    python tools/profile_c5.py [launches] [side] [balls]
+    python tools/profile_c5.py [launches] [side] [balls] [interleave world] [interleave rank]
 """
 import ctypes as C
 import os
@@ -30,7 +30,9 @@ cams = []
 for k in range(4):
     ds.setup_camera(cam, *ds.orbit_pose(k * 90.0, 360, (side / 2.0,) * 3, 328.0 * side / 256.0), 1.2, W, H)
     cams.append(cam.gpu_camera())
-fr = api.GpuFrame(W, H, 0, H, W, 0, ctx.pixfmt())
+il_world = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+il_rank = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+fr = api.GpuFrame(W, H, 0, H, W, 0, ctx.pixfmt(), None, il_world, il_rank)
 t = vv.Timer()
 ms = []
 for i in range(launches):

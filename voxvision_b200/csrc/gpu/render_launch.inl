@@ -285,16 +285,15 @@ __global__ void k_mark (TreeRef tr, const unsigned * __restrict__ cut, unsigned 
         const int tx0 = max ((int) x0, 0) >> 3, tx1 = (min ((int) x1, w) + 7) >> 3;
         const int ty0 = max ((int) y0, mb.y0) >> 2, ty1 = (min ((int) y1, mb.y1) + 3) >> 2;
         if (ty1 <= ty0) return;
-        const int nx = tx1 - tx0, n = nx * (ty1 - ty0);
-        if (n <= 4096)
+        const int nx = tx1 - tx0;
+        if (nx * (ty1 - ty0) <= 4096)
         {
-            const int u0 = mb.y0 >> 2;
+            /* only the tile rows this launch draws: with the frame split over N GPUs every N-th row, counted from y0 */
+            const int stride = mb.il_world > 1 ? mb.il_world : 1;
+            const int first = ty0 + (stride > 1 ? ((mb.il_rank - (ty0 - (mb.y0 >> 2))) % stride + stride) % stride : 0);
+            const int n = first < ty1 ? nx * ((ty1 - first + stride - 1) / stride) : 0;
             for (int j = k; j < n; j += 8)
-            {
-                const int ty = ty0 + j / nx, tx = tx0 + j % nx;
-                if (mb.il_world > 1 && (ty - u0) % mb.il_world != mb.il_rank) continue;
-                mark[(size_t) ty * tiles_x + tx] = epoch;       /* a plain store: nobody waits for it */
-            }
+                mark[(size_t) (first + (j / nx) * stride) * tiles_x + tx0 + j % nx] = epoch;    /* a plain store: nobody waits for it */
             return;
         }
     }
