@@ -167,7 +167,9 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     {
         int cull[4] = { 0, p->w, 0, p->h };
         voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
-        vx0 = cull[0] & ~7; vx1 = (cull[1] + 7) & ~7; vy0 = cull[2] & ~3; vy1 = (cull[3] + 3) & ~3;
+        /* columns on 16-pixel boundaries: whole 64-byte lines of the surface (whose rows are w*4 bytes, w a multiple of
+           16) belong either to the copy engine or to the threads that zero the margin, never to both */
+        vx0 = cull[0] & ~15; vx1 = (cull[1] + 15) & ~15; vy0 = cull[2] & ~3; vy1 = (cull[3] + 3) & ~3;
         if (vx1 > p->w) vx1 = p->w;
         if (vy1 > p->h) vy1 = p->h;
         /* one GPU's share of a split frame is copied in blocks of four whole rows: only the rows are cut, and the
