@@ -106,6 +106,19 @@ bad:
 
 extern "C" int voxgpu_present_bands (const voxgpu_present *p) { return p ? p->bands : 0; }
 
+/* The visible rectangle of a frame (see voxgpu_present_render): the root box's screen bounds on tile rows and on
+   16-pixel columns -- whole 64-byte lines of the surface (whose rows are w*4 bytes, w a multiple of 16) belong either
+   to the copy engine or to the threads that zero the margin, never to both.  false: the camera cannot see the tree. */
+static bool visible_rect (const voxgpu_tree *t, const voxgpu_camera *c, int w, int h, int *x0, int *x1, int *y0, int *y1)
+{
+    int cull[4] = { 0, w, 0, h };
+    voxgpu_screen_bounds (t->root_min, t->root_max, c, w, h, cull);
+    *x0 = cull[0] & ~15; *x1 = (cull[1] + 15) & ~15; *y0 = cull[2] & ~3; *y1 = (cull[3] + 3) & ~3;
+    if (*x1 > w) *x1 = w;
+    if (*y1 > h) *y1 = h;
+    return cull[1] > cull[0] && cull[3] > cull[2];
+}
+
 /* Zero every pixel of a w x h surface outside [x0,x1) x [y0,y1) (an empty rectangle: the whole surface).  A
    memset of several MB is bound by one core's store bandwidth, so a few threads share the rows (the num_threads
    clause, not $OMP_NUM_THREADS, which launchers like torchrun set to 1). */
@@ -163,20 +176,14 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
        link is what bounds vox_render + vox_redraw.  ($VOXGPU_HOST_CLEAR=0: the whole frame comes from the device.) */
     int vx0 = 0, vx1 = p->w, vy0 = 0, vy1 = p->h;
     static const int host_clear = !(getenv ("VOXGPU_HOST_CLEAR") && !atoi (getenv ("VOXGPU_HOST_CLEAR")));
+    bool nothing = false;
     if (host_clear && t && g_cull)
     {
-        int cull[4] = { 0, p->w, 0, p->h };
-        voxgpu_screen_bounds (t->root_min, t->root_max, c, p->w, p->h, cull);
-        /* columns on 16-pixel boundaries: whole 64-byte lines of the surface (whose rows are w*4 bytes, w a multiple of
-           16) belong either to the copy engine or to the threads that zero the margin, never to both */
-        vx0 = cull[0] & ~15; vx1 = (cull[1] + 15) & ~15; vy0 = cull[2] & ~3; vy1 = (cull[3] + 3) & ~3;
-        if (vx1 > p->w) vx1 = p->w;
-        if (vy1 > p->h) vy1 = p->h;
+        nothing = !visible_rect (t, c, p->w, p->h, &vx0, &vx1, &vy0, &vy1);
         /* one GPU's share of a split frame is copied in blocks of four whole rows: only the rows are cut, and the
            caller of all shares (voxgpu_multi_render) zeroes the margin once */
         if (il_world > 1) { vx0 = 0; vx1 = p->w; }
     }
-    const bool nothing = vx1 <= vx0 || vy1 <= vy0;
     const int v_units = nothing ? 0 : (vy1 - vy0) / 4, v_u0 = vy0 / 4;
     if (nbands > v_units) nbands = v_units > 0 ? v_units : 1;
     CU (cudaEventRecord (p->start, p->stream[0]));
@@ -473,11 +480,8 @@ extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *
         static const int host_clear = !(getenv ("VOXGPU_HOST_CLEAR") && !atoi (getenv ("VOXGPU_HOST_CLEAR")));
         if (host_clear && g_cull && trees[0])
         {
-            int cull[4] = { 0, mu->w, 0, mu->h };
-            voxgpu_screen_bounds (trees[0]->root_min, trees[0]->root_max, c, mu->w, mu->h, cull);
-            int vy0 = cull[2] & ~3, vy1 = (cull[3] + 3) & ~3;
-            if (vy1 > mu->h) vy1 = mu->h;
-            const bool nothing = ((cull[1] + 7) & ~7) <= (cull[0] & ~7) || vy1 <= vy0;
+            int vx0, vx1, vy0, vy1;
+            const bool nothing = !visible_rect (trees[0], c, mu->w, mu->h, &vx0, &vx1, &vy0, &vy1);
             if (nothing) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, 0, 0, 0, 0);
             else if (vy0 > 0 || vy1 < mu->h) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, 0, mu->w, vy0, vy1);
         }
