@@ -427,7 +427,7 @@ def test_root_box_culling_changes_nothing(gpu, checker, skull, ds, camera):
 
 
 def test_many_launches_in_flight_on_three_streams(gpu, skull, ds):
-    """More launches queued than there are render slots (64 pairs of tile counters + screen masks), on a
+    """More launches queued than there are render slots (16 pairs of tile counters + screen masks), on a
     number of streams that does not divide 64: a slot that comes round again while its previous borrower
     is still running on another stream must wait for it (slot_acquire / slot_release)."""
     t = gpu.Tree.build(skull)

@@ -66,7 +66,7 @@ def c1():
     d_tex, d_pix = vv.DeviceBuffer.from_array(ctx.texture()), vv.DeviceBuffer(W * H * 4)
     fr = api.GpuFrame(W, H, 0, H, W, 0, ctx.pixfmt(), None)
     render = lambda: g.voxgpu_render(dev, C.byref(gc), C.byref(fr), d_tex.ptr, d_pix.ptr, None, None, None)
-    for _ in range(100):        # more than the 64 mask / counter slots: the first use of a slot allocates
+    for _ in range(100):        # more than the 16 mask / counter slots: the first use of a slot allocates
         render()
     mean, best = timed(render, 200)
     ctx.set_scene(tree); ctx.set_camera(cam); ctx.set_quality(0)

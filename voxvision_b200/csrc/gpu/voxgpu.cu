@@ -1,7 +1,8 @@
 /*
  * voxgpu.cu -- CUDA kernels (sm_100a) and the thin C-ABI of include/voxgpu.h.
  *
- *   K1 k_render : camera ray generation (simple-camera.c:21-31 / doom-camera.c:36-57)
+ *   K1 k_render_persistent / k_render_blocks (render_kernels.inl):
+ *                 camera ray generation (simple-camera.c:21-31 / doom-camera.c:36-57)
  *                 + first-hit octree search (search.c:8-153) + get_color
  *                 (renderer.c:27-52) + linear framebuffer store, one thread per
  *                 pixel, one warp per 8x4 pixel tile.  Replaces the 4x4-block
