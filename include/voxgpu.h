@@ -261,6 +261,16 @@ VOXGPU_EXPORT float voxgpu_present_last_ms (voxgpu_present *p);
 /** Bytes of frames all presenters of this process have queued for device-to-host copies so far (only the visible
     rectangle of a frame crosses PCIe; the margin is zeroed on the host). */
 VOXGPU_EXPORT unsigned long long voxgpu_present_bytes_copied (void);
+/** The presenter's host arithmetic for the visible spans, on its own (no device is touched): `boxes` is six
+    arrays of n floats (min x, y, z, max x, y, z; n <= 512) that together hold every voxel; on return 1,
+    a voxel can only show in row y at columns lo[y/4] <= x < hi[y/4] (hi <= lo: the rows show nothing); 0: no
+    claim (a box beside or behind the camera).  lo, hi: h/4 ints each.  The presenter copies only those columns
+    (in strips, on 16-pixel boundaries) and zeroes the rest of the surface on the host. */
+/** Knobs of the above, process-wide (a negative / zero argument leaves that knob alone): spans on or off (off: the
+    root box's rectangle only; default on, $VOXGPU_SPANS), the most copies one frame is cut into (default 16,
+    $VOXGPU_COPY_STRIPS), and what one more copy must save in bytes to be worth it (default 98304, $VOXGPU_COPY_COST). */
+VOXGPU_EXPORT void voxgpu_set_present_spans (int on, int max_strips, long long copy_cost);
+VOXGPU_EXPORT int voxgpu_visible_spans (const float *boxes, unsigned n, const voxgpu_camera *c, int w, int h, int *lo, int *hi);
 /** The device framebuffer the last frame was rendered into (w*h pixels, pitch w). */
 VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p);
 

@@ -129,11 +129,13 @@ def test_masked_ticket_phases_leave_no_pixel_behind(gpu, skull, ds):
 
 @pytest.mark.parametrize("camera", ["simple-camera", "doom-camera"])
 def test_visible_rectangle_frames_equal_the_oracle(gpu, checker, skull, ds, camera):
-    """vox_render draws and copies only the part of the frame inside the root box's screen bounds and zeroes the
-    margin on the host (present.inl).  Random poses -- far, near, inside the volume, rolled, looking away, the box
+    """vox_render draws and copies only the part of the frame inside the root box's screen bounds -- and of that,
+    per strip of rows, only the columns the tree's coarse cut can show (the visible spans) -- and zeroes the rest
+    on the host (present.inl).  Random poses -- far, near, inside the volume, rolled, looking away, the box
     partly off screen, narrow and wide fov -- through vox_render / vox_redraw into a POISONED surface, in BEST and in
     the reference's default quality, on one context reused for all poses (so every frame meets the leftovers of a
-    frame with a different rectangle): every pixel must equal the oracle's frame."""
+    frame with a different rectangle): every pixel must equal the oracle's frame, with the spans off, with the
+    default knobs and with every band cut into as many strips as it has (copy cost 0)."""
     t, otree = gpu.Tree.build(skull), checker.tree(skull)
     w, h = 320, 160
     ctx = gpu.Context(w, h)
@@ -141,7 +143,7 @@ def test_visible_rectangle_frames_equal_the_oracle(gpu, checker, skull, ds, came
     rng = np.random.default_rng(23)
     kind = 0 if camera == "simple-camera" else 1
     g = gpu.api.libs.gpu
-    shrunk = 0
+    shrunk = tighter = 0
     for trial in range(30):
         dist = [600.0, 330.0, 200.0, 140.0, 60.0, 0.0][trial % 6]
         v = rng.normal(size=3)
@@ -156,17 +158,25 @@ def test_visible_rectangle_frames_equal_the_oracle(gpu, checker, skull, ds, came
         q = gpu.QUALITY_BEST if trial % 3 else gpu.QUALITY_ADAPTIVE
         assert ctx.set_quality(q)
         ctx.set_camera(cam)
-        ctx.pixels()[:] = 0xdeadbeef
-        before = int(g.voxgpu_present_bytes_copied())
-        ctx.render()
-        ctx.redraw()
-        assert gpu.last_error() == ""
-        copied = int(g.voxgpu_present_bytes_copied()) - before
-        assert copied <= w * h * 4
-        shrunk += copied < w * h * 4
         opix = otree.render(ocam, w, h, q, ctx.texture(), threads=THREADS, want_hits=False)
-        assert np.array_equal(ctx.pixels(), opix), (trial, copied)
+        sizes = []
+        try:
+            for knobs in ((0, 16, 98304), (1, 16, 98304), (1, 32, 0)):
+                g.voxgpu_set_present_spans(*knobs)
+                ctx.pixels()[:] = 0xdeadbeef
+                before = int(g.voxgpu_present_bytes_copied())
+                ctx.render()
+                ctx.redraw()
+                assert gpu.last_error() == ""
+                sizes.append(int(g.voxgpu_present_bytes_copied()) - before)
+                assert np.array_equal(ctx.pixels(), opix), (trial, knobs, sizes)
+        finally:
+            g.voxgpu_set_present_spans(1, 16, 98304)
+        assert w * h * 4 >= sizes[0] >= sizes[1] >= sizes[2]
+        shrunk += sizes[0] < w * h * 4
+        tighter += sizes[2] < sizes[0]
     assert shrunk > 8           # the rectangle did shrink the copy in a good part of the poses
+    assert tighter > 4          # and the spans shrank it further
 
 
 def test_tile_cost_feedback_changes_nothing(gpu, golden, skull, ds):

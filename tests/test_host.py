@@ -333,6 +333,73 @@ def test_screen_bounds_contain_every_hit_pixel(vv, port, skull, ds, kind, name):
     assert bounded > 15          # the bounds do bite in many poses (VOX_BOUNDS_TRIALS=1500 was run once: no escape)
 
 
+def host_cut_boxes(a, limit=512):
+    """The coarse host cut of tree.inl (deepest level whose cut has <= limit nodes, plus the leaves above it) of an
+    exported tree, as the six arrays voxgpu_visible_spans takes."""
+    n = len(a["flags"])
+    leafp = (a["flags"] & 3) != 0
+    level = np.zeros(n, np.int32)
+    for i in np.flatnonzero(~leafp):
+        nc, fc = bin(int(a["child_mask"][i])).count("1"), int(a["first_child"][i])
+        level[fc:fc + nc] = level[i] + 1
+    at, leaves = np.bincount(level), np.bincount(level[leafp], minlength=level.max() + 1)
+    best = above = 0
+    for lv in range(len(at)):
+        if at[lv] + above <= limit:
+            best = lv
+        above += leaves[lv]
+    cut = np.flatnonzero((level == best) | ((level < best) & leafp))
+    return np.ascontiguousarray(np.concatenate([a["bb_min"][cut].T, a["bb_max"][cut].T]), np.float32), len(cut)
+
+
+def test_visible_spans_contain_every_hit_pixel(vv, port, skull, ds):
+    """voxgpu_visible_spans (the presenter copies only these columns of every 4-row unit and zeroes the rest on the
+    host): over random poses of both cameras, every pixel the ORACLE finds a voxel for lies inside its row's span;
+    a pose with a box beside or behind the camera gets no claim; and the spans do bite (they hold clearly fewer
+    pixels than the root box's rectangle).  Host arithmetic only."""
+    g = vv.libs.gpu
+    g.voxgpu_visible_spans.argtypes = [C.c_void_p, C.c_uint, C.POINTER(vv.api.GpuCamera), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    g.voxgpu_visible_spans.restype = C.c_int
+    g.voxgpu_screen_bounds.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(vv.api.GpuCamera), C.c_int, C.c_int, C.c_void_p]
+    boxes, n = host_cut_boxes(vv.Tree.build(skull).export())
+    assert 64 < n <= 512
+    otree = port.tree(skull)
+    w, h = 320, 160
+    rng = np.random.default_rng(77)
+    claims = kept = rect = 0
+    for trial in range(int(os.environ.get("VOX_BOUNDS_TRIALS", "60"))):
+        kind = trial % 2
+        dist = [700.0, 330.0, 220.0, 150.0, 60.0][trial % 5]
+        v = rng.normal(size=3)
+        pos = 128 + dist * v / np.linalg.norm(v) + rng.normal(size=3) * 3
+        look = 128 + rng.normal(size=3) * (40 if trial % 4 else 400)
+        cam, ocam = vv.Camera("doom-camera" if kind else "simple-camera"), port.camera(kind)
+        rot = [float(x) for x in rng.normal(size=3) * (0.5 if trial % 3 == 0 else 0.0)]
+        for c_ in (cam, ocam):
+            ds.setup_camera(c_, pos, look, [0.4, 1.2, 2.5][trial % 3], w, h)
+            c_.rotate(rot)
+        gc = cam.gpu_camera()
+        lo, hi = np.zeros(h // 4, np.int32), np.zeros(h // 4, np.int32)
+        if not g.voxgpu_visible_spans(boxes.ctypes.data, n, C.byref(gc), w, h, lo.ctypes.data, hi.ctypes.data):
+            continue
+        claims += 1
+        assert (lo >= 0).all() and (hi <= w).all()
+        hit = (otree.rays(*ocam.rays(w, h))[0] >= 0).reshape(h, w)
+        x = np.arange(w)[None, :]
+        inside = (x >= np.repeat(lo, 4)[:, None]) & (x < np.repeat(hi, 4)[:, None])
+        assert not (hit & ~inside).any(), trial
+        out = (C.c_int * 4)()
+        mn, mx = np.ascontiguousarray(boxes[:3].min(1)), np.ascontiguousarray(boxes[3:].max(1))
+        g.voxgpu_screen_bounds(mn.ctypes.data, mx.ctypes.data, C.byref(gc), w, h, out)
+        kept += int(inside.sum())
+        rect += (out[1] - out[0]) * (out[3] - out[2])
+    assert claims > 15 and kept < 0.9 * rect, (claims, kept, rect)
+    # a camera in the middle of the volume has boxes behind it: no claim
+    cam = ds.setup_camera(vv.Camera("simple-camera"), [128, 128, 128], [128, 300, 128], 1.2, w, h)
+    gc = cam.gpu_camera()
+    assert g.voxgpu_visible_spans(boxes.ctypes.data, n, C.byref(gc), w, h, lo.ctypes.data, hi.ctypes.data) == 0
+
+
 def test_screen_mask_argument_on_the_host(vv, port, skull, ds):
     """The argument behind the render kernel's screen mask (k_mark in voxgpu.cu), replayed in numpy: take
     the same cut through the tree (deepest level with <= 131072 nodes plus the leaves above it), project

@@ -189,6 +189,8 @@ class _Libs:
         g.voxgpu_present_wait.argtypes = [_vp]
         g.voxgpu_launch_count.restype = C.c_ulonglong
         g.voxgpu_present_bytes_copied.restype = C.c_ulonglong
+        g.voxgpu_set_present_spans.argtypes = [C.c_int, C.c_int, C.c_longlong]
+        g.voxgpu_set_present_spans.restype = None
         g.voxgpu_timer_create.restype = _vp
         g.voxgpu_timer_destroy.argtypes = [_vp]
         g.voxgpu_timer_start.argtypes = [_vp, _vp]

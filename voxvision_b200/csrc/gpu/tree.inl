@@ -21,8 +21,13 @@ struct voxgpu_tree
        device's render lock */
     unsigned char *cost;
     int cost_tiles_x, cost_tiles_y;
+    /* a coarse cut kept on the HOST (boxes as six arrays: min x, y, z, max x, y, z): the presenter projects it
+       every frame to bound the columns each group of rows can show (present.inl: visible_spans) */
+    float *hbox;
+    unsigned n_hbox;
 };
 #define VOXGPU_CUT_MAX 131072u
+#define VOXGPU_HOST_CUT_MAX 512u
 
 extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
 {
@@ -116,12 +121,28 @@ extern "C" voxgpu_tree* voxgpu_tree_upload (const voxgpu_flat *f)
             const int nc = __builtin_popcount (f->child_mask[id] & 0xffu);
             for (int j=0; j<nc; j++) level[f->first_child[id] + j] = (unsigned char) (l + 1);
         }
-        unsigned best = 0;
+        unsigned best = 0, hbest = 0;
         uint64_t above = 0;
         for (unsigned l=0; l<f->depth && l <= VOXGPU_MAX_DEPTH; l++)
         {
             if (at[l] + above <= VOXGPU_CUT_MAX) best = l;
+            if (at[l] + above <= VOXGPU_HOST_CUT_MAX) hbest = l;
             above += leaves[l];
+        }
+        {
+            /* the host's cut: the same construction, a shallower level */
+            unsigned hn = 0;
+            for (uint64_t id=0; id<f->n_nodes; id++)
+                if (level[id] == hbest || (level[id] < hbest && (f->flags[id] & 3u))) hn++;
+            t->hbox = (float*) malloc ((size_t) (hn ? hn : 1) * 6 * sizeof (float));
+            t->n_hbox = hn;
+            unsigned k = 0;
+            for (uint64_t id=0; id<f->n_nodes; id++)
+                if (level[id] == hbest || (level[id] < hbest && (f->flags[id] & 3u)))
+                {
+                    for (int a=0; a<3; a++) { t->hbox[(size_t) a * hn + k] = f->bb_min[3*id+a]; t->hbox[(size_t) (3 + a) * hn + k] = f->bb_max[3*id+a]; }
+                    k++;
+                }
         }
         unsigned n = 0;
         unsigned *tmp = (unsigned*) malloc ((size_t) VOXGPU_CUT_MAX * sizeof (unsigned));
@@ -141,6 +162,7 @@ bad:
     if (stage_v) cudaFreeHost (stage_v);
     if (s) cudaStreamDestroy (s);
     cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut);
+    free (t->hbox);
     free (t);
     return NULL;
 }
@@ -153,6 +175,7 @@ extern "C" void voxgpu_tree_free (voxgpu_tree *t)
     if (cur != t->device) cudaSetDevice (t->device);
     cudaFree (t->rec); cudaFree (t->ctr); cudaFree (t->dots); cudaFree (t->cut); cudaFree (t->cost);
     if (cur != t->device && cur >= 0) cudaSetDevice (cur);
+    free (t->hbox);
     free (t);
 }
 extern "C" size_t voxgpu_tree_device_bytes (const voxgpu_tree *t)
