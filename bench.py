@@ -14,7 +14,7 @@ rays).  Prints ONE JSON line (rank 0).
   e2e        C2 through the reference-facing API, called from C (examples/orbit_bench.c:
              vox_context_set_camera -> vox_render -> vox_redraw per frame, one pixel of every
              finished frame read by the host): per frame the camera goes host->device and the
-             frame device->host (its visible rectangle over PCIe, the margin zeroed on the host).
+             frame device->host (its visible spans over PCIe, the margin zeroed on the host).
              `value`: a ring of contexts (a swap chain of page-locked surfaces) per rank, the best
              of the depths 1 / 2 / 6 measured; `single_context`: the reference demo's loop,
              ONE context -- at N > 1 one process splitting every frame over all N GPUs
@@ -450,8 +450,8 @@ def leg_e2e(E, args, tree, poses):
     out = {}
     bytes0 = int(E.g.voxgpu_present_bytes_copied())
     ring, _ = run(E2E_CONTEXTS, 1, 0)
-    # what crossed PCIe per pass over the path: only the visible rectangle of a frame is copied, the margin outside
-    # the root box's screen bounds is zeroed on the host (one untimed + `steps` timed passes went through)
+    # what crossed PCIe per pass over the path: only the visible spans of a frame are copied, the margin outside
+    # them is zeroed on the host (one untimed + `steps` timed passes went through)
     d2h_per_step = (int(E.g.voxgpu_present_bytes_copied()) - bytes0) // (steps + 1)
     one, _ = run(1, 1, 0)
     one_device_ms = run.device_ms
@@ -511,8 +511,9 @@ def leg_e2e(E, args, tree, poses):
     out["d2h_bytes_per_step"] = d2h_per_step
     out["frame_bytes_per_step"] = FRAMES * frame_bytes
     out["d2h_note"] = ("d2h_bytes_per_step = bytes the presenters queued for device->host copies in one pass of the ring leg "
-                       "(counted by libvoxgpu): the visible rectangle of every frame; the rest of each 8.3 MB frame lies outside the "
-                       "root box's screen bounds and is zeroed on the host inside vox_render, as the reference clears its squares on the host")
+                       "(counted by libvoxgpu): the visible spans of every frame -- per strip of rows, the columns the projected boxes of "
+                       "the tree's coarse host cut can show; the rest of each 8.3 MB frame cannot show a voxel and is zeroed on the host "
+                       "inside vox_render, as the reference clears its squares on the host")
     out["path"] = ("examples/orbit_bench.c: vox_context_set_camera + vox_render + vox_redraw per frame and a host read of the "
                    "finished surface, on a ring of contexts (each with its own page-locked surface): band kernels into a "
                    "device framebuffer, each band DMA-copied into the surface while the next band / next frame renders")
