@@ -247,7 +247,9 @@ VOXGPU_EXPORT int voxgpu_render (const voxgpu_tree *tree, const voxgpu_camera *c
  * frame->y0/y1/pitch_pixels are ignored (the whole frame is drawn) -- or, with
  * frame->interleave_world = N > 1, this device's share of a frame that N devices
  * split: the tile rows r with r % N == interleave_rank, one launch, one strided
- * DMA copy of exactly those rows into `host_pixels` (needs host_pitch_bytes == 4*w). */
+ * DMA copy of exactly those rows (the columns of the visible rectangle) into
+ * `host_pixels` (needs host_pitch_bytes == 4*w; the margin is the caller's to
+ * zero, once for all shares: voxgpu_multi_render does). */
 typedef struct voxgpu_present voxgpu_present;
 VOXGPU_EXPORT voxgpu_present* voxgpu_present_create (int w, int h, int bands);
 VOXGPU_EXPORT void voxgpu_present_destroy (voxgpu_present *p);

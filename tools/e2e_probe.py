@@ -17,6 +17,7 @@ from tools import datasets as ds
 import bench
 
 W, H, FRAMES = 1920, 1080, 360
+DEVICES = int(os.environ.get("PROBE_DEVICES", "1"))  # > 1: every frame split over that many GPUs of this process
 STEPS = int(os.environ.get("PROBE_STEPS", "2"))      # orbits per leg ($PROBE_STEPS > 2: BEST only, for runs side by side)
 orbit = C.CDLL(os.path.join(api.LIB_DIR, "liborbitbench.so"))
 orbit.orbit_bench_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int,
@@ -30,10 +31,10 @@ for bands in [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4, 6, 8]:
     else:
         os.environ.pop("VOXGPU_BANDS", None)
     line = [f"bands {bands}:"]
-    for qname, q in (("BEST", 0), ("ADAPTIVE", 2))[:1 if STEPS != 2 else 2]:
+    for qname, q in (("BEST", 0), ("ADAPTIVE", 2))[:1 if STEPS != 2 or DEVICES > 1 else 2]:
         for contexts in (1, 6):
             res = bench.OrbitBenchResult()
-            rc = orbit.orbit_bench_run(tree.h, W, H, FRAMES, poses.ctypes.data, 1.2, contexts, 1, q, STEPS, C.byref(res))
+            rc = orbit.orbit_bench_run(tree.h, W, H, FRAMES, poses.ctypes.data, 1.2, contexts, DEVICES, q, STEPS, C.byref(res))
             assert rc == 0, res.error
             wall = res.seconds / res.frames * 1e3
             line.append(f"{qname} x{contexts}: wall {wall:.4f} ms/frame ({W*H/wall/1e3:.0f} Mrays/s)" +

@@ -295,16 +295,6 @@ static int strip_runs (int b0, int b1, int sub, const int *glo, const int *ghi, 
     return n;
 }
 
-/* zero the rows outside [y0, y1) */
-static void host_clear_rows (void *pixels, size_t pitch, int w, int h, int y0, int y1)
-{
-    for (int pass=0; pass<2; pass++)
-    {
-        const int a = pass ? y1 : 0, b = pass ? h : y0;
-        if (b > a) host_clear_margin ((char*) pixels + (size_t) a * pitch, pitch, w, b - a, NULL, NULL);
-    }
-}
-
 extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c,
                                       const voxgpu_frame *f, const uint8_t *d_tex,
                                       void *host_pixels, size_t host_pitch_bytes)
@@ -337,9 +327,8 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
     if (host_clear && t && g_cull)
     {
         nothing = !visible_rect (t, c, p->w, p->h, &vx0, &vx1, &vy0, &vy1);
-        /* one GPU's share of a split frame is copied in blocks of four whole rows: only the rows are cut, and the
-           caller of all shares (voxgpu_multi_render) zeroes the margin once */
-        if (il_world > 1) { vx0 = 0; vx1 = p->w; }
+        /* (one GPU's share of a split frame: its tile rows of the rectangle; the caller of all shares,
+           voxgpu_multi_render, zeroes the margin once) */
     }
     const int v_units = nothing ? 0 : (vy1 - vy0) / 4, v_u0 = vy0 / 4;
     if (nbands > v_units) nbands = v_units > 0 ? v_units : 1;
@@ -437,8 +426,23 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
             const int b_units = (y1 - y0) / 4;
             const int own = il_rank < b_units ? (b_units - il_rank + il_world - 1) / il_world : 0;
             const size_t row4 = (size_t) p->w * 16;
-            e = own ? cudaMemcpy2DAsync (dst + (size_t) il_rank * row4, row4 * il_world, (const char*) src + (size_t) il_rank * row4,
-                                         row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[k]) : cudaSuccess;
+            if (!own) e = cudaSuccess;
+            else if (vx0 == 0 && vx1 == p->w)
+                e = cudaMemcpy2DAsync (dst + (size_t) il_rank * row4, row4 * il_world, (const char*) src + (size_t) il_rank * row4,
+                                       row4 * il_world, row4, own, cudaMemcpyDeviceToHost, p->stream[k]);
+            else
+            {
+                /* the columns of the rectangle only: a 3-D copy, one slice (4 rows of a 4*N-row slab) per tile row */
+                cudaMemcpy3DParms q;
+                memset (&q, 0, sizeof q);
+                q.srcPtr = make_cudaPitchedPtr ((void*) ((const char*) src + (size_t) il_rank * row4), (size_t) p->w * 4, (size_t) p->w * 4, (size_t) 4 * il_world);
+                q.dstPtr = make_cudaPitchedPtr ((void*) (dst + (size_t) il_rank * row4), (size_t) p->w * 4, (size_t) p->w * 4, (size_t) 4 * il_world);
+                q.srcPos = make_cudaPos ((size_t) vx0 * 4, 0, 0);
+                q.dstPos = q.srcPos;
+                q.extent = make_cudaExtent ((size_t) (vx1 - vx0) * 4, 4, (size_t) own);
+                q.kind = cudaMemcpyDeviceToHost;
+                e = cudaMemcpy3DAsync (&q, p->stream[k]);
+            }
         }
         else
         {
@@ -472,7 +476,7 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
         }
         if (e != cudaSuccess) { rc = fail ("voxgpu_present_render: copy to the surface failed: %s", cudaGetErrorString (e)); }
         else if (il_world > 1)
-            g_present_bytes += (unsigned long long) p->w * 16 * (il_rank < (y1 - y0) / 4 ? ((y1 - y0) / 4 - il_rank + il_world - 1) / il_world : 0);
+            g_present_bytes += (unsigned long long) (vx1 - vx0) * 16 * (il_rank < (y1 - y0) / 4 ? ((y1 - y0) / 4 - il_rank + il_world - 1) / il_world : 0);
         cudaEventRecord (p->done[k], p->stream[k]);
         queued++;
     }
@@ -560,6 +564,7 @@ struct voxgpu_multi
     int n, w, h;
     MultiWorker *wk;
     int in_flight;
+    int *span;                      /* 2 x h/4 ints: the columns of every 4-row unit the devices' copies write */
 };
 
 static void multi_worker_main (voxgpu_multi *mu, MultiWorker *w)
@@ -630,6 +635,7 @@ extern "C" void voxgpu_multi_destroy (voxgpu_multi *mu)
         w->th.join ();
     }
     delete[] mu->wk;
+    free (mu->span);
     free (mu);
 }
 
@@ -640,6 +646,8 @@ extern "C" voxgpu_multi* voxgpu_multi_create (int w, int h, int ndev, const int 
     voxgpu_multi *mu = (voxgpu_multi*) calloc (1, sizeof *mu);
     if (!mu) { fail ("voxgpu_multi_create: out of memory"); return NULL; }
     mu->n = ndev; mu->w = w; mu->h = h;
+    mu->span = (int*) calloc ((size_t) (h / 4) * 2, sizeof (int));
+    if (!mu->span) { free (mu); fail ("voxgpu_multi_create: out of memory"); return NULL; }
     mu->wk = new MultiWorker[ndev];
     for (int i=0; i<ndev; i++)
     {
@@ -681,7 +689,7 @@ extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *
         j.cam = *c; j.frame = *f; j.host_pixels = host_pixels; j.pitch = host_pitch_bytes;
         multi_post (&mu->wk[i], seq);
     }
-    /* the rows no device draws (outside the root box's screen bounds: see voxgpu_present_render), while the workers queue */
+    /* what no device draws (outside the root box's screen bounds: see voxgpu_present_render), while the workers queue */
     {
         static const int host_clear = !(getenv ("VOXGPU_HOST_CLEAR") && !atoi (getenv ("VOXGPU_HOST_CLEAR")));
         if (host_clear && g_cull && trees[0])
@@ -689,7 +697,13 @@ extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *
             int vx0, vx1, vy0, vy1;
             const bool nothing = !visible_rect (trees[0], c, mu->w, mu->h, &vx0, &vx1, &vy0, &vy1);
             if (nothing) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, NULL, NULL);
-            else if (vy0 > 0 || vy1 < mu->h) host_clear_rows (host_pixels, host_pitch_bytes, mu->w, mu->h, vy0, vy1);
+            else if (vx0 > 0 || vx1 < mu->w || vy0 > 0 || vy1 < mu->h)
+            {
+                const int units = mu->h / 4;
+                int *lo = mu->span, *hi = lo + units;
+                for (int u=0; u<units; u++) { const bool in = u >= vy0 / 4 && u < vy1 / 4; lo[u] = in ? vx0 : 0; hi[u] = in ? vx1 : 0; }
+                host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, lo, hi);
+            }
         }
     }
     int rc = 0;
