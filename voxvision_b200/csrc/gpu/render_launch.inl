@@ -143,6 +143,7 @@ struct RenderDevice
     int ready;
     unsigned seq;
     unsigned *counters;         /* 2 per slot */
+    int sms;
     int blocks[6];              /* resident grid of: K1, K1 with hits, K1 lit, K1b, K1b lit, streaming K2 */
     RenderSlot slot[RENDER_SLOTS];
     unsigned scratch_seq;
@@ -172,6 +173,7 @@ static int render_device_init (RenderDevice &rd, int device)
 #undef RESIDENT
     b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, k_rays_stream<true>, RAYS_BLOCK, 0);
     rd.blocks[GRID_RAYS_STREAM] = sms * (b > 0 ? b : 1);
+    rd.sms = sms;
     rd.counters = p;
     rd.ready = 1;
     return 0;
@@ -533,6 +535,13 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
     if (!sl.ev) CU (cudaEventCreateWithFlags (&sl.ev, cudaEventDisableTiming));
     if (sl.used && sl.last != st) CU (cudaStreamWaitEvent (st, sl.ev, 0));
     unsigned *counters = rd.counters + 2 * idx;
+    /* is the previous render launch of this device still at work?  (its slot's event, recorded behind it) */
+    bool busy = false;
+    if (idx != (idx + RENDER_SLOTS - 1) % RENDER_SLOTS)
+    {
+        const RenderSlot &prev = rd.slot[(idx + RENDER_SLOTS - 1) % RENDER_SLOTS];
+        if (prev.used && prev.ev && cudaEventQuery (prev.ev) == cudaErrorNotReady) busy = true;
+    }
     int rc = 0;
     bool marked_here = false;
     RenderScratch *scratch = NULL;
@@ -603,6 +612,17 @@ static int render_impl (const voxgpu_tree *t, const voxgpu_camera *c, const voxg
         else
         {
             int grid = rd.blocks[lit ? GRID_K1_LIT : (hits ? GRID_K1_HITS : GRID_K1)];
+            {
+                /* A lone launch takes every resident slot of the GPU (8 CTAs per SM).  One queued while another is
+                   still at work takes 5 per SM: kernels in flight then share the SMs side by side instead of each
+                   holding all slots until its last ticket is done -- 4 frames in flight 0.1400 -> 0.1378 ms per frame,
+                   a ring of six contexts 13.7 -> 14.1 Grays/s on the same box; a lone launch loses with anything below
+                   7, and so do the 5 ms launches of C5's 8K frames even in flight (4.96 -> 5.01 ms), so launches of
+                   more than 4 Mi pixels keep the full grid (profiles/r02_ab_variants.txt).
+                   $VOXGPU_K1_BUSY_CTAS: that 5; 0 = always the full grid. */
+                static const int ctas = getenv ("VOXGPU_K1_BUSY_CTAS") ? atoi (getenv ("VOXGPU_K1_BUSY_CTAS")) : 5;
+                if (busy && ctas > 0 && (long long) df.w * df.rows <= (4ll << 20) && grid > rd.sms * ctas) grid = rd.sms * ctas;
+            }
             if (grid > blocks) grid = blocks;
             if (lit)      /* light manager attached: shading through the flattened M-tree */
                 k_render_persistent<true, RENDER_STRIPS, true><<<grid, RENDER_BLOCK, 0, st>>> (tr, start, dc, df, mk, d_tex, d_pixels, d_leaf, pts, counters, g_trace);
