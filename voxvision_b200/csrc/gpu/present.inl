@@ -225,19 +225,24 @@ extern "C" int voxgpu_visible_spans (const float *boxes, unsigned n, const voxgp
    [lo[y/4], hi[y/4]) (hi <= lo: nothing kept; lo == NULL: nothing kept anywhere).  A memset of several MB is
    bound by one core's store bandwidth, so a few threads share the rows (the num_threads clause, not
    $OMP_NUM_THREADS, which launchers like torchrun set to 1). */
-static void host_clear_margin (void *pixels, size_t pitch, int w, int h, const int *lo, const int *hi)
+static void host_clear_margin (void *pixels, size_t pitch, int w, int h, const int *lo, const int *hi, bool all_devices = false)
 {
-    static const int threads = [] {
-        if (getenv ("VOXGPU_CLEAR_THREADS")) return atoi (getenv ("VOXGPU_CLEAR_THREADS"));
-        /* up to 4, but leave the box to its other GPUs' processes: half of the cores, shared by the visible devices */
+    /* up to 4 threads, but leave the box to its other GPUs' processes: half of the cores, shared by the visible
+       devices -- unless this process drives all of them itself (voxgpu_multi_render): then up to 8 */
+    static const int forced = getenv ("VOXGPU_CLEAR_THREADS") ? atoi (getenv ("VOXGPU_CLEAR_THREADS")) : 0;
+    static const int per_device = [] {
         int gpus = 1;
         if (cudaGetDeviceCount (&gpus) != cudaSuccess || gpus < 1) { cudaGetLastError (); gpus = 1; }
         const int n = omp_get_num_procs () / (2 * gpus);
         return n < 1 ? 1 : (n > 4 ? 4 : n);
     } ();
+    static const int whole_box = [] { const int n = omp_get_num_procs () / 2; return n < 1 ? 1 : (n > 8 ? 8 : n); } ();
+    const int threads = forced > 0 ? forced : (all_devices ? whole_box : per_device);
+    (void) threads;             /* (used by the pragma below only, which nvcc's front end does not read) */
     char *base = (char*) pixels;
     const size_t row = (size_t) w * 4;
-    #pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1) if (threads > 1)
+    /* (chunks of 16 rows dealt round: whole rows above and below the spans, parts of rows beside them) */
+    #pragma omp parallel for schedule(static, 16) num_threads(threads > 0 ? threads : 1) if (threads > 1)
     for (int y = 0; y < h; y++)
     {
         char *r = base + (size_t) y * pitch;
@@ -696,13 +701,13 @@ extern "C" int voxgpu_multi_render (voxgpu_multi *mu, const voxgpu_tree *const *
         {
             int vx0, vx1, vy0, vy1;
             const bool nothing = !visible_rect (trees[0], c, mu->w, mu->h, &vx0, &vx1, &vy0, &vy1);
-            if (nothing) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, NULL, NULL);
+            if (nothing) host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, NULL, NULL, true);
             else if (vx0 > 0 || vx1 < mu->w || vy0 > 0 || vy1 < mu->h)
             {
                 const int units = mu->h / 4;
                 int *lo = mu->span, *hi = lo + units;
                 for (int u=0; u<units; u++) { const bool in = u >= vy0 / 4 && u < vy1 / 4; lo[u] = in ? vx0 : 0; hi[u] = in ? vx1 : 0; }
-                host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, lo, hi);
+                host_clear_margin (host_pixels, host_pitch_bytes, mu->w, mu->h, lo, hi, true);
             }
         }
     }
