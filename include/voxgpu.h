@@ -272,6 +272,12 @@ VOXGPU_EXPORT unsigned long long voxgpu_present_bytes_copied (void);
     root box's rectangle only; default on, $VOXGPU_SPANS), the most copies one frame is cut into (default 16,
     $VOXGPU_COPY_STRIPS), and what one more copy must save in bytes to be worth it (default 98304, $VOXGPU_COPY_COST). */
 VOXGPU_EXPORT void voxgpu_set_present_spans (int on, int max_strips, long long copy_cost);
+/** What voxgpu_present_render would copy for a frame of a tree whose coarse cut is `boxes`, drawn in `nbands` bands
+    (host arithmetic only, for tests): per 4-row unit u the columns [keep_lo[u], keep_hi[u]) the copies write -- the
+    rest of the surface is zeroed on the host.  -> bytes copied; -1: the camera cannot see the boxes (everything is
+    zeroed); -2: bad argument. */
+VOXGPU_EXPORT long long voxgpu_present_plan (const float *boxes, unsigned n, const voxgpu_camera *c, int w, int h, int nbands,
+                                             int *keep_lo, int *keep_hi);
 VOXGPU_EXPORT int voxgpu_visible_spans (const float *boxes, unsigned n, const voxgpu_camera *c, int w, int h, int *lo, int *hi);
 /** The device framebuffer the last frame was rendered into (w*h pixels, pitch w). */
 VOXGPU_EXPORT const uint32_t* voxgpu_present_device_frame (const voxgpu_present *p);

@@ -300,6 +300,72 @@ static int strip_runs (int b0, int b1, int sub, const int *glo, const int *ghi, 
     return n;
 }
 
+/* The copies of one band: 1, 2, 4, ... (at most max_strips) strips of equal height, whichever costs least when
+   one more copy is worth copy_cost bytes.  -> number of runs in best[]. */
+static int band_copies (int b0, int b1, int max_strips, long long copy_cost, const int *glo, const int *ghi, int G,
+                        int vx0, int vx1, StripRun *best)
+{
+    StripRun runs[PRESENT_MAX_STRIPS];
+    int nbest = 0;
+    long long best_cost = 0;
+    for (int sub=1; sub<=max_strips && sub<=b1-b0 && sub<=PRESENT_MAX_STRIPS; sub*=2)
+    {
+        long long bytes = 0;
+        const int nr = strip_runs (b0, b1, sub, glo, ghi, G, vx0, vx1, runs, &bytes);
+        const long long cost = bytes + (long long) nr * copy_cost;
+        if (sub == 1 || cost < best_cost) { best_cost = cost; nbest = nr; memcpy (best, runs, sizeof (StripRun) * nr); }
+    }
+    return nbest;
+}
+
+/* What voxgpu_present_render would copy for a frame of a tree whose coarse cut is `boxes` (as for
+   voxgpu_visible_spans), cut into nbands bands -- host arithmetic only, for the tests: per 4-row unit u the kept
+   columns [keep_lo[u], keep_hi[u]) (everything else of the surface is zeroed on the host) -> bytes copied, or -1
+   if the camera cannot see the boxes at all (the whole surface is zeroed). */
+extern "C" long long voxgpu_present_plan (const float *boxes, unsigned n, const voxgpu_camera *c, int w, int h, int nbands,
+                                          int *keep_lo, int *keep_hi)
+{
+    if (!boxes || !n || !c || !keep_lo || !keep_hi || w <= 0 || h < 4 || (w & 15) || (h & 3) || nbands < 1) return -2;
+    float mn[3] = { boxes[0], boxes[n], boxes[2*(size_t)n] }, mx[3] = { boxes[3*(size_t)n], boxes[4*(size_t)n], boxes[5*(size_t)n] };
+    for (unsigned i=1; i<n; i++)
+        for (int a=0; a<3; a++)
+        {
+            if (boxes[(size_t) a * n + i] < mn[a]) mn[a] = boxes[(size_t) a * n + i];
+            if (boxes[(size_t) (3 + a) * n + i] > mx[a]) mx[a] = boxes[(size_t) (3 + a) * n + i];
+        }
+    int cull[4] = { 0, w, 0, h };
+    voxgpu_screen_bounds (mn, mx, c, w, h, cull);
+    const int units = h / 4, G = 16;
+    for (int u=0; u<units; u++) keep_lo[u] = keep_hi[u] = 0;
+    if (!(cull[1] > cull[0] && cull[3] > cull[2])) return -1;
+    int vx0 = cull[0] & ~15, vx1 = (cull[1] + 15) & ~15, vy0 = cull[2] & ~3, vy1 = (cull[3] + 3) & ~3;
+    if (vx1 > w) vx1 = w;
+    if (vy1 > h) vy1 = h;
+    const int v_units = (vy1 - vy0) / 4, v_u0 = vy0 / 4;
+    if (nbands > v_units) nbands = v_units > 0 ? v_units : 1;
+    if (nbands > PRESENT_MAX_BANDS) nbands = PRESENT_MAX_BANDS;
+    int *glo = (int*) malloc (sizeof (int) * 2 * (size_t) units), *ghi = glo + units;
+    const bool spans = g_span_cfg.on.load () && n > 1 && visible_spans_of (boxes, n, c, w, h, G, glo, ghi);
+    if (!spans) for (int q=0; q<(h+G-1)/G; q++) { glo[q] = vx0; ghi[q] = vx1; }
+    const int frame_strips = g_span_cfg.strips.load ();
+    const int band_strips = spans && frame_strips > nbands ? frame_strips / nbands : 1;
+    long long bytes = 0;
+    for (int i=0; i<nbands; i++)
+    {
+        const int b0 = v_u0 + (int) ((long long) v_units * i / nbands), b1 = v_u0 + (int) ((long long) v_units * (i + 1) / nbands);
+        if (b1 <= b0) continue;
+        StripRun best[PRESENT_MAX_STRIPS];
+        const int nb = band_copies (b0, b1, band_strips, g_span_cfg.cost.load (), glo, ghi, G, vx0, vx1, best);
+        for (int r=0; r<nb; r++)
+        {
+            bytes += (long long) (best[r].x1 - best[r].x0) * 16 * (best[r].u1 - best[r].u0);
+            for (int u=best[r].u0; u<best[r].u1; u++) { keep_lo[u] = best[r].x0; keep_hi[u] = best[r].x1; }
+        }
+    }
+    free (glo);
+    return bytes;
+}
+
 extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, const voxgpu_camera *c,
                                       const voxgpu_frame *f, const uint8_t *d_tex,
                                       void *host_pixels, size_t host_pitch_bytes)
@@ -455,16 +521,8 @@ extern "C" int voxgpu_present_render (voxgpu_present *p, const voxgpu_tree *t, c
                (1, 2, 4, ... of equal height) as pay for themselves -- a copy more costs what ~100 KB on the wire cost */
             e = cudaSuccess;
             const int b0 = y0 >> 2, b1 = y1 >> 2;
-            StripRun runs[PRESENT_MAX_STRIPS], best[PRESENT_MAX_STRIPS];
-            int nbest = 0;
-            long long best_cost = 0;
-            for (int sub=1; sub<=band_strips && sub<=b1-b0 && sub<=PRESENT_MAX_STRIPS; sub*=2)
-            {
-                long long bytes = 0;
-                const int nr = strip_runs (b0, b1, sub, ulo, uhi, G, vx0, vx1, runs, &bytes);
-                const long long cost = bytes + (long long) nr * copy_cost;
-                if (sub == 1 || cost < best_cost) { best_cost = cost; nbest = nr; memcpy (best, runs, sizeof (StripRun) * nr); }
-            }
+            StripRun best[PRESENT_MAX_STRIPS];
+            const int nbest = band_copies (b0, b1, band_strips, copy_cost, ulo, uhi, G, vx0, vx1, best);
             for (int r=0; r<nbest && e == cudaSuccess; r++)
             {
                 const int ry0 = best[r].u0 * 4, rows = (best[r].u1 - best[r].u0) * 4, rx0 = best[r].x0, rx1 = best[r].x1;
