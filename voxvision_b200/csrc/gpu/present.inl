@@ -300,10 +300,10 @@ static int strip_runs (int b0, int b1, int sub, const int *glo, const int *ghi, 
     return n;
 }
 
-/* The copies of one band: 1, 2, 4, ... (at most max_strips) strips of equal height, whichever costs least when
-   one more copy is worth copy_cost bytes.  -> number of runs in best[]. */
-static int band_copies (int b0, int b1, int max_strips, long long copy_cost, const int *glo, const int *ghi, int G,
-                        int vx0, int vx1, StripRun *best)
+/* The copies of one band, strips of equal height: 1, 2, 4, ... (at most max_strips) of them, whichever costs least
+   when one more copy is worth copy_cost bytes.  -> number of runs in best[]. */
+static int band_copies_equal (int b0, int b1, int max_strips, long long copy_cost, const int *glo, const int *ghi, int G,
+                              int vx0, int vx1, StripRun *best)
 {
     StripRun runs[PRESENT_MAX_STRIPS];
     int nbest = 0;
@@ -316,6 +316,75 @@ static int band_copies (int b0, int b1, int max_strips, long long copy_cost, con
         if (sub == 1 || cost < best_cost) { best_cost = cost; nbest = nr; memcpy (best, runs, sizeof (StripRun) * nr); }
     }
     return nbest;
+}
+
+/* The copies of one band (units [b0, b1)): the cut into strips along group boundaries that moves the fewest bytes
+   when every copy is worth copy_cost bytes more -- a shortest path over at most 64 cut points (f[j] = the cheapest
+   way to cover the units before cut j), ~2 000 steps.  On the C2 orbit 44.4 % of the frames' bytes against 46.6 %
+   for strips of equal height with the same ~3 copies per frame.  More than max_strips strips (a copy cost near
+   zero): the equal strips instead.  -> number of runs in best[]. */
+#define PRESENT_MAX_CUTS 64
+static int band_copies (int b0, int b1, int max_strips, long long copy_cost, const int *glo, const int *ghi, int G,
+                        int vx0, int vx1, StripRun *best)
+{
+    static const int dp = !(getenv ("VOXGPU_STRIP_DP") && !atoi (getenv ("VOXGPU_STRIP_DP")));     /* 0: equal strips (A/B) */
+    if (!dp) return band_copies_equal (b0, b1, max_strips, copy_cost, glo, ghi, G, vx0, vx1, best);
+    if (max_strips <= 1 || b1 - b0 < 2) return band_copies_equal (b0, b1, 1, copy_cost, glo, ghi, G, vx0, vx1, best);
+    const int gu = G / 4;                                   /* units per group */
+    const int q0 = b0 / gu, q1 = (b1 + gu - 1) / gu;        /* groups the band touches */
+    const int step = (q1 - q0 + PRESENT_MAX_CUTS - 1) / PRESENT_MAX_CUTS;
+    int cut[PRESENT_MAX_CUTS + 2], lo[PRESENT_MAX_CUTS + 1], hi[PRESENT_MAX_CUTS + 1], m = 0;
+    for (int q=q0; q<q1; q+=step)
+    {
+        /* segment m: the groups [q, q + step) inside the band */
+        const int qe = q + step < q1 ? q + step : q1;
+        cut[m] = q * gu > b0 ? q * gu : b0;
+        int a = vx1, b = vx0;
+        for (int r=q; r<qe; r++) { if (glo[r] < a) a = glo[r]; if (ghi[r] > b) b = ghi[r]; }
+        a &= ~15; b = (b + 15) & ~15;
+        lo[m] = a > vx0 ? a : vx0; hi[m] = b < vx1 ? b : vx1;
+        if (hi[m] <= lo[m]) { lo[m] = vx1; hi[m] = vx0; }   /* nothing: neutral for the min / max below */
+        m++;
+    }
+    cut[m] = b1;
+    long long f[PRESENT_MAX_CUTS + 1];
+    int from[PRESENT_MAX_CUTS + 1];
+    f[0] = 0; from[0] = 0;
+    for (int j=1; j<=m; j++)
+    {
+        long long bestc = -1;
+        int a = vx1, b = vx0, bi = j - 1;
+        for (int i=j-1; i>=0; i--)
+        {
+            if (lo[i] < a) a = lo[i];
+            if (hi[i] > b) b = hi[i];
+            const long long bytes = b > a ? (long long) (b - a) * 16 * (cut[j] - cut[i]) : 0;
+            const long long c = f[i] + bytes + (bytes ? copy_cost : 0);
+            if (bestc < 0 || c < bestc) { bestc = c; bi = i; }
+        }
+        f[j] = bestc; from[j] = bi;
+    }
+    /* walk back, then emit top to bottom with equal neighbours joined */
+    int ends[PRESENT_MAX_CUTS + 1], ne = 0;
+    for (int j=m; j>0; j=from[j]) ends[ne++] = j;
+    int n = 0, i = 0;
+    for (int e=ne-1; e>=0; e--)
+    {
+        const int j = ends[e];
+        int a = vx1, b = vx0;
+        for (int r=i; r<j; r++) { if (lo[r] < a) a = lo[r]; if (hi[r] > b) b = hi[r]; }
+        if (b > a)
+        {
+            if (n && best[n-1].u1 == cut[i] && best[n-1].x0 == a && best[n-1].x1 == b) best[n-1].u1 = cut[j];
+            else
+            {
+                if (n >= max_strips || n >= PRESENT_MAX_STRIPS) return band_copies_equal (b0, b1, max_strips, copy_cost, glo, ghi, G, vx0, vx1, best);
+                best[n].u0 = cut[i]; best[n].u1 = cut[j]; best[n].x0 = a; best[n].x1 = b; n++;
+            }
+        }
+        i = j;
+    }
+    return n;
 }
 
 /* What voxgpu_present_render would copy for a frame of a tree whose coarse cut is `boxes` (as for
